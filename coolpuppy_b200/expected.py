@@ -1,0 +1,65 @@
+"""Cis expected-by-distance tables (input preparation, not on the pile-up hot path).
+
+The reference consumes an *expected* DataFrame produced by
+``cooltools expected-cis`` (``CLI.py:484-508``; consumed at
+``coolpup.py:861-918``).  cooltools is not importable here, so this module
+computes a table with the same schema (``region1, region2, dist, n_valid,
+count.sum, count.avg[, balanced.sum, balanced.avg]``) for a view of cis
+regions, so that expected-normalised pile-ups can be configured without any
+external tool.
+
+Semantics (cooltools ``expected_cis`` with ``smooth=False``): for every view
+region and diagonal ``d``: ``n_valid`` = number of pixel positions on the
+diagonal whose two bins are both valid (non-NaN weight when balanced, all bins
+otherwise), ``*.sum`` = sum over those positions, ``*.avg = sum / n_valid``;
+the first ``ignore_diags`` diagonals are NaN.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+
+def expected_cis(clr, view_df=None, clr_weight_name=None, ignore_diags=2):
+    if view_df is None:
+        names = list(clr.chromnames)
+        view_df = pd.DataFrame(
+            {"chrom": names, "start": 0, "end": [int(clr.chromsizes[c]) for c in names], "name": names}
+        )
+    rows = []
+    for chrom, start, end, name in zip(view_df["chrom"], view_df["start"], view_df["end"], view_df["name"]):
+        lo, hi = clr.extent((chrom, start, end))
+        nb = hi - lo
+        b1, b2, cnt = clr._upper_pixels(lo, hi)
+        d = (b2 - b1).astype(np.int64)
+        dist = np.arange(nb)
+        tab = {"region1": name, "region2": name, "dist": dist}
+        if clr_weight_name:
+            w = np.asarray(clr._bin_column(clr_weight_name), dtype=np.float64)[lo:hi]
+            ok = ~np.isnan(w)
+            # number of valid positions on diagonal d = sum_i ok[i] & ok[i+d]
+            okf = ok.astype(np.float64)
+            nfft = 1 << int(np.ceil(np.log2(max(2 * nb, 2))))
+            f = np.fft.rfft(okf, nfft)
+            n_valid = np.rint(np.fft.irfft(f * np.conj(f), nfft)[:nb]).astype(np.int64)
+            val = w[b1 - lo] * w[b2 - lo] * cnt
+            good = ~np.isnan(val)
+            bal_sum = np.bincount(d[good], weights=val[good], minlength=nb)[:nb]
+            cnt_sum = np.bincount(d[good], weights=cnt[good].astype(np.float64), minlength=nb)[:nb]
+        else:
+            n_valid = (nb - dist).astype(np.int64)
+            cnt_sum = np.bincount(d, weights=cnt.astype(np.float64), minlength=nb)[:nb]
+            bal_sum = None
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tab["n_valid"] = n_valid
+            cs = cnt_sum.copy()
+            cs[:ignore_diags] = np.nan
+            tab["count.sum"] = cs
+            tab["count.avg"] = cs / n_valid
+            if bal_sum is not None:
+                bs = bal_sum.copy()
+                bs[:ignore_diags] = np.nan
+                tab["balanced.sum"] = bs
+                tab["balanced.avg"] = bs / n_valid
+        rows.append(pd.DataFrame(tab))
+    return pd.concat(rows, ignore_index=True)

@@ -1,0 +1,590 @@
+"""CPU ORACLE for the pile-up hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+This is a plain numpy/scipy restatement of the reference algorithm
+(open2c/coolpuppy 1.1.0 @592673c), written from the reference's behaviour and
+citing the lines it follows.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
+product package ``coolpuppy_b200`` never does.
+
+Parity pinning: the unmodified reference itself runs in the build container
+through ``oracle/refshim`` (stand-ins for its absent third-party imports) and
+``tests/golden/make_golden.py`` stores its outputs -- final pile-ups, the
+per-region window streams (incl. ``np.random`` control-shift order) and the
+per-region accumulators -- under ``tests/golden/``.  ``tests/test_oracle.py``
+checks this restatement against every one of those vectors, against the
+reference-asserted known answers (``tests/test_coolpup.py:50-72, 97, 124-142,
+167-172``) and statistically against the legacy ``loop_ref.np.txt``.  What
+remains unpinned by the reference's *own* tests: the third-party pieces
+(cooler's balanced fetch, cooltools' LazyToeplitz / ExpectedSnipper), which are
+restated from their documentation in ``oracle/refshim`` and
+``coolpuppy_b200/coolio.py``.
+
+Scope: cis pile-ups (bed all-pairs, bed local, bedpe), random-shift controls,
+expected (ooe and not), balancing weights, coverage normalisation, grouping by
+strand / distance / arbitrary columns / window, flips, stripes.  Not restated:
+``trans`` and ``rescale`` (out of scope).
+"""
+from __future__ import annotations
+
+import re
+from functools import reduce
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+__all__ = ["oracle_pileup", "OracleResult", "key_repr"]
+
+
+# --------------------------------------------------------------------------- helpers
+def natsorted(seq):
+    """natsort.natsorted for chromosome names (coolpup.py:350-355, 927)."""
+    tok = re.compile(r"(\d+)")
+
+    def key(s):
+        return tuple((0, int(p)) if p.isdigit() else (1, p) for p in tok.split(str(s)) if p != "")
+
+    return sorted(seq, key=key)
+
+
+def key_repr(g):
+    """Stable text form of a group key (same convention as tests/golden/make_golden.py)."""
+    if isinstance(g, str):
+        return g
+    return repr(tuple(x.item() if isinstance(x, np.generic) else x for x in g))
+
+
+def default_band_edges():
+    """coolpup.py:46-47."""
+    return np.append([0], 50000 * 2 ** np.arange(30))
+
+
+# --------------------------------------------------------------------------- a1: windows
+def expand_windows(center, flank, resolution):
+    """[exp_start, exp_end) of a feature centre (coolpup.py:78-86, 94-107).
+
+    ``exp_start = floor(center / res) * res - flank``,
+    ``exp_end   = floor(center / res + 1) * res + flank``.
+    """
+    center = np.asarray(center, dtype=float)
+    exp_start = np.floor(center / resolution) * resolution - flank
+    exp_end = np.floor(center / resolution + 1) * resolution + flank
+    return exp_start, exp_end
+
+
+def to_bins(exp_start, exp_end, resolution):
+    """stBin = floor(exp_start/res), endBin = ceil(exp_end/res) (coolpup.py:492-497, 503-514)."""
+    return (
+        np.floor(np.asarray(exp_start) / resolution).astype(int),
+        np.ceil(np.asarray(exp_end) / resolution).astype(int),
+    )
+
+
+class Coords:
+    """Restatement of ``CoordCreator.process`` (coolpup.py:259-385)."""
+
+    def __init__(self, features, resolution, *, features_format="auto", flank=100000, chroms="all",
+                 minshift=10**5, maxshift=10**6, nshifts=10, mindist="auto", maxdist=None, local=False,
+                 subset=0, seed=None):
+        df = features.copy()
+        self.resolution = resolution
+        self.flank = flank
+        self.minshift, self.maxshift, self.nshifts = minshift, maxshift, nshifts
+        self.mindist = 2 * flank + 2 * resolution if mindist == "auto" else mindist  # 240-243
+        self.maxdist = np.inf if maxdist is None else maxdist  # 247-250
+        self.local = local
+        if features_format in (None, "auto"):  # 260-277
+            if all(c in df.columns for c in ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]):
+                self.kind = "bedpe"
+            elif all(c in df.columns for c in ["chrom", "start", "end"]):
+                self.kind = "bed"
+            else:
+                raise ValueError("cannot determine feature kind")
+        else:
+            self.kind = features_format
+        if subset > 0:  # 281-282, 455-461
+            if seed is not None:
+                np.random.seed(seed)
+            if subset < len(df):
+                df = df.sample(subset)
+        if self.kind == "bed":  # 284-294
+            df["chrom"] = df["chrom"].astype(str)
+            df["center"] = (df["start"] + df["end"]) / 2
+            df["exp_start"], df["exp_end"] = expand_windows(df["center"], flank, resolution)
+        else:  # 295-321
+            df[["chrom1", "chrom2"]] = df[["chrom1", "chrom2"]].astype(str)
+            df["center1"] = (df["start1"] + df["end1"]) / 2
+            df["center2"] = (df["start2"] + df["end2"]) / 2
+            df["distance"] = df["center2"] - df["center1"]
+            df = df[(self.mindist <= df["distance"].abs()) & (df["distance"].abs() <= self.maxdist)]
+            df = df.reset_index(drop=True)
+            df["exp_start1"], df["exp_end1"] = expand_windows(df["center1"], flank, resolution)
+            df["exp_start2"], df["exp_end2"] = expand_windows(df["center2"], flank, resolution)
+        self.empty = df.shape[0] == 0  # 323-331
+        if self.empty:
+            self.final_chroms = []
+            self.intervals = df
+            return
+        if self.kind == "bed":  # 336-356
+            base = set(df["chrom"])
+        else:
+            if local:
+                raise ValueError("Can't make local with both sides of loops defined")
+            base = set(df["chrom1"]).intersection(set(df["chrom2"]))
+        self.final_chroms = natsorted(base) if chroms == "all" else natsorted(set(chroms) & base)
+        if not self.final_chroms:
+            raise ValueError("No chromosomes are in common between the coordinate file and the cooler file")
+        if self.kind == "bed":  # 489-500
+            df = df.sort_values(["chrom", "start"])
+            df["stBin"], df["endBin"] = to_bins(df["exp_start"], df["exp_end"], resolution)
+        else:  # 501-520
+            df = df.sort_values(["chrom1", "chrom2", "start1", "start2"])
+            df["stBin1"], df["endBin1"] = to_bins(df["exp_start1"], df["exp_end1"], resolution)
+            df["stBin2"], df["endBin2"] = to_bins(df["exp_start2"], df["exp_end2"], resolution)
+        self.intervals = df
+
+    # ------------------------------------------------------------------ a2: control shifts
+    def control_shifts(self, frame, nshifts):
+        """Random-shift controls appended after the ROI rows (coolpup.py:387-453).
+
+        ``frame`` rows are replicated ``nshifts`` times block-wise; one
+        ``np.random.randint(minshift, maxshift)`` and one
+        ``np.random.choice([-1, 1])`` per replicated row (drawn as two vectors,
+        in that order); the same signed shift moves both sides by
+        ``np.round(shift / res)`` bins (half-to-even).
+        """
+        frame = frame.copy()
+        frame["kind"] = "ROI"
+        if nshifts <= 0:
+            return frame
+        ctrl = pd.concat([frame] * nshifts).reset_index(drop=True)
+        shift = np.random.randint(self.minshift, self.maxshift, ctrl.shape[0])
+        sign = np.random.choice([-1, 1], ctrl.shape[0])
+        shift = shift * sign
+        dbin = np.round(shift / self.resolution).astype(int)
+        for c in ("stBin1", "endBin1", "stBin2", "endBin2"):
+            ctrl[c] = ctrl[c].values + dbin
+        for c in ("center1", "center2"):
+            ctrl[c] = ctrl[c].values + shift
+        ctrl["kind"] = "control"
+        return pd.concat([frame, ctrl]).reset_index(drop=True)
+
+    # ------------------------------------------------------------------ a2: per-region streams
+    def region_frames(self, region, control, modify=None):
+        """Frames of 2-D intervals of one view region, in the reference's emission order.
+
+        bedpe: ``get_intervals_stream`` (coolpup.py:716-746) with the region
+        filter of 554-563.  bed: ``get_combinations`` (598-714) with the filter
+        of 546-552 -- ``local`` pairs every feature with itself (620-627), else
+        all ordered pairs by offset ``i`` then position ``k`` (682-699) with
+        controls drawn once per offset.
+        """
+        chrom, start, end = region
+        df = self.intervals
+        if self.kind == "bedpe":
+            sel = df[(df["chrom1"] == chrom) & (df["chrom2"] == chrom) & (df["start1"] >= start) & (df["end1"] < end)
+                     & (df["start2"] >= start) & (df["end2"] < end)].reset_index(drop=True)
+            fr = self.control_shifts(sel, self.nshifts * control)
+            if modify is not None:
+                fr = modify(fr)
+            if len(fr):
+                yield fr
+            return
+        sel = df[(df["chrom"] == chrom) & (df["start"] >= start) & (df["end"] < end)].reset_index(drop=True)
+        left = sel.rename(columns=lambda c: c + "1")
+        right = sel.rename(columns=lambda c: c + "2")
+        if self.local:
+            merged = pd.concat([left, right], axis=1)
+            fr = self.control_shifts(merged, self.nshifts * control)
+            if modify is not None:
+                fr = modify(fr)
+            if len(fr):
+                yield fr
+            return
+        m = len(sel)
+        for i in range(1, m):  # offsets >= m give empty frames in the reference (682-689)
+            comb = pd.concat([left.iloc[:-i].reset_index(drop=True), right.iloc[i:].reset_index(drop=True)], axis=1)
+            comb["distance"] = comb["center2"] - comb["center1"]
+            comb = comb[(self.mindist <= comb["distance"].abs()) & (comb["distance"].abs() <= self.maxdist)]
+            fr = self.control_shifts(comb, self.nshifts * control)
+            if modify is not None:
+                fr = modify(fr)
+            if len(fr):
+                yield fr
+
+
+def band_annotator(edges):
+    """``bin_distance_intervals`` (coolpup.py:28-51)."""
+    edges = default_band_edges() if isinstance(edges, str) and edges == "default" else np.asarray(edges)
+
+    def annotate(fr):
+        ids = np.searchsorted(edges, fr["distance"], side="right")
+        fr = fr.copy()
+        fr["distance_band"] = [tuple(edges[i - 1 : i + 1]) for i in ids]
+        return fr
+
+    return annotate
+
+
+# --------------------------------------------------------------------------- a6/a7: accumulate
+def add_snip(store, key, snip):
+    """``_add_snip`` (lib/puputils.py:12-38): first snippet kept verbatim, later ones nansum'ed."""
+    if key not in store:
+        store[key] = {
+            "data": snip["data"],
+            "cov_start": snip["cov_start"],
+            "cov_end": snip["cov_end"],
+            "num": np.isfinite(snip["data"]).astype(int),
+            "n": 1,
+            "coordinates": [snip["coordinates"]],
+            "horizontal_stripe": [snip["horizontal_stripe"]],
+            "vertical_stripe": [snip["vertical_stripe"]],
+        }
+    else:
+        p = store[key]
+        p["data"] = np.nansum([p["data"], snip["data"]], axis=0)
+        p["num"] = p["num"] + np.isfinite(snip["data"]).astype(int)
+        p["cov_start"] = np.nansum([p["cov_start"], snip["cov_start"]], axis=0)
+        p["cov_end"] = np.nansum([p["cov_end"], snip["cov_end"]], axis=0)
+        p["n"] += 1
+        for f in ("coordinates", "horizontal_stripe", "vertical_stripe"):
+            p[f] = p[f] + [snip[f]]
+
+
+def sum_pups(p1, p2):
+    """``sum_pups`` (lib/puputils.py:88-113): NaN -> 0 and +inf -> 1.797e308 on both inputs, then add."""
+    d1 = np.nan_to_num(p1["data"])
+    d2 = np.nan_to_num(p2["data"])
+    return {
+        "data": d1 + d2,
+        "cov_start": p1["cov_start"] + p2["cov_start"],
+        "cov_end": p1["cov_end"] + p2["cov_end"],
+        "n": p1["n"] + p2["n"],
+        "num": p1["num"] + p2["num"],
+        "horizontal_stripe": p1["horizontal_stripe"] + p2["horizontal_stripe"],
+        "vertical_stripe": p1["vertical_stripe"] + p2["vertical_stripe"],
+        "coordinates": p1["coordinates"] + p2["coordinates"],
+    }
+
+
+def norm_coverage(pup):
+    """``norm_coverage`` (lib/puputils.py:168-190)."""
+    cov = np.outer(pup["cov_start"], pup["cov_end"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cov = cov / np.nanmean(cov)
+        data = pup["data"] / cov
+    data[np.isnan(data)] = 0
+    out = dict(pup)
+    out["data"] = data
+    return out
+
+
+class OracleResult:
+    def __init__(self, rows, regions, windows, params):
+        self.rows = rows  # list of dicts in the reference's final row order
+        self.regions = regions  # region -> {(kind, key_repr): pup}
+        self.windows = windows  # region -> dict of arrays (st1, st2, kind, flip, group key reprs)
+        self.params = params
+
+    def by_key(self):
+        return {key_repr(r["group"]): r for r in self.rows}
+
+
+# --------------------------------------------------------------------------- the path
+def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_df=None,
+                  expected_value_col="balanced.avg", clr_weight_name="weight", flank=100000, minshift=10**5,
+                  maxshift=10**6, nshifts=0, ooe=True, mindist="auto", maxdist=None, min_diag=2, subset=0,
+                  by_window=False, by_strand=False, by_distance=False, groupby=[], ignore_group_order=False,
+                  flip_negative_strand=False, local=False, coverage_norm=False, store_stripes=False, seed=None,
+                  max_windows_per_region=None):
+    """Restatement of ``pileup()`` -> ``PileUpper.pileupsWith*Control`` (coolpup.py:1922-2279, 1360-1919).
+
+    ``max_windows_per_region`` is NOT a reference feature: it truncates every
+    region's ROI+control stream after that many windows so that ``bench.py``
+    can time a bounded sample of a large workload on the CPU.
+    """
+    # ---- pileup(): argument normalisation (2088-2138)
+    distance_edges = None
+    if by_distance is not False:
+        if local:
+            raise ValueError("Can't do local pileups by distance")
+        if isinstance(by_distance, np.ndarray):
+            distance_edges = [int(i) for i in by_distance]
+        elif by_distance is True or (isinstance(by_distance, str) and by_distance == "default"):
+            distance_edges = "default"
+        else:
+            raise ValueError("Invalid by_distance value")
+        by_distance = True
+    if seed is not None:
+        np.random.seed(seed)
+    resolution = clr.binsize
+    if view_df is None:
+        names = list(clr.chromnames)
+        view = pd.DataFrame({"chrom": names, "start": 0, "end": [int(clr.chromsizes[c]) for c in names], "name": names})
+    else:
+        view = view_df.copy()
+        if "name" not in view.columns:
+            view["name"] = view["chrom"]
+    control = nshifts > 0
+    chroms = list(view["chrom"].unique())
+    if by_window and (features_format != "bed" or local):
+        raise ValueError("by-window needs bed features and non-local pile-ups")
+
+    cc = Coords(features, resolution, features_format=features_format, flank=flank, chroms=chroms, minshift=minshift,
+                maxshift=maxshift, nshifts=nshifts, mindist=mindist, maxdist=maxdist, local=local, subset=subset,
+                seed=seed)
+
+    # ---- PileUpper.__init__ (837-997)
+    pad = flank // resolution
+    W = 2 * pad + 1
+    expected = expected_df is not None and expected_df is not False
+    E = {}
+    if expected:
+        ex = expected_df[expected_df["region1"].isin(view["name"]) & expected_df["region2"].isin(view["name"])]
+        ex = ex[ex["region1"] == ex["region2"]].reset_index(drop=True)
+        if control:  # 867-872
+            control = False
+        for name in view["name"]:  # ExpectedSnipper.select: table row order (907-916)
+            E[name] = ex.loc[(ex["region1"] == name) & (ex["region2"] == name), expected_value_col].values.astype(float)
+    extents = {}
+    for _, r in view.iterrows():  # 922-925
+        lo, hi = clr.extent((r["chrom"], r["start"], r["end"]))
+        off = clr.offset(r["chrom"])
+        extents[r["name"]] = (lo - off, hi - off)
+    use_chroms = natsorted(set(cc.final_chroms) & set(clr.chromnames))  # 927-930
+    view = view[view["chrom"].isin(use_chroms)].set_index("name")
+    if coverage_norm is True:  # 944-949
+        coverage_norm = "cov_tot_raw"
+    elif coverage_norm == "cis":
+        coverage_norm = "cov_cis_raw"
+    elif coverage_norm == "total":
+        coverage_norm = "cov_tot_raw"
+    if coverage_norm and clr_weight_name:
+        raise ValueError("Can't do coverage normalization when clr_weight_name is provided")
+
+    # ---- wrappers (1656-1919)
+    groupby = list(groupby)
+    modify = None
+    dup_by_region = False
+    if by_window:
+        dup_by_region = True
+        groupby = []
+    elif by_strand and by_distance:
+        groupby = ["strand1", "strand2", "distance_band"] + groupby
+    elif by_strand:
+        groupby = ["strand1", "strand2"] + groupby
+    elif by_distance:
+        groupby = ["distance_band"] + groupby
+    if by_distance:
+        edges = distance_edges
+        if not (isinstance(edges, str) and edges == "default"):  # 1789-1797
+            edges = list(np.sort(edges))
+            for _ in range(len(edges)):
+                if np.min(edges) < cc.mindist:
+                    edges[int(np.argmin(edges))] = cc.mindist
+                else:
+                    break
+        modify = band_annotator(edges)
+
+    # ---- flip wiring (1431-1493)
+    flipby = None
+    do_flip = False
+    if flip_negative_strand:
+        flipby = "strand"
+        do_flip = True
+    elif ignore_group_order and groupby:
+        g = np.array(groupby)
+        filt = [f"{x}1" in g and f"{x}2" in g for x in [y[:-1] for y in g]]
+        gf = np.sort(g[filt])
+        if ignore_group_order is True:
+            fb = list(set(x[:-1] for x in gf))
+        elif isinstance(ignore_group_order, str):
+            fb = [ignore_group_order]
+        elif len(ignore_group_order) == 1:
+            fb = list(ignore_group_order)
+        else:
+            fb = list(set(x[:-1] for x in ignore_group_order))
+        if len(fb) == 1 and f"{fb[0]}1" in gf:
+            flipby = fb[0]
+        else:
+            raise ValueError("Ambiguous ignore_group_order")
+        do_flip = True
+
+    def modify_final(fr):  # flip_mark_intervals_func (118-125)
+        if do_flip:
+            fr = fr.copy()
+            if flip_negative_strand:
+                fr["flip"] = np.where(fr["strand1"] == "-", True, False)
+            else:
+                fr["flip"] = fr[f"{flipby}1"] > fr[f"{flipby}2"]
+        if modify is not None:
+            fr = modify(fr)
+        return fr
+
+    # ---- per region (1285-1358)
+    if cc.empty or len(view) == 0:
+        return OracleResult([], {}, {}, {"W": W})
+    region_out = {}
+    window_log = {}
+    for rname, r in view.iterrows():
+        region_out[rname], window_log[rname] = _pileup_region(
+            clr, cc, rname, (r["chrom"], r["start"], r["end"]), extents[rname], control, modify_final, groupby,
+            do_flip, ignore_group_order, dup_by_region, E.get(rname) if expected else None, ooe, clr_weight_name,
+            coverage_norm, min_diag, W, store_stripes, max_windows_per_region)
+
+    # ---- reduce over regions, keys in order of first appearance (1511-1531)
+    def reduce_kind(kind):
+        order = []
+        for rname in region_out:
+            for k in region_out[rname][kind]:
+                if k not in order:
+                    order.append(k)
+        return {k: reduce(sum_pups, [region_out[rn][kind][k] for rn in region_out if k in region_out[rn][kind]])
+                for k in order}
+
+    roi = reduce_kind("ROI")
+    has_ctrl = control or (expected and not ooe)
+    ctrl = reduce_kind("control") if has_ctrl else None
+    # ---- final normalisation (1533-1607)
+    if coverage_norm:
+        roi = {k: norm_coverage(v) for k, v in roi.items()}
+        if control:
+            ctrl = {k: norm_coverage(v) for k, v in ctrl.items()}
+    rows = []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for k, p in roi.items():
+            data = p["data"] / p["num"]
+            row = {"group": k, "n": p["n"], "num": p["num"]}
+            if has_ctrl:
+                if k in ctrl:
+                    c = ctrl[k]
+                    data = data / (c["data"] / c["num"])
+                    row["control_n"], row["control_num"] = c["n"], c["num"]
+                else:  # pandas index alignment gives NaN (1546-1548)
+                    data = data * np.nan
+                    row["control_n"], row["control_num"] = np.nan, np.nan
+            data = np.where(data == np.inf, np.nan, data)
+            if store_stripes:
+                row["coordinates"] = [x.split(".") for x in p["coordinates"]]
+                hs, vs = p["horizontal_stripe"], p["vertical_stripe"]
+                if has_ctrl:
+                    call = ctrl["all"]
+                    cn = call["data"] / call["num"]
+                    cntr = int(np.floor(cn.shape[0] / 2))
+                    hs = [np.divide(x, cn[cntr, :]) for x in hs]
+                    vs = [np.divide(x, cn[:, cntr][::-1]) for x in vs]
+                row["horizontal_stripe"] = np.vstack(hs)
+                row["vertical_stripe"] = np.vstack(vs)
+            if local:
+                import warnings
+
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", category=RuntimeWarning)
+                    data = np.nanmean(np.dstack((data, data.T)), 2)
+            row["data"] = data
+            rows.append(row)
+    if by_distance:  # 1805-1807, 1890-1892
+        rows = [r for r in rows if not (isinstance(r["group"], tuple) and () in r["group"])]
+    return OracleResult(rows, {rn: {(kd, key_repr(k)): p for kd in v for k, p in v[kd].items()} for rn, v in region_out.items()},
+                        window_log, {"W": W, "groupby": groupby})
+
+
+def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_flip, ignore_group_order,
+                   dup_by_region, E, ooe, weight_name, coverage_norm, ignore_diags, W, store_stripes, max_windows):
+    """``pileup_region`` = ``pos_stream`` -> ``_stream_snips`` -> ``accumulate_stream`` (coolpup.py:1285-1358)."""
+    lo_rel, hi_rel = extent
+    nb = hi_rel - lo_rel
+    out = {"ROI": {}, "control": {}}
+    log = {"st1": [], "st2": [], "kind": [], "flip": [], "group": []}
+    bigdata = None
+    empty = np.zeros((W, W))
+    n_seen = 0
+    stop = False
+    for fr in cc.region_frames(region, control, modify):
+        cols = {c: fr[c].tolist() for c in fr.columns}  # to_dict(records) gives native python scalars
+        nrow = len(fr)
+        for i in range(nrow):
+            if max_windows is not None and n_seen >= max_windows:
+                stop = True
+                break
+            n_seen += 1
+            rec = {c: cols[c][i] for c in cols}
+            group = tuple(rec[c] for c in groupby) if groupby else "all"  # assign_groups (54-75)
+            flip = bool(rec.get("flip", False)) if do_flip else False
+            log["st1"].append(rec["stBin1"])
+            log["st2"].append(rec["stBin2"])
+            log["kind"].append(0 if rec["kind"] == "ROI" else 1)
+            log["flip"].append(int(flip))
+            log["group"].append(key_repr(group))
+            if bigdata is None:  # get_data (1024-1057) + NaN-weight masks (1081-1098)
+                chrom, start, end = region
+                bigdata = clr.matrix(sparse=True, balance=weight_name).fetch((chrom, start, end)).tocsr()
+                if weight_name:
+                    isnan = np.isnan(clr.bins()[weight_name].fetch((chrom, start, end)).values)
+                else:
+                    isnan = np.zeros(nb, dtype=bool)
+                cov = clr.bins()[coverage_norm].fetch((chrom, start, end)).values if coverage_norm else None
+            # region-relative bins and bounds test (1105-1114)
+            s1, e1 = rec["stBin1"] - lo_rel, rec["endBin1"] - lo_rel
+            s2, e2 = rec["stBin2"] - lo_rel, rec["endBin2"] - lo_rel
+            if s1 < 0 or e1 > nb or s2 < 0 or e2 > nb:
+                continue
+            data = bigdata[s1:e1, s2:e2].toarray().astype(float)  # 1115-1121
+            data[isnan[s1:e1], :] = np.nan  # 1122-1123
+            data[:, isnan[s2:e2]] = np.nan
+            ii = np.arange(s1, e1)[:, None]
+            jj = np.arange(s2, e2)[None, :]
+            exp_data = None
+            if E is not None:  # expected_selections[region][s1:e1, s2:e2] = E[|i-j|] (1130-1133)
+                exp_data = E[np.abs(jj - ii)]
+            data[(jj - ii) < ignore_diags] = np.nan  # signed diagonal mask (1141-1149)
+            snip = {"kind": rec["kind"], "group": group, "coordinates": [], "horizontal_stripe": [],
+                    "vertical_stripe": [], "cov_start": np.zeros(W), "cov_end": np.zeros(W)}
+            if coverage_norm:  # 1151-1153
+                snip["cov_start"] = cov[s1:e1]
+                snip["cov_end"] = cov[s2:e2]
+            if E is not None and ooe:  # 1154-1156
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    data = data / exp_data
+            snip["data"] = data
+            if store_stripes:  # 1164-1182
+                cntr = int(np.floor(data.shape[0] / 2))
+                snip["horizontal_stripe"] = np.array(data[cntr, :], dtype=float)
+                snip["vertical_stripe"] = np.array(data[:, cntr][::-1], dtype=float)
+                snip["coordinates"] = ".".join(str(rec[c]) for c in ("chrom1", "start1", "end1", "chrom2", "start2", "end2"))
+            emitted = [snip]
+            if E is not None and not ooe:  # bare expected block as a control snippet (1135-1139, 1190-1191)
+                es = dict(snip)
+                es["kind"] = "control"
+                es["data"] = exp_data
+                es["coordinates"] = []
+                emitted.append(es)
+            for s in emitted:
+                if do_flip and flip:  # flip_snip_func (128-147): anti-transpose, optional group swap
+                    s["data"] = np.rot90(np.flipud(s["data"]))
+                    if ignore_group_order:
+                        sw = dict(rec)
+                        for c in list(rec):
+                            if c.endswith("1") and c[:-1] + "2" in rec:
+                                sw[c], sw[c[:-1] + "2"] = rec[c[:-1] + "2"], rec[c]
+                        if groupby:
+                            s["group"] = tuple(sw[c] for c in groupby)
+                if dup_by_region:  # group_by_region (lib/puputils.py:218-223)
+                    targets = [(rec["chrom1"], rec["start1"], rec["end1"]), (rec["chrom2"], rec["start2"], rec["end2"])]
+                else:
+                    targets = [s["group"]]
+                for g in targets:
+                    add_snip(out[s["kind"]], g if isinstance(g, str) else tuple(g), s)
+        if stop:
+            break
+    # "all" (1272-1282)
+    empty_pup = {"data": empty, "horizontal_stripe": [], "vertical_stripe": [], "n": 0, "num": empty,
+                 "cov_start": np.zeros(W), "cov_end": np.zeros(W), "coordinates": []}
+    if "all" not in out["ROI"]:
+        out["ROI"]["all"] = reduce(sum_pups, out["ROI"].values(), empty_pup)
+    if control or (E is not None and not ooe):
+        if "all" not in out["control"]:
+            out["control"]["all"] = reduce(sum_pups, out["control"].values(), empty_pup)
+    for k in ("st1", "st2", "kind", "flip"):
+        log[k] = np.asarray(log[k], dtype=np.int64)
+    return out, log
