@@ -1,0 +1,219 @@
+"""Vectorised window-coordinate generation (host side of the hot path).
+
+Replaces the reference's per-row generator ``CoordCreator.pos_stream`` ->
+``to_dict(orient="records")`` (``coolpup.py:598-746``) with numpy array
+construction: one :class:`RegionWindows` per view region holding the first
+row / first column bin, kind (ROI / control), flip flag and integer group
+codes of every window, in the reference's emission order.  The random control
+shifts are drawn with the same ``np.random`` calls, sizes and order as the
+reference (``coolpup.py:387-453``: ``randint`` then ``choice``, once per region
+for bedpe / local, once per pair offset for bed pairs), so a seeded run sees
+identical windows.
+"""
+from __future__ import annotations
+
+import re
+
+import numpy as np
+import pandas as pd
+
+_tok = re.compile(r"(\d+)")
+
+
+def natsorted(seq):
+    """Natural sort of chromosome names (the reference uses ``natsort.natsorted``, coolpup.py:350-355, 927)."""
+
+    def key(s):
+        return tuple((0, int(p)) if p.isdigit() else (1, p) for p in _tok.split(str(s)) if p != "")
+
+    return sorted(seq, key=key)
+
+
+def default_band_edges():
+    return np.append([0], 50000 * 2 ** np.arange(30))
+
+
+class RegionWindows:
+    """Windows of one view region, in emission order.
+
+    ``st1``/``st2``: chromosome-relative first bins (int64); ``kind``: 0 ROI,
+    1 control; ``idx1``/``idx2``: rows of ``sel`` (the region's feature table)
+    on side 1 / side 2; ``distance``: centre2 - centre1 in bp (None for local).
+    """
+
+    __slots__ = ("region", "sel", "st1", "st2", "kind", "idx1", "idx2", "distance", "paired", "frame")
+
+    def __init__(self, region, sel, st1, st2, kind, idx1, idx2, distance, paired):
+        self.region = region
+        self.sel = sel
+        self.st1 = st1
+        self.st2 = st2
+        self.kind = kind
+        self.idx1 = idx1
+        self.idx2 = idx2
+        self.distance = distance
+        self.paired = paired  # True: bed features paired up (columns get suffix 1/2); False: bedpe rows
+        self.frame = None  # full DataFrame, only materialised for user callbacks
+
+    def __len__(self):
+        return int(self.st1.shape[0])
+
+    def column(self, name, swap=None):
+        """Values of 2-D interval column ``name`` for every window.
+
+        ``swap`` (bool array) exchanges side 1 and side 2 for the flagged
+        windows -- the group swap of ``flip_snip_func`` (coolpup.py:131-144).
+        """
+        if self.frame is not None:
+            vals = self.frame[name].to_numpy()
+            if swap is not None and swap.any() and name[-1] in "12":
+                other = name[:-1] + ("2" if name[-1] == "1" else "1")
+                if other in self.frame.columns:
+                    vals = np.where(swap, self.frame[other].to_numpy(), vals)
+            return vals
+        if name == "distance":
+            return self.distance
+        if self.paired:
+            if name[-1] not in "12" or name[:-1] not in self.sel.columns:
+                raise KeyError(f"no 2-D interval column {name!r}")
+            base = self.sel[name[:-1]].to_numpy()
+            a, b = (self.idx1, self.idx2) if name[-1] == "1" else (self.idx2, self.idx1)
+            if swap is not None and swap.any():
+                return base[np.where(swap, b, a)]
+            return base[a]
+        if name not in self.sel.columns:
+            raise KeyError(f"no 2-D interval column {name!r}")
+        vals = self.sel[name].to_numpy()[self.idx1]
+        if swap is not None and swap.any() and name[-1] in "12":
+            other = name[:-1] + ("2" if name[-1] == "1" else "1")
+            if other in self.sel.columns:
+                vals = np.where(swap, self.sel[other].to_numpy()[self.idx1], vals)
+        return vals
+
+    def has_column(self, name):
+        if self.frame is not None:
+            return name in self.frame.columns
+        if name == "distance":
+            return self.distance is not None
+        if self.paired:
+            return name[-1] in "12" and name[:-1] in self.sel.columns
+        return name in self.sel.columns
+
+    def to_frame(self):
+        """The reference's 2-D interval DataFrame for this region (all columns) -- slow path for callbacks."""
+        if self.frame is not None:
+            return self.frame
+        if self.paired:
+            left = self.sel.iloc[self.idx1].reset_index(drop=True).rename(columns=lambda c: c + "1")
+            right = self.sel.iloc[self.idx2].reset_index(drop=True).rename(columns=lambda c: c + "2")
+            fr = pd.concat([left, right], axis=1)
+            if self.distance is not None:
+                fr["distance"] = self.distance
+        else:
+            fr = self.sel.iloc[self.idx1].reset_index(drop=True)
+        w = fr["endBin1"].values - fr["stBin1"].values
+        fr["stBin1"] = self.st1
+        fr["endBin1"] = self.st1 + w
+        w2 = fr["endBin2"].values - fr["stBin2"].values
+        fr["stBin2"] = self.st2
+        fr["endBin2"] = self.st2 + w2
+        fr["kind"] = np.where(self.kind == 0, "ROI", "control")
+        return fr
+
+
+def _draw_shifts(n, minshift, maxshift, resolution):
+    """One control-shift draw of the reference (coolpup.py:392-396, 442-445): bins to add to all four bin columns."""
+    shift = np.random.randint(minshift, maxshift, n)
+    sign = np.random.choice([-1, 1], n)
+    shift = shift * sign
+    return np.round(shift / resolution).astype(np.int64)
+
+
+def pair_offsets(m):
+    """All ordered pairs (k, k+i), ordered by offset i then k (coolpup.py:682-689)."""
+    if m < 2:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z
+    counts = np.arange(m - 1, 0, -1, dtype=np.int64)  # offset i = 1..m-1 has m-i pairs
+    i_arr = np.repeat(np.arange(1, m, dtype=np.int64), counts)
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    k_arr = np.arange(i_arr.shape[0], dtype=np.int64) - np.repeat(starts, counts)
+    return i_arr, k_arr
+
+
+def build_region_windows(cc, region, control):
+    """Windows of one view region ``(chrom, start, end)`` (reference: coolpup.py:546-563, 598-746)."""
+    chrom, start, end = region
+    df = cc.intervals
+    nctrl = cc.nshifts if control else 0
+    res = cc.resolution
+    if cc.kind == "bedpe":
+        m = (
+            (df["chrom1"].values == chrom) & (df["chrom2"].values == chrom)
+            & (df["start1"].values >= start) & (df["end1"].values < end)
+            & (df["start2"].values >= start) & (df["end2"].values < end)
+        )
+        sel = df[m].reset_index(drop=True)
+        q = len(sel)
+        idx = np.arange(q, dtype=np.int64)
+        st1 = sel["stBin1"].values.astype(np.int64)
+        st2 = sel["stBin2"].values.astype(np.int64)
+        dist = sel["distance"].values.astype(np.float64)
+        kind = np.zeros(q, dtype=np.int8)
+        if nctrl > 0 and q > 0:
+            dbin = _draw_shifts(q * nctrl, cc.minshift, cc.maxshift, res)
+            cidx = np.tile(idx, nctrl)
+            st1 = np.concatenate([st1, st1[cidx] + dbin])
+            st2 = np.concatenate([st2, st2[cidx] + dbin])
+            dist = np.concatenate([dist, dist[cidx]])
+            kind = np.concatenate([kind, np.ones(q * nctrl, dtype=np.int8)])
+            idx = np.concatenate([idx, cidx])
+        return RegionWindows(region, sel, st1, st2, kind, idx, idx, dist, paired=False)
+
+    m = (df["chrom"].values == chrom) & (df["start"].values >= start) & (df["end"].values < end)
+    sel = df[m].reset_index(drop=True)
+    nfeat = len(sel)
+    stbin = sel["stBin"].values.astype(np.int64)
+    if cc.local:
+        idx = np.arange(nfeat, dtype=np.int64)
+        st = stbin.copy()
+        kind = np.zeros(nfeat, dtype=np.int8)
+        st1 = st2 = st
+        if nctrl > 0 and nfeat > 0:
+            dbin = _draw_shifts(nfeat * nctrl, cc.minshift, cc.maxshift, res)
+            cidx = np.tile(idx, nctrl)
+            st1 = st2 = np.concatenate([st, st[cidx] + dbin])
+            kind = np.concatenate([kind, np.ones(nfeat * nctrl, dtype=np.int8)])
+            idx = np.concatenate([idx, cidx])
+        return RegionWindows(region, sel, st1, st2, kind, idx, idx, None, paired=True)
+
+    i_arr, k_arr = pair_offsets(nfeat)
+    l_arr = k_arr + i_arr
+    center = sel["center"].values.astype(np.float64)
+    dist = center[l_arr] - center[k_arr]
+    keep = (cc.mindist <= np.abs(dist)) & (np.abs(dist) <= cc.maxdist)
+    i_arr, k_arr, l_arr, dist = i_arr[keep], k_arr[keep], l_arr[keep], dist[keep]
+    if nctrl == 0 or i_arr.shape[0] == 0:
+        kind = np.zeros(k_arr.shape[0], dtype=np.int8)
+        return RegionWindows(region, sel, stbin[k_arr], stbin[l_arr], kind, k_arr, l_arr, dist, paired=True)
+    # controls are drawn once per offset block, ROI rows of the block first, then its nshifts replicas
+    q = np.bincount(i_arr, minlength=nfeat)
+    block_start = np.concatenate([[0], np.cumsum(q)])
+    parts_k, parts_l, parts_shift, parts_kind = [], [], [], []
+    for i in np.nonzero(q)[0]:
+        a, b = block_start[i], block_start[i + 1]
+        n = int(q[i])
+        dbin = _draw_shifts(n * nctrl, cc.minshift, cc.maxshift, res)
+        kk, ll = k_arr[a:b], l_arr[a:b]
+        parts_k.append(np.concatenate([kk, np.tile(kk, nctrl)]))
+        parts_l.append(np.concatenate([ll, np.tile(ll, nctrl)]))
+        parts_shift.append(np.concatenate([np.zeros(n, dtype=np.int64), dbin]))
+        kd = np.ones(n * (nctrl + 1), dtype=np.int8)
+        kd[:n] = 0
+        parts_kind.append(kd)
+    kk = np.concatenate(parts_k)
+    ll = np.concatenate(parts_l)
+    sh = np.concatenate(parts_shift)
+    kind = np.concatenate(parts_kind)
+    dist_all = center[ll] - center[kk]
+    return RegionWindows(region, sel, stbin[kk] + sh, stbin[ll] + sh, kind, kk, ll, dist_all, paired=True)

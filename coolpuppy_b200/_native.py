@@ -1,0 +1,185 @@
+"""ctypes binding of ``libpileup_b200.so`` (C ABI: ``include/pileup_b200.h``).
+
+There is deliberately no fallback: if the library is missing, or no CUDA device
+is visible, every compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PUP_F_OOE = 1
+PUP_F_EXPCTRL = 2
+PUP_F_COVERAGE = 4
+PUP_F_NODIAG = 8
+
+_LIB = None
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200.so")
+
+SYMBOLS = [
+    "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_destroy",
+    "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
+    "pup_last_launches", "pup_algorithmic_bytes",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_PATH):
+        raise NativeError(
+            f"{_PATH} is missing: build it with `python -m coolpuppy_b200.build` "
+            "(there is no CPU fallback for the pile-up path)"
+        )
+    L = C.CDLL(_PATH)
+    vp, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint
+    L.pup_abi_version.restype = C.c_int
+    L.pup_last_error.restype = C.c_char_p
+    L.pup_last_launches.restype = C.c_int
+    L.pup_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.pup_region_create.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.pup_region_destroy.argtypes = [vp]
+    L.pup_region_device_bytes.argtypes = [vp]
+    L.pup_region_device_bytes.restype = i64
+    L.pup_acc_stride.argtypes = [C.c_int]
+    L.pup_acc_stride.restype = i64
+    L.pup_accumulate.argtypes = [vp, i64, vp, vp, vp, C.c_int, C.c_int, C.c_int, u32, vp, vp, C.POINTER(i64)]
+    L.pup_accumulate_region.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, C.c_int, C.c_int,
+                                        C.c_int, u32, vp, vp, C.POINTER(i64)]
+    L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pup_algorithmic_bytes.argtypes = [vp, i64, vp, vp, C.c_int, u32, vp, C.POINTER(i64), C.POINTER(i64)]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(f"libpileup_b200 error {rc}: {lib().pup_last_error().decode()}")
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().pup_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def require_device():
+    if device_count() < 1:
+        raise NativeError("no CUDA device visible: the pile-up path has no CPU fallback")
+
+
+def ptr(a, dtype=None):
+    """Raw address of a numpy array / torch tensor (host or device) or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        if dtype is not None and a.dtype != np.dtype(dtype):
+            raise TypeError(f"expected {np.dtype(dtype)}, got {a.dtype}")
+        if not a.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(a)}")
+
+
+def alloc_accumulator(n_doubles, device):
+    """Zeroed fp64 accumulator in HBM (a torch tensor, so that torch.distributed can all-reduce it)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device visible: the pile-up path has no CPU fallback")
+    return torch.zeros(int(n_doubles), dtype=torch.float64, device=torch.device("cuda", device))
+
+
+def current_stream(device):
+    """The caller's current CUDA stream on ``device`` as a raw ``cudaStream_t`` value."""
+    import torch
+
+    return torch.cuda.current_stream(torch.device("cuda", device)).cuda_stream
+
+
+def acc_stride(W):
+    return int(lib().pup_acc_stride(int(W)))
+
+
+class Region:
+    """A region matrix resident in HBM (``pup_region_t``)."""
+
+    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, stream=0):
+        self._h = C.c_void_p()
+        self.nb = int(nb)
+        self.nnz = int(col.shape[0]) if col is not None else 0
+        self.device = device
+        self.balanced = weight is not None
+        check(lib().pup_region_create(device, self.nb, self.nnz, ptr(indptr, np.int32) if isinstance(indptr, np.ndarray) else ptr(indptr),
+                                      ptr(col), ptr(count), ptr(weight), ptr(expected), ptr(coverage), stream,
+                                      C.byref(self._h)))
+
+    @property
+    def device_bytes(self):
+        return int(lib().pup_region_device_bytes(self._h))
+
+    def accumulate(self, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream=0, want_n_valid=False):
+        n = int(r0.shape[0])
+        nv = C.c_int64(0)
+        check(lib().pup_accumulate(self._h, n, ptr(r0), ptr(c0), ptr(slot), int(W), int(ignore_diags), int(n_slots),
+                                   int(flags), ptr(acc), stream, C.byref(nv) if want_n_valid else None))
+        return nv.value if want_n_valid else None
+
+    def algorithmic_bytes(self, r0, c0, W, flags=0, stream=0):
+        b, z = C.c_int64(0), C.c_int64(0)
+        check(lib().pup_algorithmic_bytes(self._h, int(r0.shape[0]), ptr(r0), ptr(c0), int(W), int(flags), stream,
+                                          C.byref(b), C.byref(z)))
+        return b.value, z.value
+
+    def close(self):
+        if self._h:
+            lib().pup_region_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def accumulate_region(device, nb, indptr, col, count, weight, expected, coverage, r0, c0, slot, W, ignore_diags,
+                      n_slots, flags, acc, stream=0):
+    """One-shot ``pup_accumulate_region`` (everything may be host memory). Returns n_valid."""
+    nv = C.c_int64(0)
+    check(lib().pup_accumulate_region(device, int(nb), int(col.shape[0]), ptr(indptr), ptr(col), ptr(count),
+                                      ptr(weight), ptr(expected), ptr(coverage), int(r0.shape[0]), ptr(r0), ptr(c0),
+                                      ptr(slot), int(W), int(ignore_diags), int(n_slots), int(flags), ptr(acc),
+                                      stream, C.byref(nv)))
+    return nv.value
+
+
+def acc_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):
+    """Decode an accumulator buffer into dict(sum, num, n[, cov_start, cov_end][, exp_sum, exp_num])."""
+    W, n_slots = int(W), int(n_slots)
+    out = {
+        "sum": np.empty((n_slots, W, W), dtype=np.float64),
+        "num": np.empty((n_slots, W, W), dtype=np.int64),
+        "n": np.empty(n_slots, dtype=np.int64),
+    }
+    if want_cov:
+        out["cov_start"] = np.empty((n_slots, W), dtype=np.float64)
+        out["cov_end"] = np.empty((n_slots, W), dtype=np.float64)
+    if want_expected:
+        out["exp_sum"] = np.empty((n_slots, W, W), dtype=np.float64)
+        out["exp_num"] = np.empty((n_slots, W, W), dtype=np.int64)
+    check(lib().pup_acc_export(ptr(acc), W, n_slots, device, stream, ptr(out["sum"]), ptr(out["num"]), ptr(out["n"]),
+                               ptr(out.get("cov_start")), ptr(out.get("cov_end")), ptr(out.get("exp_sum")),
+                               ptr(out.get("exp_num"))))
+    return out

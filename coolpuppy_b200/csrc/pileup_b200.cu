@@ -1,0 +1,1015 @@
+// pileup_b200.cu -- sm_100a kernels + C ABI of the pile-up engine (see include/pileup_b200.h).
+//
+// Hot path restated for the GPU (reference: coolpup.py:1059-1191 _stream_snips, 1236-1283 accumulate_stream,
+// lib/puputils.py:12-41 _add_snip):
+//
+//   for every window (r0, c0, slot):                       # sorted by (slot, r0, c0) on the device
+//     for every window row di:                             # one sub-warp row-group owns row di of the smem tile
+//       start = bucket[(c0 >> lb) * nb + r0 + di]          # column-bucket-major row pointer table: no binary search
+//       stream the row's (col, count) pairs from `start` while col < c0 + W     # coalesced 8-byte loads
+//       v = (w[row] * w[col]) * count / E[|col-row|]       # balancing + expected fused; signed diagonal mask
+//       tile[di][col - c0] += v                            # fp64 shared-memory tile, race-free by row ownership
+//   flush tile with red.global.add.f64 when the slot changes
+//
+// `num` (count of finite contributions) is dense in the reference (W*W work per window).  Here it is
+//   num = n_fast - rowbad[di] - colbad[dj] + xtile[di][dj]
+// with O(W) vector work per window plus a sparse bad-row x bad-col correction; only windows that touch the
+// masked diagonals / NaN expected values ("slow" windows) take the dense W*W path.
+#include "pileup_b200.h"
+
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_launches = 0;
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess)
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  else
+    snprintf(buf, sizeof buf, "%s", what);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(e_ == cudaErrorMemoryAllocation ? PUP_E_OOM : PUP_E_CUDA, #call, e_);        \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                     \
+  do {                                                                                         \
+    ++g_launches;                                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                       \
+    if (e_ != cudaSuccess) return fail(PUP_E_CUDA, "launch " name, e_);                        \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// stream-ordered scratch allocations, released when the holder goes out of scope
+struct Scratch {
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t s) : stream(s) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, stream);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr int NT = 512;   // threads per CTA of the main kernel
+constexpr int VT = 512;   // threads per CTA of the vector kernel
+constexpr int VCH = 1024; // windows per CTA step of the vector kernel
+
+// ------------------------------------------------------------------------------------------ accumulator layout
+struct AccLayout {
+  int W;
+  int64_t w2, off_num, off_rb, off_cb, off_covs, off_cove, off_tsum, off_tnum, off_n, off_nfast, stride;
+  __host__ __device__ explicit AccLayout(int W_) : W(W_) {
+    w2 = (int64_t)W * W;
+    off_num = w2;
+    off_rb = 2 * w2;
+    off_cb = off_rb + W;
+    off_covs = off_cb + W;
+    off_cove = off_covs + W;
+    off_tsum = off_cove + W;
+    off_tnum = off_tsum + 2 * W;
+    off_n = off_tnum + 2 * W;
+    off_nfast = off_n + 1;
+    stride = off_n + 8;
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ region
+struct pup_region {
+  int device;
+  int32_t nb;
+  int64_t nnz;
+  int lb;   // log2 of the column-bucket width
+  int nbk;  // number of column buckets
+  int2* ent;          // [nnz] (col, count) interleaved
+  int32_t* indptr;    // [nb+1]
+  int32_t* bucket;    // [nbk][nb] first entry of row r with col >= b << lb
+  double* weight;     // [nb] or null
+  double* expected;   // [nb] or null
+  double* coverage;   // [nb] or null
+  uint8_t* bad;       // [nb] weight is NaN
+  uint8_t* ebad;      // [nb] expected is NaN or 0
+  int32_t* ebadpre;   // [nb+1] exclusive prefix of ebad
+  cudaStream_t stream;
+  int64_t bytes;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ prep kernels
+__global__ void k_interleave(const int32_t* __restrict__ col, const int32_t* __restrict__ cnt, int2* __restrict__ ent,
+                             int64_t nnz) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < nnz; i += step) ent[i] = make_int2(col[i], cnt[i]);
+}
+
+// bucket[b * nb + r] = first entry index of row r whose column is >= (b << lb)
+__global__ void k_build_buckets(const int2* __restrict__ ent, const int32_t* __restrict__ indptr,
+                                int32_t* __restrict__ bucket, int nb, int nbk, int lb) {
+  int64_t total = (int64_t)nb * nbk;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    int r = (int)(i % nb);
+    int b = (int)(i / nb);
+    int lo = indptr[r], hi = indptr[r + 1];
+    int target = b << lb;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldg(&ent[mid].x) < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    bucket[i] = lo;
+  }
+}
+
+__global__ void k_masks(const double* __restrict__ weight, const double* __restrict__ expected, uint8_t* bad,
+                        uint8_t* ebad, int32_t* ebad32, int nb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nb) return;
+  if (i == nb) {
+    ebad32[i] = 0;
+    return;
+  }
+  bad[i] = (weight != nullptr && isnan(weight[i])) ? 1 : 0;
+  uint8_t eb = 0;
+  if (expected != nullptr) {
+    double e = expected[i];
+    eb = (isnan(e) || e == 0.0) ? 1 : 0;
+  }
+  ebad[i] = eb;
+  ebad32[i] = eb;
+}
+
+// ------------------------------------------------------------------------------------------ window keys
+// key = [invalid:1][slot][r0:pb][c0:pb]; out-of-region windows get only the invalid bit and sort last.
+__global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __restrict__ c0,
+                              const int32_t* __restrict__ slot, uint64_t* __restrict__ keys, int64_t n, int nb, int W,
+                              int n_slots, int pb) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int r = r0[i], c = c0[i], s = slot[i];
+  bool ok = r >= 0 && c >= 0 && r + W <= nb && c + W <= nb && s >= 0 && s < n_slots;
+  uint64_t k;
+  if (ok)
+    k = ((uint64_t)s << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c;
+  else
+    k = ~0ull;
+  keys[i] = k;
+}
+
+// slot_start[s] = first sorted window of slot s (s = n_slots: number of valid windows);
+// nchunks[s] = ceil(count / ch)
+__global__ void k_slot_bounds(const uint64_t* __restrict__ keys, int n, int n_slots, int pb, int ch,
+                              int32_t* __restrict__ slot_start, int32_t* __restrict__ nchunks) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > n_slots) return;
+  auto lower = [&](int sl) {
+    uint64_t target = (sl >= n_slots) ? (1ull << 63) : ((uint64_t)sl << (2 * pb));
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (keys[mid] < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    return lo;
+  };
+  int a = lower(s);
+  slot_start[s] = a;
+  if (s < n_slots) {
+    int b = lower(s + 1);
+    nchunks[s] = (b - a + ch - 1) / ch;
+  } else {
+    nchunks[s] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ shared device helpers
+struct WinCtx {
+  int nb, W, pb, ignore_diags;
+  unsigned flags;
+  const int32_t* ebadpre;
+};
+
+__device__ __forceinline__ void decode_key(uint64_t k, int pb, int& slot, int& r0, int& c0) {
+  uint64_t m = (1ull << pb) - 1;
+  c0 = (int)(k & m);
+  r0 = (int)((k >> pb) & m);
+  slot = (int)(k >> (2 * pb));
+}
+
+// A window is "slow" when some pixel is masked by the signed diagonal rule or by a NaN/zero expected value:
+// its `num` contribution is then evaluated densely.  Fast windows contribute through rb/cb/n_fast only.
+__device__ __forceinline__ bool window_is_slow(const WinCtx& c, int r0, int c0) {
+  int D0 = c0 - r0;
+  int dmin = D0 - (c.W - 1), dmax = D0 + (c.W - 1);
+  if (!(c.flags & PUP_F_NODIAG) && dmin < c.ignore_diags) return true;
+  if (c.flags & PUP_F_OOE) {
+    int a, b;
+    if (dmin >= 0) {
+      a = dmin;
+      b = dmax;
+    } else if (dmax <= 0) {
+      a = -dmax;
+      b = -dmin;
+    } else {
+      a = 0;
+      b = max(-dmin, dmax);
+    }
+    b = min(b, c.nb - 1);
+    a = min(a, b);
+    return (__ldg(&c.ebadpre[b + 1]) - __ldg(&c.ebadpre[a])) > 0;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------------------ vector kernel
+// Per-window O(W) quantities: n, n_fast, bad-row / bad-col counts, coverage sums, Toeplitz sums of the bare
+// expected block.  One CTA walks VCH consecutive sorted windows; thread t owns vector index t.
+struct VecParams {
+  WinCtx ctx;
+  const uint64_t* keys;
+  const int32_t* slot_start;  // [n_slots+1]
+  int n_slots;
+  const uint8_t* bad;        // null when raw
+  const double* expected;    // for EXPCTRL
+  const double* coverage;    // for COVERAGE
+  double* acc;
+};
+
+__global__ void __launch_bounds__(VT) k_vector(const VecParams p) {
+  const int n = __ldg(&p.slot_start[p.n_slots]);
+  const int W = p.ctx.W;
+  const AccLayout L(W);
+  const int t = threadIdx.x;
+  const bool has_bad = p.bad != nullptr;
+  const bool cov = (p.ctx.flags & PUP_F_COVERAGE) && p.coverage != nullptr;
+  const bool ectl = (p.ctx.flags & PUP_F_EXPCTRL) && p.expected != nullptr;
+  for (int base = blockIdx.x * VCH; base < n; base += gridDim.x * VCH) {
+    int end = min(base + VCH, n);
+    int cur = -1;
+    double rb = 0, cb = 0, cs = 0, ce = 0, ts = 0, tn = 0, nn = 0, nf = 0;
+    auto flush = [&]() {
+      if (cur < 0) return;
+      double* a = p.acc + (int64_t)cur * L.stride;
+      if (t < W) {
+        if (rb != 0) atomicAdd(a + L.off_rb + t, rb);
+        if (cb != 0) atomicAdd(a + L.off_cb + t, cb);
+        if (cs != 0) atomicAdd(a + L.off_covs + t, cs);
+        if (ce != 0) atomicAdd(a + L.off_cove + t, ce);
+      }
+      if (t < 2 * W - 1) {
+        if (ts != 0) atomicAdd(a + L.off_tsum + t, ts);
+        if (tn != 0) atomicAdd(a + L.off_tnum + t, tn);
+      }
+      if (t == 0) {
+        atomicAdd(a + L.off_n, nn);
+        if (nf != 0) atomicAdd(a + L.off_nfast, nf);
+      }
+      rb = cb = cs = ce = ts = tn = nn = nf = 0;
+    };
+    for (int w = base; w < end; ++w) {
+      int slot, r0, c0;
+      decode_key(__ldg(&p.keys[w]), p.ctx.pb, slot, r0, c0);
+      if (slot != cur) {
+        flush();
+        cur = slot;
+      }
+      bool slow = window_is_slow(p.ctx, r0, c0);
+      if (t == 0) {
+        nn += 1;
+        if (!slow) nf += 1;
+      }
+      if (t < W) {
+        if (has_bad && !slow) {
+          rb += p.bad[r0 + t];
+          cb += p.bad[c0 + t];
+        }
+        if (cov) {
+          double a = __ldg(&p.coverage[r0 + t]), b = __ldg(&p.coverage[c0 + t]);
+          if (!isnan(a)) cs += a;
+          if (!isnan(b)) ce += b;
+        }
+      }
+      if (ectl && t < 2 * W - 1) {
+        int d = c0 - r0 + t - (W - 1);
+        d = d < 0 ? -d : d;
+        double e = __ldg(&p.expected[d]);
+        if (!isnan(e)) ts += e;
+        if (isfinite(e)) tn += 1;
+      }
+    }
+    flush();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ main kernel
+struct MainParams {
+  WinCtx ctx;
+  const int2* ent;
+  const int32_t* indptr;
+  const int32_t* bucket;
+  int lb;
+  const double* weight;
+  const double* expected;
+  const uint8_t* bad;
+  const uint8_t* ebad;
+  const uint64_t* keys;
+  const int32_t* slot_start;   // [n_slots+1]
+  const int32_t* chunk_start;  // [n_slots+1] exclusive scan of chunks per slot
+  int n_slots;
+  int Wb;       // tile rows per band
+  int n_bands;
+  int ch;       // windows per chunk
+  double* acc;
+  int* counter;
+};
+
+template <int S, bool BAL, bool OOE>
+__global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int W = p.ctx.W;
+  const int Wb = p.Wb;
+  double* sumT = reinterpret_cast<double*>(smem_raw);
+  int* numT = reinterpret_cast<int*>(sumT + (size_t)Wb * W);
+  __shared__ int s_slot, s_lo, s_hi, s_band;
+
+  const AccLayout L(W);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int GPW = 32 / S;           // row-groups per warp
+  constexpr int NG = (NT / 32) * GPW;   // row-groups per CTA
+  const int sub = lane / S;
+  const int ls = lane % S;
+  const int g = warp * GPW + sub;
+  const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
+  const bool nodiag = p.ctx.flags & PUP_F_NODIAG;
+  const int igd = p.ctx.ignore_diags;
+  const int nb = p.ctx.nb;
+  const int tile = Wb * W;
+
+  for (int i = threadIdx.x; i < tile; i += NT) {
+    sumT[i] = 0.0;
+    numT[i] = 0;
+  }
+  int cur_slot = -1, cur_band = 0;
+  const int total_chunks = __ldg(&p.chunk_start[p.n_slots]);
+
+  auto flush = [&]() {
+    // every thread adds its cells of the tile into the global accumulator, then clears them
+    double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)cur_band * Wb * W;
+    int rows = min(Wb, W - cur_band * Wb);
+    int cells = rows * W;
+    for (int i = threadIdx.x; i < cells; i += NT) {
+      double v = sumT[i];
+      if (v != 0.0) {
+        atomicAdd(a + i, v);
+        sumT[i] = 0.0;
+      }
+      int c = numT[i];
+      if (c != 0) {
+        atomicAdd(a + L.off_num + i, (double)c);
+        numT[i] = 0;
+      }
+    }
+  };
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int item = atomicAdd(p.counter, 1);
+      if (item >= total_chunks * p.n_bands) {
+        s_slot = -1;
+      } else {
+        int band = item / total_chunks;
+        int chunk = item - band * total_chunks;
+        int lo = 0, hi = p.n_slots;  // last s with chunk_start[s] <= chunk
+        while (lo < hi) {
+          int mid = (lo + hi + 1) >> 1;
+          if (__ldg(&p.chunk_start[mid]) <= chunk)
+            lo = mid;
+          else
+            hi = mid - 1;
+        }
+        int s = lo;
+        int w0 = __ldg(&p.slot_start[s]) + (chunk - __ldg(&p.chunk_start[s])) * p.ch;
+        s_slot = s;
+        s_band = band;
+        s_lo = w0;
+        s_hi = min(w0 + p.ch, __ldg(&p.slot_start[s + 1]));
+      }
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot < 0) break;
+    const int band = s_band;
+    if (slot != cur_slot || band != cur_band) {
+      if (cur_slot >= 0) {
+        flush();
+        __syncthreads();
+      }
+      cur_slot = slot;
+      cur_band = band;
+    }
+    const int row_lo = band * Wb;
+    const int nrows = min(Wb, W - row_lo);
+    const int w_lo = s_lo, w_hi = s_hi;
+
+    for (int w = w_lo; w < w_hi; ++w) {
+      int kslot, r0, c0;
+      decode_key(__ldg(&p.keys[w]), p.ctx.pb, kslot, r0, c0);
+      const bool slow = window_is_slow(p.ctx, r0, c0);
+      const int bcol = (c0 >> p.lb);
+      for (int dl = g; dl < nrows; dl += NG) {
+        const int r = r0 + row_lo + dl;
+        double* trow = sumT + dl * W;
+        int* nrow = numT + dl * W;
+        bool rbad = false;
+        double wr = 1.0;
+        if (BAL) {
+          wr = __ldg(&p.weight[r]);
+          rbad = isnan(wr);
+        }
+        if (!rbad) {
+          int idx = __ldg(&p.bucket[(size_t)bcol * nb + r]) + ls;
+          const int pend = __ldg(&p.indptr[r + 1]);
+          for (; idx < pend; idx += S) {
+            const int2 e = __ldg(&p.ent[idx]);
+            const int dj = e.x - c0;
+            if (dj >= W) break;
+            if (dj < 0) continue;
+            const int d = e.x - r;
+            if (!nodiag && d < igd) continue;
+            double v = (double)e.y;
+            if (BAL) v = (wr * __ldg(&p.weight[e.x])) * v;
+            if (OOE) v = v / __ldg(&p.expected[d < 0 ? -d : d]);
+            if (v != v) continue;
+            trow[dj] += v;
+          }
+        }
+        if (slow) {
+          for (int dj = ls; dj < W; dj += S) {
+            const int c = c0 + dj;
+            const int d = c - r;
+            bool ok = !rbad;
+            if (BAL) ok = ok && !__ldg(&p.bad[c]);
+            if (!nodiag) ok = ok && (d >= igd);
+            if (OOE) ok = ok && !__ldg(&p.ebad[d < 0 ? -d : d]);
+            if (ok) nrow[dj] += 1;
+          }
+        } else if (BAL && rbad) {
+          for (int dj = ls; dj < W; dj += S)
+            if (__ldg(&p.bad[c0 + dj])) nrow[dj] += 1;
+        }
+        __syncwarp(gmask);
+      }
+    }
+  }
+  __syncthreads();
+  if (cur_slot >= 0) flush();
+}
+
+// ------------------------------------------------------------------------------------------ byte counter
+// Exact algorithmic pixel count of a window list (measurement helper, not on the timed path).
+__global__ void k_count_nnz(const int2* __restrict__ ent, const int32_t* __restrict__ indptr,
+                            const int32_t* __restrict__ r0, const int32_t* __restrict__ c0, int64_t n, int nb, int W,
+                            unsigned long long* out_nnz, unsigned long long* out_valid) {
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long local = 0, valid = 0;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    int r = r0[i], c = c0[i];
+    if (r < 0 || c < 0 || r + W > nb || c + W > nb) continue;
+    if (lane == 0) valid += 1;
+    for (int di = lane; di < W; di += 32) {
+      int lo = indptr[r + di], hi = indptr[r + di + 1];
+      auto lower = [&](int target) {
+        int a = lo, b = hi;
+        while (a < b) {
+          int mid = (a + b) >> 1;
+          if (__ldg(&ent[mid].x) < target)
+            a = mid + 1;
+          else
+            b = mid;
+        }
+        return a;
+      };
+      local += (unsigned long long)(lower(c + W) - lower(c));
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    local += __shfl_down_sync(0xffffffffu, local, o);
+    valid += __shfl_down_sync(0xffffffffu, valid, o);
+  }
+  if (lane == 0) {
+    if (local) atomicAdd(out_nnz, local);
+    if (valid) atomicAdd(out_valid, valid);
+  }
+}
+
+int ilog2_ceil(int64_t v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
+template <int S>
+cudaError_t launch_main(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe) {
+#define PUP_LAUNCH(B, O)                                                                                  \
+  do {                                                                                                    \
+    auto kern = k_pileup_main<S, B, O>;                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return e;                                                                       \
+    kern<<<grid, NT, smem, st>>>(p);                                                                      \
+    return cudaGetLastError();                                                                            \
+  } while (0)
+  if (bal && ooe) PUP_LAUNCH(true, true);
+  if (bal && !ooe) PUP_LAUNCH(true, false);
+  if (!bal && ooe) PUP_LAUNCH(false, true);
+  PUP_LAUNCH(false, false);
+#undef PUP_LAUNCH
+}
+
+template <int S>
+cudaError_t main_occupancy(int* blocks, size_t smem, bool bal, bool ooe) {
+#define PUP_OCC(B, O)                                                                                     \
+  do {                                                                                                    \
+    auto kern = k_pileup_main<S, B, O>;                                                                   \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+    if (e != cudaSuccess) return e;                                                                       \
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem);                         \
+  } while (0)
+  if (bal && ooe) PUP_OCC(true, true);
+  if (bal && !ooe) PUP_OCC(true, false);
+  if (!bal && ooe) PUP_OCC(false, true);
+  PUP_OCC(false, false);
+#undef PUP_OCC
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+}  // namespace
+
+// =========================================================================================== C ABI
+extern "C" {
+
+int pup_abi_version(void) { return 1; }
+
+const char* pup_last_error(void) { return g_err.c_str(); }
+
+int pup_last_launches(void) { return g_launches; }
+
+int pup_device_count(int* n_out) {
+  if (!n_out) return fail(PUP_E_ARG, "pup_device_count: null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *n_out = 0;
+    return fail(PUP_E_NODEV, "cudaGetDeviceCount", e);
+  }
+  *n_out = n;
+  return PUP_OK;
+}
+
+int64_t pup_acc_stride(int W) {
+  if (W <= 0) return 0;
+  return AccLayout(W).stride;
+}
+
+int64_t pup_region_device_bytes(const pup_region_t* r) { return r ? r->bytes : 0; }
+
+int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
+                      const int32_t* count, const double* weight, const double* expected, const double* coverage,
+                      void* stream, pup_region_t** out) {
+  if (!out) return fail(PUP_E_ARG, "pup_region_create: null output");
+  *out = nullptr;
+  if (nb <= 0 || nnz < 0 || nnz >= (1ll << 31) || !indptr || (nnz > 0 && (!col || !count)))
+    return fail(PUP_E_ARG, "pup_region_create: bad sizes or null CSR arrays");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(PUP_E_NODEV, "pup_region_create: no such CUDA device");
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_region_create: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches = 0;
+
+  pup_region* r = new pup_region();
+  memset(r, 0, sizeof *r);
+  r->device = device;
+  r->nb = nb;
+  r->nnz = nnz;
+  r->stream = st;
+
+  // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
+  double avg = (double)nnz / nb;
+  int target = env_int("PUP_BUCKET_TARGET", 8);
+  if (avg <= 24.0) {
+    r->lb = 31;
+    r->nbk = 1;
+  } else {
+    int lb = (int)floor(log2((double)target * nb / avg));
+    if (lb < 3) lb = 3;
+    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)2 * nnz + (64 << 20)) ++lb;  // cap: 25% of pixel bytes
+    r->lb = lb;
+    r->nbk = (nb + (1 << lb) - 1) >> lb;
+  }
+
+  auto cleanup = [&](int code) {
+    pup_region_destroy(r);
+    return code;
+  };
+#define RCK(call)                                                                                            \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return cleanup(fail(e_ == cudaErrorMemoryAllocation ? PUP_E_OOM : PUP_E_CUDA, #call, e_));             \
+  } while (0)
+
+  size_t n_ent = (size_t)(nnz > 0 ? nnz : 1);
+  RCK(cudaMallocAsync((void**)&r->ent, n_ent * sizeof(int2), st));
+  RCK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
+  RCK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
+  RCK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
+  RCK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
+  RCK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
+  r->bytes = (int64_t)(n_ent * sizeof(int2) + (size_t)(nb + 1) * 8 + (size_t)r->nbk * nb * 4 + 2 * (size_t)nb);
+  if (weight) {
+    RCK(cudaMallocAsync((void**)&r->weight, (size_t)nb * 8, st));
+    RCK(cudaMemcpyAsync(r->weight, weight, (size_t)nb * 8, cudaMemcpyDefault, st));
+    r->bytes += (int64_t)nb * 8;
+  }
+  if (expected) {
+    RCK(cudaMallocAsync((void**)&r->expected, (size_t)nb * 8, st));
+    RCK(cudaMemcpyAsync(r->expected, expected, (size_t)nb * 8, cudaMemcpyDefault, st));
+    r->bytes += (int64_t)nb * 8;
+  }
+  if (coverage) {
+    RCK(cudaMallocAsync((void**)&r->coverage, (size_t)nb * 8, st));
+    RCK(cudaMemcpyAsync(r->coverage, coverage, (size_t)nb * 8, cudaMemcpyDefault, st));
+    r->bytes += (int64_t)nb * 8;
+  }
+  RCK(cudaMemcpyAsync(r->indptr, indptr, (size_t)(nb + 1) * 4, cudaMemcpyDefault, st));
+  {
+    Scratch tmp(st);
+    if (nnz > 0) {
+      const int32_t* dcol = col;
+      const int32_t* dcnt = count;
+      if (!is_device_ptr(col)) {
+        int32_t* t;
+        RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
+        RCK(cudaMemcpyAsync(t, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        dcol = t;
+      }
+      if (!is_device_ptr(count)) {
+        int32_t* t;
+        RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
+        RCK(cudaMemcpyAsync(t, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        dcnt = t;
+      }
+      int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 32);
+      k_interleave<<<grid, 256, 0, st>>>(dcol, dcnt, r->ent, nnz);
+      ++g_launches;
+      RCK(cudaGetLastError());
+    }
+    {
+      int64_t total = (int64_t)nb * r->nbk;
+      int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
+      k_build_buckets<<<grid, 256, 0, st>>>(r->ent, r->indptr, r->bucket, nb, r->nbk, r->lb);
+      ++g_launches;
+      RCK(cudaGetLastError());
+    }
+    {
+      int32_t* ebad32;
+      RCK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
+      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(r->weight, r->expected, r->bad, r->ebad, ebad32, nb);
+      ++g_launches;
+      RCK(cudaGetLastError());
+      size_t tb = 0;
+      RCK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ebad32, r->ebadpre, nb + 1, st));
+      void* t;
+      RCK(tmp.alloc(&t, tb));
+      RCK(cub::DeviceScan::ExclusiveSum(t, tb, ebad32, r->ebadpre, nb + 1, st));
+      ++g_launches;
+    }
+    // host staging buffers must stay valid until the copies have been consumed
+    if (!is_device_ptr(indptr) || (nnz > 0 && (!is_device_ptr(col) || !is_device_ptr(count))) ||
+        (weight && !is_device_ptr(weight)) || (expected && !is_device_ptr(expected)) ||
+        (coverage && !is_device_ptr(coverage)))
+      RCK(cudaStreamSynchronize(st));
+  }
+#undef RCK
+  *out = r;
+  return PUP_OK;
+}
+
+int pup_region_destroy(pup_region_t* r) {
+  if (!r) return PUP_OK;
+  DeviceGuard guard(r->device);
+  cudaStream_t st = r->stream;
+  void* ptrs[] = {r->ent, r->indptr, r->bucket, r->weight, r->expected, r->coverage, r->bad, r->ebad, r->ebadpre};
+  for (void* p : ptrs)
+    if (p) cudaFreeAsync(p, st);
+  delete r;
+  return PUP_OK;
+}
+
+int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0, const int32_t* slot,
+                   int W, int ignore_diags, int n_slots, unsigned flags, double* acc, void* stream,
+                   int64_t* n_valid_out) {
+  if (!m) return fail(PUP_E_ARG, "pup_accumulate: null region");
+  if (n_win < 0 || n_win >= (1ll << 31) || W <= 0 || W > 4096 || n_slots <= 0 || !acc)
+    return fail(PUP_E_ARG, "pup_accumulate: bad sizes or null accumulator");
+  if (n_win > 0 && (!r0 || !c0 || !slot)) return fail(PUP_E_ARG, "pup_accumulate: null window arrays");
+  if ((flags & (PUP_F_OOE | PUP_F_EXPCTRL)) && !m->expected)
+    return fail(PUP_E_ARG, "pup_accumulate: expected requested but the region has none");
+  if ((flags & PUP_F_OOE) && (flags & PUP_F_EXPCTRL))
+    return fail(PUP_E_ARG, "pup_accumulate: PUP_F_OOE and PUP_F_EXPCTRL are exclusive");
+  if ((flags & PUP_F_COVERAGE) && !m->coverage)
+    return fail(PUP_E_ARG, "pup_accumulate: coverage requested but the region has none");
+  const int pb = ilog2_ceil((int64_t)m->nb + 1);
+  const int sb = ilog2_ceil((int64_t)n_slots + 1);
+  if (2 * pb + sb > 62) return fail(PUP_E_ARG, "pup_accumulate: too many slots for this region size");
+  DeviceGuard guard(m->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_accumulate: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches = 0;
+  if (n_valid_out) *n_valid_out = 0;
+  if (n_win == 0) return PUP_OK;
+
+  const AccLayout L(W);
+  const int64_t acc_len = L.stride * n_slots;
+  Scratch tmp(st);
+  bool host_inputs = false;
+
+  const int32_t *d_r0 = r0, *d_c0 = c0, *d_slot = slot;
+  auto stage = [&](const int32_t*& d, const int32_t* h) -> cudaError_t {
+    if (is_device_ptr(h)) return cudaSuccess;
+    host_inputs = true;
+    int32_t* t;
+    cudaError_t e = tmp.alloc((void**)&t, (size_t)n_win * 4);
+    if (e != cudaSuccess) return e;
+    d = t;
+    return cudaMemcpyAsync(t, h, (size_t)n_win * 4, cudaMemcpyHostToDevice, st);
+  };
+  CK(stage(d_r0, r0));
+  CK(stage(d_c0, c0));
+  CK(stage(d_slot, slot));
+
+  double* d_acc = acc;
+  const bool host_acc = !is_device_ptr(acc);
+  if (host_acc) {
+    CK(tmp.alloc((void**)&d_acc, (size_t)acc_len * 8));
+    CK(cudaMemsetAsync(d_acc, 0, (size_t)acc_len * 8, st));
+  }
+
+  // 1. sort keys
+  uint64_t *keys_a, *keys_b;
+  CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
+  CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
+  k_window_keys<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(d_r0, d_c0, d_slot, keys_a, n_win, m->nb, W, n_slots,
+                                                                  pb);
+  LAUNCH_CHECK("k_window_keys");
+  cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
+  {
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_win, 0, 64, st));
+    void* t;
+    CK(tmp.alloc(&t, tb));
+    // valid keys use 2*pb+sb bits; the invalid marker (~0) needs bit 63 -> sort [0, 2pb+sb) plus the top bit
+    // by sorting the full 64 bits only when it is cheap; otherwise two partial sorts would be needed, so we
+    // simply sort all 64 bits (n_win * 8 passes over 8 bytes: negligible next to the pile-up itself).
+    CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, 64, st));
+    g_launches += 8;
+  }
+  const uint64_t* keys = dbuf.Current();
+
+  // 2. slot boundaries and chunk table
+  const int ch = std::max(1, env_int("PUP_CHUNK", 64));
+  int32_t *slot_start, *nchunks, *chunk_start;
+  CK(tmp.alloc((void**)&slot_start, (size_t)(n_slots + 1) * 4));
+  CK(tmp.alloc((void**)&nchunks, (size_t)(n_slots + 1) * 4));
+  CK(tmp.alloc((void**)&chunk_start, (size_t)(n_slots + 1) * 4));
+  k_slot_bounds<<<(n_slots + 1 + 127) / 128, 128, 0, st>>>(keys, (int)n_win, n_slots, pb, ch, slot_start, nchunks);
+  LAUNCH_CHECK("k_slot_bounds");
+  {
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nchunks, chunk_start, n_slots + 1, st));
+    void* t;
+    CK(tmp.alloc(&t, tb));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, nchunks, chunk_start, n_slots + 1, st));
+    ++g_launches;
+  }
+
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  WinCtx ctx{m->nb, W, pb, ignore_diags, flags, m->ebadpre};
+
+  // 3. per-window vector quantities
+  {
+    if (2 * W - 1 > VT) return fail(PUP_E_ARG, "pup_accumulate: W too large for the vector kernel (max 256)");
+    VecParams vp{ctx, keys, slot_start, n_slots, m->weight ? m->bad : nullptr, m->expected, m->coverage, d_acc};
+    int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 8);
+    k_vector<<<grid, VT, 0, st>>>(vp);
+    LAUNCH_CHECK("k_vector");
+  }
+
+  // 4. the pile-up itself
+  {
+    int* counter;
+    CK(tmp.alloc((void**)&counter, 4));
+    CK(cudaMemsetAsync(counter, 0, 4, st));
+    // band height: keep the fp64 + int32 tile within PUP_TILE_KB so that >= 2 CTAs fit per SM
+    const int tile_kb = env_int("PUP_TILE_KB", 100);
+    int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (12ll * W));
+    if (Wb < 1) Wb = 1;
+    const int n_bands = (W + Wb - 1) / Wb;
+    Wb = (W + n_bands - 1) / n_bands;  // balance the bands
+    const size_t smem = (size_t)Wb * W * 12;
+    MainParams mp{ctx,          m->ent, m->indptr,  m->bucket,   m->lb,   m->weight, m->expected, m->bad, m->ebad,
+                  keys,         slot_start, chunk_start, n_slots, Wb,     n_bands,   ch,          d_acc,  counter};
+    const bool bal = m->weight != nullptr, ooe = (flags & PUP_F_OOE) != 0;
+    int S = env_int("PUP_GROUP", 16);
+    int occ = 1;
+    cudaError_t e;
+    if (S == 32)
+      e = main_occupancy<32>(&occ, smem, bal, ooe);
+    else if (S == 8)
+      e = main_occupancy<8>(&occ, smem, bal, ooe);
+    else
+      e = main_occupancy<16>(&occ, smem, bal, ooe);
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
+    if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
+    int grid = n_sm * occ;
+    if (S == 32)
+      e = launch_main<32>(mp, grid, smem, st, bal, ooe);
+    else if (S == 8)
+      e = launch_main<8>(mp, grid, smem, st, bal, ooe);
+    else
+      e = launch_main<16>(mp, grid, smem, st, bal, ooe);
+    ++g_launches;
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
+  }
+
+  // 5. outputs that live on the host
+  if (host_acc) {
+    std::vector<double> h((size_t)acc_len);
+    CK(cudaMemcpyAsync(h.data(), d_acc, (size_t)acc_len * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < acc_len; ++i) acc[i] += h[(size_t)i];
+  }
+  if (n_valid_out) {
+    int32_t nv = 0;
+    CK(cudaMemcpyAsync(&nv, slot_start + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_valid_out = nv;
+  } else if (host_inputs && !host_acc) {
+    CK(cudaStreamSynchronize(st));
+  }
+  return PUP_OK;
+}
+
+int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
+                          const int32_t* count, const double* weight, const double* expected,
+                          const double* coverage, int64_t n_win, const int32_t* r0, const int32_t* c0,
+                          const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags, double* acc,
+                          void* stream, int64_t* n_valid_out) {
+  pup_region_t* r = nullptr;
+  int rc = pup_region_create(device, nb, nnz, indptr, col, count, weight, expected, coverage, stream, &r);
+  if (rc != PUP_OK) return rc;
+  int l0 = g_launches;
+  rc = pup_accumulate(r, n_win, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream, n_valid_out);
+  g_launches += l0;
+  pup_region_destroy(r);
+  return rc;
+}
+
+int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stream, double* sum, int64_t* num,
+                   int64_t* n, double* cov_start, double* cov_end, double* exp_sum, int64_t* exp_num) {
+  if (!acc || W <= 0 || n_slots <= 0) return fail(PUP_E_ARG, "pup_acc_export: bad arguments");
+  const AccLayout L(W);
+  const int64_t len = L.stride * n_slots;
+  std::vector<double> hbuf;
+  const double* h = acc;
+  if (is_device_ptr(acc)) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(PUP_E_NODEV, "pup_acc_export: cudaSetDevice failed");
+    hbuf.resize((size_t)len);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(hbuf.data(), acc, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h = hbuf.data();
+  }
+  for (int s = 0; s < n_slots; ++s) {
+    const double* a = h + (int64_t)s * L.stride;
+    const double nfast = a[L.off_nfast];
+    if (n) n[s] = (int64_t)llround(a[L.off_n]);
+    for (int i = 0; i < W; ++i) {
+      if (cov_start) cov_start[(int64_t)s * W + i] = a[L.off_covs + i];
+      if (cov_end) cov_end[(int64_t)s * W + i] = a[L.off_cove + i];
+      for (int j = 0; j < W; ++j) {
+        const int64_t o = (int64_t)s * L.w2 + (int64_t)i * W + j;
+        if (sum) sum[o] = a[(int64_t)i * W + j];
+        if (num) num[o] = (int64_t)llround(nfast - a[L.off_rb + i] - a[L.off_cb + j] + a[L.off_num + (int64_t)i * W + j]);
+        if (exp_sum) exp_sum[o] = a[L.off_tsum + (j - i + W - 1)];
+        if (exp_num) exp_num[o] = (int64_t)llround(a[L.off_tnum + (j - i + W - 1)]);
+      }
+    }
+  }
+  return PUP_OK;
+}
+
+int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0, int W,
+                          unsigned flags, void* stream, int64_t* bytes_out, int64_t* nnz_out) {
+  if (!m || n_win < 0 || W <= 0 || !bytes_out) return fail(PUP_E_ARG, "pup_algorithmic_bytes: bad arguments");
+  DeviceGuard guard(m->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_algorithmic_bytes: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch tmp(st);
+  const int32_t *d_r0 = r0, *d_c0 = c0;
+  if (n_win > 0 && !is_device_ptr(r0)) {
+    int32_t* t;
+    CK(tmp.alloc((void**)&t, (size_t)n_win * 4));
+    CK(cudaMemcpyAsync(t, r0, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+    d_r0 = t;
+  }
+  if (n_win > 0 && !is_device_ptr(c0)) {
+    int32_t* t;
+    CK(tmp.alloc((void**)&t, (size_t)n_win * 4));
+    CK(cudaMemcpyAsync(t, c0, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+    d_c0 = t;
+  }
+  unsigned long long* d_out;
+  CK(tmp.alloc((void**)&d_out, 16));
+  CK(cudaMemsetAsync(d_out, 0, 16, st));
+  if (n_win > 0) {
+    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->ent, m->indptr, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_count_nnz", e);
+  }
+  unsigned long long h[2] = {0, 0};
+  CK(cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int64_t per_win = 16 + (int64_t)(W + 1) * 4;
+  if (m->weight) per_win += 16ll * W;
+  if (flags & PUP_F_COVERAGE) per_win += 16ll * W;
+  *bytes_out = (int64_t)h[1] * per_win + (int64_t)h[0] * 8;
+  if (nnz_out) *nnz_out = (int64_t)h[0];
+  return PUP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+"""Region sharding across GPUs: one process per GPU, one all-reduce of the accumulators.
+
+The reference parallelises over view regions with ``multiprocessing.Pool.starmap`` and merges the pickled
+per-region dictionaries with a serial ``reduce(sum_pups)`` (``coolpup.py:1502-1531``).  Here every rank (one per
+GPU, launched by ``torchrun``) takes a cost-balanced subset of the regions, accumulates them into its own packed
+fp64 accumulator in HBM and a single ``all_reduce(SUM)`` over NCCL (NVLink / NVSwitch) merges them; there is no
+other data-path collective because regions are independent.  With the ``gloo`` backend the same code runs on CPU
+tensors, which is how the sharding logic is tested without GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def lpt_assign(costs, n_ranks):
+    """Longest-processing-time-first assignment of items to ranks; returns rank per item."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load = [0.0] * n_ranks
+    owner = [0] * len(costs)
+    for i in order:
+        r = min(range(n_ranks), key=lambda k: (load[k], k))
+        owner[i] = r
+        load[r] += max(float(costs[i]), 1e-9)
+    return owner
+
+
+class RegionSharder:
+    """Deterministic region -> rank assignment + the collectives the pile-up needs."""
+
+    def __init__(self, rank=None, world_size=None, group=None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        if rank is None or world_size is None:
+            if not dist.is_initialized():
+                raise RuntimeError("torch.distributed is not initialised")
+            rank = dist.get_rank(group)
+            world_size = dist.get_world_size(group)
+        self.rank = rank
+        self.world_size = world_size
+
+    def my_items(self, items, cost_fn):
+        costs = [cost_fn(it) for it in items]
+        owner = lpt_assign(costs, self.world_size)
+        return [it for it, o in zip(items, owner) if o == self.rank]
+
+    def all_reduce(self, tensor):
+        if self.world_size > 1:
+            self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
+        return tensor
+
+    def merge_min(self, mapping):
+        """Union of per-rank ``{key: sortable}`` dictionaries keeping the minimum value per key."""
+        if self.world_size == 1:
+            return mapping
+        gathered = [None] * self.world_size
+        self._dist.all_gather_object(gathered, mapping, group=self.group)
+        out = {}
+        for m in gathered:
+            for k, v in m.items():
+                if k not in out or v < out[k]:
+                    out[k] = v
+        return out
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / MASTER_*)."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        return RegionSharder()
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend)
+    return RegionSharder()

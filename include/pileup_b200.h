@@ -1,0 +1,137 @@
+/*
+ * pileup_b200.h -- C ABI of the B200-native pile-up engine (libpileup_b200.so).
+ *
+ * The reference (open2c/coolpuppy 1.1.0) has no native plugin interface: the
+ * seam this library replaces is the Python callable that
+ * PileUpper.pileupsWithControl maps over view regions,
+ *
+ *     PileUpper.pileup_region(region1, region2, groupby, ...)      coolpup.py:1285-1358
+ *       = CoordCreator.pos_stream  -> window dicts                  coolpup.py:598-746
+ *       + PileUpper.get_data       -> region CSR                    coolpup.py:1024-1057
+ *       + PileUpper._stream_snips  -> slice / mask / divide         coolpup.py:1059-1191
+ *       + PileUpper.accumulate_stream + puputils._add_snip          coolpup.py:1236-1283, lib/puputils.py:12-41
+ *
+ * One call of pup_accumulate() does what one call of pileup_region() does for
+ * the windows of one region: it adds every window into per-slot accumulators.
+ * A "slot" is the host's dense id for (kind in {ROI, control}, group, flip);
+ * the host maps slots back to the reference's {"ROI": {group: pup}, "control":
+ * {...}} dictionary (coolpuppy_b200/coolpup.py).
+ *
+ * Conventions
+ *  - Plain C types only.  Every data pointer may point to HOST memory (pageable
+ *    or pinned) or to DEVICE memory on `device`; the library finds out with
+ *    cudaPointerGetAttributes.  Caller keeps ownership of everything it passes.
+ *  - All functions return PUP_OK (0) or a negative PUP_E_* code;
+ *    pup_last_error() returns a thread-local description of the last failure.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *    Work is enqueued on it; calls that touch host buffers synchronise the
+ *    stream before returning, calls on device buffers only enqueue.
+ *  - Thread-safety: re-entrant; no global mutable state besides the
+ *    thread-local error string.  A pup_region_t is immutable after creation
+ *    and may be shared by concurrent pup_accumulate() calls on different
+ *    streams of the same device.
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with PUP_E_NODEV.
+ */
+#ifndef PILEUP_B200_H
+#define PILEUP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PUP_OK 0
+#define PUP_E_ARG (-1)   /* bad argument (NULL, negative size, unsorted CSR, ...) */
+#define PUP_E_CUDA (-2)  /* a CUDA runtime call or kernel failed */
+#define PUP_E_OOM (-3)   /* device allocation failed */
+#define PUP_E_NODEV (-4) /* no usable CUDA device */
+
+/* flags for pup_accumulate() */
+#define PUP_F_OOE 1u      /* divide every pixel by expected[|col-row|]         (coolpup.py:1154-1156) */
+#define PUP_F_EXPCTRL 2u  /* also accumulate the bare expected block per window (coolpup.py:1135-1139, 1190-1191) */
+#define PUP_F_COVERAGE 4u /* accumulate cov_start / cov_end                      (coolpup.py:1151-1153) */
+#define PUP_F_NODIAG 8u   /* do NOT apply the signed diagonal mask (trans; unused by the cis path) */
+
+typedef struct pup_region pup_region_t; /* opaque: a region matrix prepared in HBM */
+
+int pup_abi_version(void);
+const char* pup_last_error(void);
+int pup_device_count(int* n_out);
+
+/*
+ * Upload and index one view region's contact matrix (replaces PileUpper.get_data +
+ * cooler.Cooler.matrix(sparse=True).fetch(region).tocsr(), coolpup.py:1053-1057, and the
+ * per-region bin vectors fetched at coolpup.py:1081-1098).
+ *
+ *   nb            number of bins of the region
+ *   nnz           stored pixels of the SYMMETRIC-FILLED matrix (both triangles), < 2^31
+ *   indptr[nb+1]  CSR row pointers, col[nnz] column ids sorted within each row, count[nnz] raw counts
+ *   weight[nb]    balancing weights or NULL for raw counts; NaN marks a masked bin.
+ *                 pixel value = (weight[row] * weight[col]) * count, as cooler computes it.
+ *   expected[nb]  expected value by |col-row| or NULL; entries beyond the table must be NaN
+ *   coverage[nb]  per-bin coverage (coverage_norm) or NULL
+ */
+int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
+                      const int32_t* count, const double* weight, const double* expected,
+                      const double* coverage, void* stream, pup_region_t** out);
+int pup_region_destroy(pup_region_t* region);
+/* bytes of HBM held by the region, and the algorithmic bytes of its pixels (8 per stored pixel) */
+int64_t pup_region_device_bytes(const pup_region_t* region);
+
+/*
+ * Accumulator buffer: n_slots * pup_acc_stride(W) doubles, caller-owned (host or device), caller-zeroed;
+ * pup_accumulate() only ever ADDS into it, so several regions (and, after an all-reduce, several GPUs)
+ * can share one buffer -- the analogue of reduce(sum_pups) at coolpup.py:1511-1531.
+ * The layout is linear in every field; decode it with pup_acc_export() AFTER all additions.
+ */
+int64_t pup_acc_stride(int W);
+
+/*
+ * Accumulate n_win windows of one region (replaces _stream_snips + accumulate_stream).
+ *   r0[i], c0[i]   region-relative first row / first column bin of window i (W x W bins)
+ *   slot[i]        accumulator slot in [0, n_slots)
+ * Windows not fully inside [0, nb) are skipped and not counted (coolpup.py:1111-1114).
+ * Pixels with (col - row) < ignore_diags are masked (signed, coolpup.py:1141-1149).
+ * n_valid_out (host pointer or NULL) receives the number of windows accumulated (forces a stream sync).
+ */
+int pup_accumulate(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0,
+                   const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags, double* acc,
+                   void* stream, int64_t* n_valid_out);
+
+/* One-shot convenience: pup_region_create + pup_accumulate + pup_region_destroy. */
+int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
+                          const int32_t* count, const double* weight, const double* expected,
+                          const double* coverage, int64_t n_win, const int32_t* r0, const int32_t* c0,
+                          const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags,
+                          double* acc, void* stream, int64_t* n_valid_out);
+
+/*
+ * Decode an accumulator buffer (host or device) into the reference's per-pile-up fields
+ * (lib/puputils.py:12-38).  All outputs are HOST arrays, any of them may be NULL:
+ *   sum[n_slots][W][W]      nansum of the snippets ("data")
+ *   num[n_slots][W][W]      number of finite contributions per pixel ("num")
+ *   n[n_slots]              number of windows ("n")
+ *   cov_start/cov_end[n_slots][W]
+ *   exp_sum/exp_num[n_slots][W][W]   sum / finite-count of the bare expected blocks (PUP_F_EXPCTRL)
+ */
+int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stream, double* sum, int64_t* num,
+                   int64_t* n, double* cov_start, double* cov_end, double* exp_sum, int64_t* exp_num);
+
+/* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
+ * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */
+int pup_last_launches(void);
+
+/*
+ * Exact algorithmic bytes of a window list on a prepared region:
+ *   sum over in-bounds windows of 16 + (W+1)*4 + 8*nnz_win (+16*W if balanced) (+16*W if coverage).
+ * Computed on the device by a separate counting kernel (not part of the timed path).
+ */
+int pup_algorithmic_bytes(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0, int W,
+                          unsigned flags, void* stream, int64_t* bytes_out, int64_t* nnz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PILEUP_B200_H */

@@ -588,3 +588,57 @@ def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_
     for k in ("st1", "st2", "kind", "flip"):
         log[k] = np.asarray(log[k], dtype=np.int64)
     return out, log
+
+
+# --------------------------------------------------------------------------- boundary-level oracle (C ABI)
+def oracle_accumulate(nb, indptr, col, count, weight, expected, coverage, r0, c0, slot, W, ignore_diags, n_slots,
+                      ooe=False, expctrl=False):
+    """What ``pup_accumulate`` + ``pup_acc_export`` must return, computed the reference's way.
+
+    Literal per-window restatement of ``_stream_snips`` (coolpup.py:1104-1157) and ``_add_snip``
+    (lib/puputils.py:12-38) over explicit window arrays: dense ``W x W`` slice of the symmetric CSR,
+    ``(w_row * w_col) * count`` balancing as cooler does it, NaN rows / columns for NaN weights, signed diagonal
+    mask, optional divide by ``expected[|col - row|]``, then ``nansum`` / ``isfinite`` accumulation per slot.
+    With ``expctrl`` the bare expected block of every window is accumulated too (coolpup.py:1135-1139).
+    """
+    indptr = np.asarray(indptr)
+    mat = sparse.csr_matrix((np.asarray(count, dtype=np.float64), np.asarray(col), indptr), shape=(nb, nb))
+    if weight is not None:
+        w = np.asarray(weight, dtype=np.float64)
+        coo = mat.tocoo()
+        coo.data = w[coo.row] * w[coo.col] * coo.data  # cooler: bias1[row] * bias2[col] * data
+        mat = coo.tocsr()
+        isnan = np.isnan(w)
+    else:
+        isnan = np.zeros(nb, dtype=bool)
+    out = {
+        "sum": np.zeros((n_slots, W, W)), "num": np.zeros((n_slots, W, W), dtype=np.int64),
+        "n": np.zeros(n_slots, dtype=np.int64), "cov_start": np.zeros((n_slots, W)), "cov_end": np.zeros((n_slots, W)),
+        "exp_sum": np.zeros((n_slots, W, W)), "exp_num": np.zeros((n_slots, W, W), dtype=np.int64),
+    }
+    for i in range(len(r0)):
+        s1, s2, s = int(r0[i]), int(c0[i]), int(slot[i])
+        if s1 < 0 or s1 + W > nb or s2 < 0 or s2 + W > nb:
+            continue
+        data = mat[s1 : s1 + W, s2 : s2 + W].toarray().astype(float)
+        data[isnan[s1 : s1 + W], :] = np.nan
+        data[:, isnan[s2 : s2 + W]] = np.nan
+        ii = np.arange(s1, s1 + W)[:, None]
+        jj = np.arange(s2, s2 + W)[None, :]
+        data[(jj - ii) < ignore_diags] = np.nan
+        if expected is not None and (ooe or expctrl):
+            e = np.asarray(expected)[np.abs(jj - ii)]
+            if ooe:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    data = data / e
+            else:
+                out["exp_sum"][s] = np.nansum([out["exp_sum"][s], e], axis=0)
+                out["exp_num"][s] += np.isfinite(e)
+        out["sum"][s] = np.nansum([out["sum"][s], data], axis=0)
+        out["num"][s] += np.isfinite(data)
+        out["n"][s] += 1
+        if coverage is not None:
+            cv = np.asarray(coverage, dtype=float)
+            out["cov_start"][s] = np.nansum([out["cov_start"][s], cv[s1 : s1 + W]], axis=0)
+            out["cov_end"][s] = np.nansum([out["cov_end"][s], cv[s2 : s2 + W]], axis=0)
+    return out

@@ -1,0 +1,162 @@
+"""numpy emulation of the C ABI (`include/pileup_b200.h`) -- TEST INFRASTRUCTURE ONLY.
+
+It mirrors what the CUDA kernels compute, *including* the raw accumulator layout and the `num` decomposition
+(`n_fast - rowbad - colbad + tile`), so that the host pipeline
+(`coolpuppy_b200/coolpup.py`: window generation, slot assignment, flip merging, final normalisation, DataFrame
+schema) and the decomposition itself can be checked against the golden vectors on a machine without a GPU.
+Tests install it with `monkeypatch` over `coolpuppy_b200._native`; the product never imports this module.
+"""
+import numpy as np
+
+from coolpuppy_b200 import _native
+
+F_OOE, F_EXPCTRL, F_COVERAGE, F_NODIAG = 1, 2, 4, 8
+
+
+def layout(W):
+    w2 = W * W
+    L = dict(w2=w2, num=w2, rb=2 * w2)
+    L["cb"] = L["rb"] + W
+    L["covs"] = L["cb"] + W
+    L["cove"] = L["covs"] + W
+    L["tsum"] = L["cove"] + W
+    L["tnum"] = L["tsum"] + 2 * W
+    L["n"] = L["tnum"] + 2 * W
+    L["nfast"] = L["n"] + 1
+    L["stride"] = L["n"] + 8
+    return L
+
+
+class EmuRegion:
+    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, stream=0):
+        self.nb = int(nb)
+        self.indptr, self.col, self.count = np.asarray(indptr), np.asarray(col), np.asarray(count)
+        self.weight, self.expected, self.coverage = weight, expected, coverage
+        self.bad = np.isnan(weight) if weight is not None else np.zeros(nb, dtype=bool)
+        if expected is not None:
+            self.ebad = np.isnan(expected) | (expected == 0)
+        else:
+            self.ebad = np.zeros(nb, dtype=bool)
+        self.ebadpre = np.concatenate([[0], np.cumsum(self.ebad)])
+        self.balanced = weight is not None
+        self.device_bytes = 0
+
+    def _slow(self, r0, c0, W, igd, flags):
+        D0 = c0 - r0
+        dmin, dmax = D0 - (W - 1), D0 + (W - 1)
+        if not (flags & F_NODIAG) and dmin < igd:
+            return True
+        if flags & F_OOE:
+            if dmin >= 0:
+                a, b = dmin, dmax
+            elif dmax <= 0:
+                a, b = -dmax, -dmin
+            else:
+                a, b = 0, max(-dmin, dmax)
+            b = min(b, self.nb - 1)
+            a = min(a, b)
+            return self.ebadpre[b + 1] - self.ebadpre[a] > 0
+        return False
+
+    def accumulate(self, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream=0, want_n_valid=False):
+        L = layout(W)
+        a = acc.numpy() if hasattr(acc, "numpy") else acc
+        a = a.reshape(n_slots, L["stride"])
+        nv = 0
+        nb = self.nb
+        m = np.arange(-(W - 1), W)
+        for i in range(len(r0)):
+            r, c, s = int(r0[i]), int(c0[i]), int(slot[i])
+            if r < 0 or c < 0 or r + W > nb or c + W > nb or s < 0 or s >= n_slots:
+                continue
+            nv += 1
+            A = a[s]
+            slow = self._slow(r, c, W, ignore_diags, flags)
+            A[L["n"]] += 1
+            if not slow:
+                A[L["nfast"]] += 1
+                A[L["rb"] : L["rb"] + W] += self.bad[r : r + W]
+                A[L["cb"] : L["cb"] + W] += self.bad[c : c + W]
+            if flags & F_COVERAGE:
+                A[L["covs"] : L["covs"] + W] += np.nan_to_num(self.coverage[r : r + W], nan=0.0, posinf=np.inf, neginf=-np.inf)
+                A[L["cove"] : L["cove"] + W] += np.nan_to_num(self.coverage[c : c + W], nan=0.0, posinf=np.inf, neginf=-np.inf)
+            if flags & F_EXPCTRL:
+                e = self.expected[np.abs(c - r + m)]
+                A[L["tsum"] : L["tsum"] + 2 * W - 1] += np.where(np.isnan(e), 0.0, e)
+                A[L["tnum"] : L["tnum"] + 2 * W - 1] += np.isfinite(e)
+            S = A[: L["w2"]].reshape(W, W)
+            N = A[L["num"] : L["num"] + L["w2"]].reshape(W, W)
+            for di in range(W):
+                row = r + di
+                rbad = bool(self.bad[row])
+                if not rbad:
+                    lo, hi = self.indptr[row], self.indptr[row + 1]
+                    cols = self.col[lo:hi]
+                    k0, k1 = np.searchsorted(cols, c), np.searchsorted(cols, c + W)
+                    cc = cols[k0:k1]
+                    v = self.count[lo + k0 : lo + k1].astype(np.float64)
+                    d = cc - row
+                    keep = np.ones(len(cc), dtype=bool) if (flags & F_NODIAG) else d >= ignore_diags
+                    if self.balanced:
+                        v = (self.weight[row] * self.weight[cc]) * v
+                    if flags & F_OOE:
+                        with np.errstate(divide="ignore", invalid="ignore"):
+                            v = v / self.expected[np.abs(d)]
+                    keep &= ~np.isnan(v)
+                    np.add.at(S[di], cc[keep] - c, v[keep])
+                if slow:
+                    cs = np.arange(c, c + W)
+                    d = cs - row
+                    ok = np.full(W, not rbad) & ~self.bad[cs]
+                    if not (flags & F_NODIAG):
+                        ok &= d >= ignore_diags
+                    if flags & F_OOE:
+                        ok &= ~self.ebad[np.abs(d)]
+                    N[di] += ok
+                elif rbad:
+                    N[di] += self.bad[c : c + W]
+        return nv if want_n_valid else None
+
+    def algorithmic_bytes(self, r0, c0, W, flags=0, stream=0):
+        return 0, 0
+
+    def close(self):
+        pass
+
+
+def emu_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):
+    L = layout(W)
+    a = (acc.numpy() if hasattr(acc, "numpy") else acc).reshape(n_slots, L["stride"])
+    out = {"sum": a[:, : L["w2"]].reshape(n_slots, W, W).copy(), "n": np.rint(a[:, L["n"]]).astype(np.int64)}
+    numt = a[:, L["num"] : L["num"] + L["w2"]].reshape(n_slots, W, W)
+    rb = a[:, L["rb"] : L["rb"] + W]
+    cb = a[:, L["cb"] : L["cb"] + W]
+    out["num"] = np.rint(a[:, L["nfast"]][:, None, None] - rb[:, :, None] - cb[:, None, :] + numt).astype(np.int64)
+    if want_cov:
+        out["cov_start"] = a[:, L["covs"] : L["covs"] + W].copy()
+        out["cov_end"] = a[:, L["cove"] : L["cove"] + W].copy()
+    if want_expected:
+        i = np.arange(W)
+        idx = i[None, :] - i[:, None] + W - 1
+        out["exp_sum"] = a[:, L["tsum"] : L["tsum"] + 2 * W][:, idx]
+        out["exp_num"] = np.rint(a[:, L["tnum"] : L["tnum"] + 2 * W][:, idx]).astype(np.int64)
+    return out
+
+
+def install(monkeypatch):
+    """Route coolpuppy_b200._native's device entry points to the emulator (tests only)."""
+    import torch
+
+    monkeypatch.setattr(_native, "Region", EmuRegion)
+    monkeypatch.setattr(_native, "acc_export", emu_export)
+    monkeypatch.setattr(_native, "require_device", lambda: None)
+    monkeypatch.setattr(_native, "alloc_accumulator", lambda n, device: torch.zeros(int(n), dtype=torch.float64))
+    monkeypatch.setattr(_native, "current_stream", lambda device: 0)
+    monkeypatch.setattr(_native, "acc_stride", lambda W: layout(int(W))["stride"])
+
+    class _L:
+        @staticmethod
+        def pup_last_launches():
+            return 0
+
+    monkeypatch.setattr(_native, "lib", lambda: _L)

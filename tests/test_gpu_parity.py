@@ -1,0 +1,217 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI."""
+import warnings
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from synth import random_region, random_windows
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # BASELINE.json north_star: "within 1e-6 relative"; observed differences are ~1e-15 (fp64 sum order)
+
+
+def _cuda():
+    from coolpuppy_b200 import _native
+
+    if _native.device_count() < 1:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    return _native
+
+
+def _compare_rows(pups, name):
+    from oracle.pileup_oracle import key_repr
+
+    z, _ = gu.load_golden(name)
+    if "group" in pups.columns:
+        keys = [key_repr(g) for g in pups["group"]]
+    else:
+        keys = [repr((r.chrom, int(r.start), int(r.end))) for r in pups.itertuples()]
+    assert keys == [str(k) for k in z["row_keys"]], "row keys / order differ from the reference"
+    assert list(pups.columns) == [str(c) for c in z["columns"]], "DataFrame schema differs from the reference"
+    for i in range(len(keys)):
+        g = {f.split(".", 1)[1]: z[f] for f in z.files if f.startswith(f"row{i}.")}
+        a = np.asarray(pups["data"].iloc[i], dtype=float)
+        b = g["data"]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f"{name} row {keys[i]}: NaN pattern differs"
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=RTOL, atol=0)
+        assert int(pups["n"].iloc[i]) == int(g["n"])
+        assert np.array_equal(np.asarray(pups["num"].iloc[i]), g["num"])
+        if "control_n" in g:
+            assert int(pups["control_n"].iloc[i]) == int(g["control_n"])
+            assert np.array_equal(np.asarray(pups["control_num"].iloc[i]), g["control_num"])
+
+
+@pytest.mark.parametrize("name", [n for n in gu.all_cases() if "stripes" not in n])
+def test_golden_case_through_cuda(name):
+    """coolpuppy_b200.pileup() on the GPU == the real reference's stored output (tests/golden)."""
+    _cuda()
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, feats, **kw)
+    _compare_rows(pups, name)
+
+
+MODES = {
+    "raw": dict(bal=False, flags=0),
+    "balanced": dict(bal=True, flags=0),
+    "balanced_ooe": dict(bal=True, flags=1, exp=True),
+    "raw_ooe": dict(bal=False, flags=1, exp=True),
+    "balanced_expctrl": dict(bal=True, flags=2, exp=True),
+    "raw_coverage": dict(bal=False, flags=4, cov=True),
+}
+
+
+def _check_against_oracle(nv, out, ref):
+    assert nv == int(ref["n"].sum())
+    assert np.array_equal(out["n"], ref["n"])
+    assert np.array_equal(out["num"], ref["num"])
+    assert np.array_equal(np.isinf(out["sum"]), np.isinf(ref["sum"]))
+    m = np.isfinite(ref["sum"])
+    np.testing.assert_allclose(out["sum"][m], ref["sum"][m], rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(300, 21, 30, 500, 3), (700, 83, 200, 300, 2), (64, 5, 4, 200, 7),
+                                                      (900, 203, 400, 60, 2), (2000, 21, 3, 3000, 40)])
+@pytest.mark.parametrize("memory", ["host", "device"])
+def test_kernel_vs_oracle_random(mode, nb, W, dens, nwin, n_slots, memory):
+    """pup_accumulate on seeded random CSR + windows == the dense per-window restatement, host and device buffers."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    cfg = MODES[mode]
+    ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb + W, nan_frac=0.05, with_expected=True, with_cov=True)
+    weight = w if cfg["bal"] else None
+    expected = e if cfg.get("exp") else None
+    coverage = cov if cfg.get("cov") else None
+    r0, c0, sl = random_windows(nb, W, nwin, n_slots, seed=7 * nb + W)
+    ref = oracle_accumulate(nb, ip, col, cnt, weight, expected, coverage, r0, c0, sl, W, 2, n_slots,
+                            ooe=cfg["flags"] == 1, expctrl=cfg["flags"] == 2)
+    stride = nat.acc_stride(W)
+    if memory == "host":
+        acc = np.zeros(n_slots * stride)
+        nv = nat.accumulate_region(0, nb, ip, col, cnt, weight, expected, coverage, r0, c0, sl, W, 2, n_slots,
+                                   cfg["flags"], acc)
+        out = nat.acc_export(acc, W, n_slots, want_expected=True, want_cov=True)
+    else:
+        import torch
+
+        dev = torch.device("cuda", 0)
+        t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        tens = [t(x) for x in (ip, col, cnt, weight, expected, coverage, r0, c0, sl)]
+        acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], tens[5], stream=stream)
+        # two calls into the same accumulator: the buffer is purely additive
+        half = nwin // 2
+        nv = reg.accumulate(tens[6][:half].contiguous(), tens[7][:half].contiguous(), tens[8][:half].contiguous(), W, 2,
+                            n_slots, cfg["flags"], acc, stream=stream, want_n_valid=True)
+        nv += reg.accumulate(tens[6][half:].contiguous(), tens[7][half:].contiguous(), tens[8][half:].contiguous(), W, 2,
+                             n_slots, cfg["flags"], acc, stream=stream, want_n_valid=True)
+        out = nat.acc_export(acc, W, n_slots, device=0, stream=stream, want_expected=True, want_cov=True)
+        reg.close()
+    _check_against_oracle(nv, out, ref)
+    if cfg["flags"] == 2:
+        assert np.array_equal(out["exp_num"], ref["exp_num"])
+        np.testing.assert_allclose(out["exp_sum"], ref["exp_sum"], rtol=RTOL)
+    if cfg.get("cov"):
+        np.testing.assert_allclose(out["cov_start"], ref["cov_start"], rtol=RTOL)
+        np.testing.assert_allclose(out["cov_end"], ref["cov_end"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("ignore_diags", [0, 2, 5, -1000000])
+def test_ignore_diags_variants(ignore_diags):
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    nb, W, n_slots = 400, 11, 2
+    ip, col, cnt, w, e, cov = random_region(nb, 40, seed=3, nan_frac=0.1, with_expected=True)
+    r0, c0, sl = random_windows(nb, W, 800, n_slots, seed=5, near_diag_frac=0.7)
+    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, ignore_diags, n_slots, ooe=True)
+    acc = np.zeros(n_slots * nat.acc_stride(W))
+    nv = nat.accumulate_region(0, nb, ip, col, cnt, w, e, None, r0, c0, sl, W, ignore_diags, n_slots, 1, acc)
+    _check_against_oracle(nv, nat.acc_export(acc, W, n_slots), ref)
+
+
+def test_empty_and_degenerate_inputs():
+    nat = _cuda()
+    nb, W = 50, 5
+    ip, col, cnt, w, e, cov = random_region(nb, 5, seed=1, nan_frac=0.0)
+    acc = np.zeros(nat.acc_stride(W))
+    z = np.zeros(0, dtype=np.int32)
+    assert nat.accumulate_region(0, nb, ip, col, cnt, None, None, None, z, z, z, W, 2, 1, 0, acc) == 0
+    assert not acc.any()
+    # all windows out of bounds
+    r0 = np.array([-1, 48, 10], dtype=np.int32)
+    c0 = np.array([3, 3, 46], dtype=np.int32)
+    sl = np.zeros(3, dtype=np.int32)
+    assert nat.accumulate_region(0, nb, ip, col, cnt, None, None, None, r0, c0, sl, W, 2, 1, 0, acc) == 0
+    assert not acc.any()
+    # empty matrix
+    ip0 = np.zeros(nb + 1, dtype=np.int32)
+    r0 = np.array([0, 10], dtype=np.int32)
+    c0 = np.array([20, 30], dtype=np.int32)
+    sl = np.zeros(2, dtype=np.int32)
+    nv = nat.accumulate_region(0, nb, ip0, z, z, None, None, None, r0, c0, sl, W, 2, 1, 0, acc)
+    out = nat.acc_export(acc, W, 1)
+    assert nv == 2 and out["n"][0] == 2 and not out["sum"].any() and (out["num"] == 2).all()
+    # error reporting
+    with pytest.raises(nat.NativeError):
+        nat.accumulate_region(0, nb, ip, col, cnt, None, None, None, r0, c0, sl, W, 2, 1, 1, acc)  # OOE without expected
+
+
+def test_linearity_and_permutation_large():
+    """Size-independent properties on a matrix larger than L2: windows permuted / split across calls give the same
+    accumulators, and duplicating every window doubles them."""
+    nat = _cuda()
+    import torch
+
+    dev = torch.device("cuda", 0)
+    from coolpuppy_b200.synthetic import synthetic_region
+
+    nb, W, n_slots = 12000, 83, 4
+    reg_t = synthetic_region(nb, depth=500.0, seed=11, device=dev, nan_frac=0.03)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    reg = nat.Region(0, nb, reg_t["indptr"], reg_t["col"], reg_t["count"], reg_t["weight"], reg_t["expected"], None,
+                     stream=stream)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = 200_000
+    r0 = torch.randint(0, nb - W, (n,), generator=g, dtype=torch.int32)
+    c0 = torch.clamp(r0 + torch.randint(0, 3000, (n,), generator=g, dtype=torch.int32), max=nb - W)
+    sl = torch.randint(0, n_slots, (n,), generator=g, dtype=torch.int32)
+    r0, c0, sl = r0.to(dev), c0.to(dev), sl.to(dev)
+    stride = nat.acc_stride(W)
+
+    def run(parts):
+        acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
+        for idx in parts:
+            reg.accumulate(r0[idx].contiguous(), c0[idx].contiguous(), sl[idx].contiguous(), W, 2, n_slots, 1, acc, stream=stream)
+        return nat.acc_export(acc, W, n_slots, device=0, stream=stream)
+
+    base = run([torch.arange(n, device=dev)])
+    perm = torch.randperm(n, generator=g).to(dev)
+    split = run([perm[: n // 3], perm[n // 3 :]])
+    dup = run([torch.arange(n, device=dev), perm])
+    assert base["n"].sum() == n
+    assert np.array_equal(base["num"], split["num"]) and np.array_equal(base["n"], split["n"])
+    np.testing.assert_allclose(split["sum"], base["sum"], rtol=1e-9)
+    assert np.array_equal(2 * base["num"], dup["num"])
+    np.testing.assert_allclose(dup["sum"], 2 * base["sum"], rtol=1e-9)
+    # spot-check a sample of the same windows against the dense oracle
+    from oracle.pileup_oracle import oracle_accumulate
+
+    k = 300
+    h = lambda t: t.cpu().numpy()
+    ref = oracle_accumulate(nb, h(reg_t["indptr"]), h(reg_t["col"]), h(reg_t["count"]), h(reg_t["weight"]),
+                            h(reg_t["expected"]), None, h(r0[:k]), h(c0[:k]), h(sl[:k]), W, 2, n_slots, ooe=True)
+    acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
+    reg.accumulate(r0[:k].contiguous(), c0[:k].contiguous(), sl[:k].contiguous(), W, 2, n_slots, 1, acc, stream=stream)
+    out = nat.acc_export(acc, W, n_slots, device=0, stream=stream)
+    _check_against_oracle(k, out, ref)
+    reg.close()
