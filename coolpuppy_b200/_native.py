@@ -21,7 +21,7 @@ _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200
 SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_destroy",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
-    "pup_last_launches", "pup_algorithmic_bytes",
+    "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read",
 ]
 
 
@@ -55,6 +55,8 @@ def lib():
                                         C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pup_algorithmic_bytes.argtypes = [vp, i64, vp, vp, C.c_int, u32, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.pup_timing_enable.argtypes = [C.c_int]
+    L.pup_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     _LIB = L
     return L
 
@@ -163,6 +165,18 @@ def accumulate_region(device, nb, indptr, col, count, weight, expected, coverage
                                       ptr(slot), int(W), int(ignore_diags), int(n_slots), int(flags), ptr(acc),
                                       stream, C.byref(nv)))
     return nv.value
+
+
+def timing_enable(on=True):
+    check(lib().pup_timing_enable(1 if on else 0))
+
+
+def timing_read(reset=True):
+    """{phase: (milliseconds, spans)} for phases 'plan', 'vector', 'main' recorded since the last reset."""
+    ms = (C.c_double * 3)()
+    cnt = (C.c_int * 3)()
+    check(lib().pup_timing_read(ms, cnt, 1 if reset else 0))
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(("plan", "vector", "main"))}
 
 
 def acc_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):

@@ -31,6 +31,32 @@ namespace {
 thread_local std::string g_err;
 thread_local int g_launches = 0;
 
+// optional per-phase device timing (bench.py): CUDA events recorded on the caller's stream
+struct TimedSpan {
+  int tag;  // 0 sort/plan, 1 vector kernel, 2 main kernel
+  cudaEvent_t a, b;
+};
+thread_local bool g_timing = false;
+thread_local std::vector<TimedSpan> g_spans;
+
+struct SpanGuard {
+  bool on;
+  TimedSpan sp;
+  cudaStream_t st;
+  SpanGuard(int tag, cudaStream_t s) : on(g_timing), st(s) {
+    if (!on) return;
+    sp.tag = tag;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+  }
+  ~SpanGuard() {
+    if (!on) return;
+    cudaEventRecord(sp.b, st);
+    g_spans.push_back(sp);
+  }
+};
+
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   char buf[512];
   if (e != cudaSuccess)
@@ -93,7 +119,7 @@ bool is_device_ptr(const void* p) {
 
 constexpr int NT = 512;   // threads per CTA of the main kernel
 constexpr int VT = 512;   // threads per CTA of the vector kernel
-constexpr int VCH = 1024; // windows per CTA step of the vector kernel
+constexpr int VCH = 256;  // windows per CTA step of the vector kernel
 
 // ------------------------------------------------------------------------------------------ accumulator layout
 struct AccLayout {
@@ -284,7 +310,9 @@ struct VecParams {
   double* acc;
 };
 
-__global__ void __launch_bounds__(VT) k_vector(const VecParams p) {
+constexpr int VU = 4;  // windows in flight per thread of the vector kernel
+
+__global__ void k_vector(const VecParams p) {
   const int n = __ldg(&p.slot_start[p.n_slots]);
   const int W = p.ctx.W;
   const AccLayout L(W);
@@ -293,7 +321,7 @@ __global__ void __launch_bounds__(VT) k_vector(const VecParams p) {
   const bool cov = (p.ctx.flags & PUP_F_COVERAGE) && p.coverage != nullptr;
   const bool ectl = (p.ctx.flags & PUP_F_EXPCTRL) && p.expected != nullptr;
   for (int base = blockIdx.x * VCH; base < n; base += gridDim.x * VCH) {
-    int end = min(base + VCH, n);
+    const int end = min(base + VCH, n);
     int cur = -1;
     double rb = 0, cb = 0, cs = 0, ce = 0, ts = 0, tn = 0, nn = 0, nf = 0;
     auto flush = [&]() {
@@ -315,35 +343,59 @@ __global__ void __launch_bounds__(VT) k_vector(const VecParams p) {
       }
       rb = cb = cs = ce = ts = tn = nn = nf = 0;
     };
-    for (int w = base; w < end; ++w) {
-      int slot, r0, c0;
-      decode_key(__ldg(&p.keys[w]), p.ctx.pb, slot, r0, c0);
-      if (slot != cur) {
-        flush();
-        cur = slot;
-      }
-      bool slow = window_is_slow(p.ctx, r0, c0);
-      if (t == 0) {
-        nn += 1;
-        if (!slow) nf += 1;
-      }
-      if (t < W) {
-        if (has_bad && !slow) {
-          rb += p.bad[r0 + t];
-          cb += p.bad[c0 + t];
+    for (int w = base; w < end; w += VU) {
+      int slot[VU];
+      bool slow[VU];
+      unsigned br[VU], bc[VU];
+      double ca[VU], cbv[VU], ev[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) {
+        slot[u] = -1;
+        br[u] = bc[u] = 0;
+        ca[u] = cbv[u] = 0.0;
+        ev[u] = 0.0;
+        slow[u] = false;
+        if (w + u < end) {
+          int r0, c0;
+          decode_key(__ldg(&p.keys[w + u]), p.ctx.pb, slot[u], r0, c0);
+          slow[u] = window_is_slow(p.ctx, r0, c0);
+          if (t < W) {
+            if (has_bad && !slow[u]) {
+              br[u] = p.bad[r0 + t];
+              bc[u] = p.bad[c0 + t];
+            }
+            if (cov) {
+              ca[u] = __ldg(&p.coverage[r0 + t]);
+              cbv[u] = __ldg(&p.coverage[c0 + t]);
+            }
+          }
+          if (ectl && t < 2 * W - 1) {
+            int d = c0 - r0 + t - (W - 1);
+            ev[u] = __ldg(&p.expected[d < 0 ? -d : d]);
+          }
         }
-        if (cov) {
-          double a = __ldg(&p.coverage[r0 + t]), b = __ldg(&p.coverage[c0 + t]);
-          if (!isnan(a)) cs += a;
-          if (!isnan(b)) ce += b;
-        }
       }
-      if (ectl && t < 2 * W - 1) {
-        int d = c0 - r0 + t - (W - 1);
-        d = d < 0 ? -d : d;
-        double e = __ldg(&p.expected[d]);
-        if (!isnan(e)) ts += e;
-        if (isfinite(e)) tn += 1;
+#pragma unroll
+      for (int u = 0; u < VU; ++u) {
+        if (slot[u] < 0) continue;
+        if (slot[u] != cur) {
+          flush();
+          cur = slot[u];
+        }
+        if (t == 0) {
+          nn += 1;
+          if (!slow[u]) nf += 1;
+        }
+        rb += br[u];
+        cb += bc[u];
+        if (cov && t < W) {
+          if (!isnan(ca[u])) cs += ca[u];
+          if (!isnan(cbv[u])) ce += cbv[u];
+        }
+        if (ectl && t < 2 * W - 1) {
+          if (!isnan(ev[u])) ts += ev[u];
+          if (isfinite(ev[u])) tn += 1;
+        }
       }
     }
     flush();
@@ -372,7 +424,9 @@ struct MainParams {
   int* counter;
 };
 
-template <int S, bool BAL, bool OOE>
+constexpr int MAXOWN_LIMIT = 4;  // tile rows one row-group can own (Wb <= MAXOWN * row-groups per CTA)
+
+template <int S, bool BAL, bool OOE, int MAXOWN>
 __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = p.ctx.W;
@@ -393,7 +447,9 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
   const bool nodiag = p.ctx.flags & PUP_F_NODIAG;
   const int igd = p.ctx.ignore_diags;
   const int nb = p.ctx.nb;
+  const int pb = p.ctx.pb;
   const int tile = Wb * W;
+  const int2 SENTINEL = make_int2(0x7fffffff, 0);
 
   for (int i = threadIdx.x; i < tile; i += NT) {
     sumT[i] = 0.0;
@@ -461,54 +517,109 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
     const int row_lo = band * Wb;
     const int nrows = min(Wb, W - row_lo);
     const int w_lo = s_lo, w_hi = s_hi;
+    const int nown = (g < nrows) ? (nrows - 1 - g) / NG + 1 : 0;  // tile rows dl = g + j * NG owned by this group
 
-    for (int w = w_lo; w < w_hi; ++w) {
-      int kslot, r0, c0;
-      decode_key(__ldg(&p.keys[w]), p.ctx.pb, kslot, r0, c0);
-      const bool slow = window_is_slow(p.ctx, r0, c0);
-      const int bcol = (c0 >> p.lb);
-      for (int dl = g; dl < nrows; dl += NG) {
-        const int r = r0 + row_lo + dl;
-        double* trow = sumT + dl * W;
-        int* nrow = numT + dl * W;
-        bool rbad = false;
-        double wr = 1.0;
-        if (BAL) {
-          wr = __ldg(&p.weight[r]);
-          rbad = isnan(wr);
-        }
-        if (!rbad) {
-          int idx = __ldg(&p.bucket[(size_t)bcol * nb + r]) + ls;
-          const int pend = __ldg(&p.indptr[r + 1]);
-          for (; idx < pend; idx += S) {
-            const int2 e = __ldg(&p.ent[idx]);
-            const int dj = e.x - c0;
-            if (dj >= W) break;
-            if (dj < 0) continue;
-            const int d = e.x - r;
-            if (!nodiag && d < igd) continue;
-            double v = (double)e.y;
-            if (BAL) v = (wr * __ldg(&p.weight[e.x])) * v;
-            if (OOE) v = v / __ldg(&p.expected[d < 0 ? -d : d]);
-            if (v != v) continue;
-            trow[dj] += v;
+    if (nown > 0) {
+      // ---- pass 1: sums.  Row pointers of window w+1 are fetched while window w is being accumulated.
+      int n_idx[MAXOWN], n_end[MAXOWN];
+      int n_r0 = 0, n_c0 = 0;
+      auto fetch_ptrs = [&](int w) {
+        int kslot;
+        decode_key(__ldg(&p.keys[w]), pb, kslot, n_r0, n_c0);
+        const int rbase = n_r0 + row_lo + g;
+        const int32_t* bk = p.bucket + (size_t)(n_c0 >> p.lb) * nb + rbase;
+#pragma unroll
+        for (int j = 0; j < MAXOWN; ++j) {
+          if (j < nown) {
+            n_idx[j] = __ldg(bk + j * NG) + ls;
+            n_end[j] = __ldg(&p.indptr[rbase + j * NG + 1]);
+          } else {
+            n_idx[j] = 0;
+            n_end[j] = 0;
           }
         }
-        if (slow) {
-          for (int dj = ls; dj < W; dj += S) {
-            const int c = c0 + dj;
-            const int d = c - r;
-            bool ok = !rbad;
-            if (BAL) ok = ok && !__ldg(&p.bad[c]);
-            if (!nodiag) ok = ok && (d >= igd);
-            if (OOE) ok = ok && !__ldg(&p.ebad[d < 0 ? -d : d]);
-            if (ok) nrow[dj] += 1;
-          }
-        } else if (BAL && rbad) {
-          for (int dj = ls; dj < W; dj += S)
-            if (__ldg(&p.bad[c0 + dj])) nrow[dj] += 1;
+      };
+      fetch_ptrs(w_lo);
+      for (int w = w_lo; w < w_hi; ++w) {
+        int idx[MAXOWN], pend[MAXOWN];
+        double wr[MAXOWN];
+        int2 e[MAXOWN];
+        const int r0 = n_r0, c0 = n_c0;
+#pragma unroll
+        for (int j = 0; j < MAXOWN; ++j) {
+          idx[j] = n_idx[j];
+          pend[j] = n_end[j];
+          e[j] = (idx[j] < pend[j]) ? __ldg(&p.ent[idx[j]]) : SENTINEL;
+          wr[j] = (BAL && j < nown) ? __ldg(&p.weight[r0 + row_lo + g + j * NG]) : 1.0;
         }
-        __syncwarp(gmask);
+        if (w + 1 < w_hi) fetch_ptrs(w + 1);
+#pragma unroll
+        for (int j = 0; j < MAXOWN; ++j) {
+          if (j < nown) {
+            const int dl = g + j * NG;
+            const int r = r0 + row_lo + dl;
+            double* trow = sumT + dl * W;
+            int2 ce = e[j];
+            int id = idx[j];
+            const int pe = pend[j];
+            const double w_r = wr[j];
+            if (!(BAL && isnan(w_r))) {
+              for (;;) {
+                const int dj = ce.x - c0;
+                if (dj >= W) break;
+                const int nid = id + S;
+                // dense rows need the next S entries too: start that load before touching shared memory
+                int2 ne = SENTINEL;
+                if (nid < pe && dj + S < W + S / 2) ne = __ldg(&p.ent[nid]);
+                if (dj >= 0) {
+                  const int d = ce.x - r;
+                  if (nodiag || d >= igd) {
+                    double v = (double)ce.y;
+                    if (BAL) v = (w_r * __ldg(&p.weight[ce.x])) * v;
+                    if (OOE) v = v / __ldg(&p.expected[d < 0 ? -d : d]);
+                    if (v == v) trow[dj] += v;
+                  }
+                }
+                if (nid >= pe) break;
+                if (ne.x == 0x7fffffff) ne = __ldg(&p.ent[nid]);
+                ce = ne;
+                id = nid;
+              }
+            }
+            __syncwarp(gmask);
+          }
+        }
+      }
+
+      // ---- pass 2: pixel counts that are not covered by the vector kernel's closed form
+      for (int w = w_lo; w < w_hi; ++w) {
+        int kslot, r0, c0;
+        decode_key(__ldg(&p.keys[w]), pb, kslot, r0, c0);
+        const bool slow = window_is_slow(p.ctx, r0, c0);
+        if (!slow && !BAL) continue;
+#pragma unroll
+        for (int j = 0; j < MAXOWN; ++j) {
+          if (j < nown) {
+            const int dl = g + j * NG;
+            const int r = r0 + row_lo + dl;
+            int* nrow = numT + dl * W;
+            const bool rbad = BAL && __ldg(&p.bad[r]);
+            if (slow) {
+              for (int dj = ls; dj < W; dj += S) {
+                const int c = c0 + dj;
+                const int d = c - r;
+                bool ok = !rbad;
+                if (BAL) ok = ok && !__ldg(&p.bad[c]);
+                if (!nodiag) ok = ok && (d >= igd);
+                if (OOE) ok = ok && !__ldg(&p.ebad[d < 0 ? -d : d]);
+                if (ok) nrow[dj] += 1;
+              }
+            } else if (rbad) {
+              for (int dj = ls; dj < W; dj += S)
+                if (__ldg(&p.bad[c0 + dj])) nrow[dj] += 1;
+            }
+          }
+        }
       }
     }
   }
@@ -561,13 +672,14 @@ int ilog2_ceil(int64_t v) {
   return b;
 }
 
-template <int S>
-cudaError_t launch_main(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe) {
+template <int S, int MO>
+cudaError_t launch_main2(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe, int* occ) {
 #define PUP_LAUNCH(B, O)                                                                                  \
   do {                                                                                                    \
-    auto kern = k_pileup_main<S, B, O>;                                                                   \
+    auto kern = k_pileup_main<S, B, O, MO>;                                                               \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
+    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, NT, smem);                   \
     kern<<<grid, NT, smem, st>>>(p);                                                                      \
     return cudaGetLastError();                                                                            \
   } while (0)
@@ -578,20 +690,16 @@ cudaError_t launch_main(const MainParams& p, int grid, size_t smem, cudaStream_t
 #undef PUP_LAUNCH
 }
 
+// occ != nullptr: only query the occupancy; else launch
 template <int S>
-cudaError_t main_occupancy(int* blocks, size_t smem, bool bal, bool ooe) {
-#define PUP_OCC(B, O)                                                                                     \
-  do {                                                                                                    \
-    auto kern = k_pileup_main<S, B, O>;                                                                   \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return e;                                                                       \
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kern, NT, smem);                         \
-  } while (0)
-  if (bal && ooe) PUP_OCC(true, true);
-  if (bal && !ooe) PUP_OCC(true, false);
-  if (!bal && ooe) PUP_OCC(false, true);
-  PUP_OCC(false, false);
-#undef PUP_OCC
+cudaError_t launch_main(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe, int maxown,
+                        int* occ) {
+  switch (maxown) {
+    case 1: return launch_main2<S, 1>(p, grid, smem, st, bal, ooe, occ);
+    case 2: return launch_main2<S, 2>(p, grid, smem, st, bal, ooe, occ);
+    case 3: return launch_main2<S, 3>(p, grid, smem, st, bal, ooe, occ);
+    default: return launch_main2<S, 4>(p, grid, smem, st, bal, ooe, occ);
+  }
 }
 
 int env_int(const char* name, int dflt) {
@@ -621,6 +729,38 @@ int pup_device_count(int* n_out) {
     return fail(PUP_E_NODEV, "cudaGetDeviceCount", e);
   }
   *n_out = n;
+  return PUP_OK;
+}
+
+int pup_timing_enable(int on) {
+  g_timing = on != 0;
+  return PUP_OK;
+}
+
+int pup_timing_read(double* ms_by_tag, int* count_by_tag, int reset) {
+  double ms[3] = {0, 0, 0};
+  int cnt[3] = {0, 0, 0};
+  for (auto& sp : g_spans) {
+    float f = 0;
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&f, sp.a, sp.b);
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "pup_timing_read", e);
+    if (sp.tag >= 0 && sp.tag < 3) {
+      ms[sp.tag] += f;
+      cnt[sp.tag] += 1;
+    }
+  }
+  if (reset) {
+    for (auto& sp : g_spans) {
+      cudaEventDestroy(sp.a);
+      cudaEventDestroy(sp.b);
+    }
+    g_spans.clear();
+  }
+  for (int i = 0; i < 3; ++i) {
+    if (ms_by_tag) ms_by_tag[i] = ms[i];
+    if (count_by_tag) count_by_tag[i] = cnt[i];
+  }
   return PUP_OK;
 }
 
@@ -818,6 +958,13 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   }
 
   // 1. sort keys
+  SpanGuard* span = new SpanGuard(0, st);
+  struct SpanDeleter {
+    SpanGuard** g;
+    ~SpanDeleter() {
+      if (*g) delete *g;
+    }
+  } span_deleter{&span};
   uint64_t *keys_a, *keys_b;
   CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
   CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
@@ -827,14 +974,14 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
   {
     size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_win, 0, 64, st));
+    // valid keys use 2*pb+sb bits and have bit (2*pb+sb) clear; the invalid marker (~0) has it set,
+    // so sorting bits [0, 2*pb+sb+1) orders everything and puts the invalid windows last.
+    const int end_bit = 2 * pb + sb + 1;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_win, 0, end_bit, st));
     void* t;
     CK(tmp.alloc(&t, tb));
-    // valid keys use 2*pb+sb bits; the invalid marker (~0) needs bit 63 -> sort [0, 2pb+sb) plus the top bit
-    // by sorting the full 64 bits only when it is cheap; otherwise two partial sorts would be needed, so we
-    // simply sort all 64 bits (n_win * 8 passes over 8 bytes: negligible next to the pile-up itself).
-    CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, 64, st));
-    g_launches += 8;
+    CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, end_bit, st));
+    g_launches += (end_bit + 7) / 8 + 1;
   }
   const uint64_t* keys = dbuf.Current();
 
@@ -859,23 +1006,33 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
   WinCtx ctx{m->nb, W, pb, ignore_diags, flags, m->ebadpre};
 
+  delete span;
+  span = nullptr;
+
   // 3. per-window vector quantities
   {
+    SpanGuard vspan(1, st);
     if (2 * W - 1 > VT) return fail(PUP_E_ARG, "pup_accumulate: W too large for the vector kernel (max 256)");
     VecParams vp{ctx, keys, slot_start, n_slots, m->weight ? m->bad : nullptr, m->expected, m->coverage, d_acc};
-    int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 8);
-    k_vector<<<grid, VT, 0, st>>>(vp);
+    const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
+    const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
+    int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
+    k_vector<<<grid, vthreads, 0, st>>>(vp);
     LAUNCH_CHECK("k_vector");
   }
 
   // 4. the pile-up itself
   {
+    SpanGuard mspan(2, st);
     int* counter;
     CK(tmp.alloc((void**)&counter, 4));
     CK(cudaMemsetAsync(counter, 0, 4, st));
     // band height: keep the fp64 + int32 tile within PUP_TILE_KB so that >= 2 CTAs fit per SM
     const int tile_kb = env_int("PUP_TILE_KB", 100);
     int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (12ll * W));
+    int S = env_int("PUP_GROUP", 16);
+    if (S != 32) S = 16;
+    Wb = std::min(Wb, MAXOWN_LIMIT * (NT / 32) * (32 / S));
     if (Wb < 1) Wb = 1;
     const int n_bands = (W + Wb - 1) / Wb;
     Wb = (W + n_bands - 1) / n_bands;  // balance the bands
@@ -883,24 +1040,16 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     MainParams mp{ctx,          m->ent, m->indptr,  m->bucket,   m->lb,   m->weight, m->expected, m->bad, m->ebad,
                   keys,         slot_start, chunk_start, n_slots, Wb,     n_bands,   ch,          d_acc,  counter};
     const bool bal = m->weight != nullptr, ooe = (flags & PUP_F_OOE) != 0;
-    int S = env_int("PUP_GROUP", 16);
+    const int ngroups = (NT / 32) * (32 / S);
+    const int maxown = (Wb + ngroups - 1) / ngroups;
     int occ = 1;
-    cudaError_t e;
-    if (S == 32)
-      e = main_occupancy<32>(&occ, smem, bal, ooe);
-    else if (S == 8)
-      e = main_occupancy<8>(&occ, smem, bal, ooe);
-    else
-      e = main_occupancy<16>(&occ, smem, bal, ooe);
+    cudaError_t e = (S == 32) ? launch_main<32>(mp, 0, smem, st, bal, ooe, maxown, &occ)
+                              : launch_main<16>(mp, 0, smem, st, bal, ooe, maxown, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
     int grid = n_sm * occ;
-    if (S == 32)
-      e = launch_main<32>(mp, grid, smem, st, bal, ooe);
-    else if (S == 8)
-      e = launch_main<8>(mp, grid, smem, st, bal, ooe);
-    else
-      e = launch_main<16>(mp, grid, smem, st, bal, ooe);
+    e = (S == 32) ? launch_main<32>(mp, grid, smem, st, bal, ooe, maxown, nullptr)
+                  : launch_main<16>(mp, grid, smem, st, bal, ooe, maxown, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
   }

@@ -124,6 +124,15 @@ int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stre
 int pup_last_launches(void);
 
 /*
+ * Optional device-side timing for benchmarks: when enabled (per host thread), every pup_accumulate() records
+ * CUDA events on the caller's stream around its three phases: [0] window sort + chunk plan, [1] vector kernel,
+ * [2] main pile-up kernel.  pup_timing_read() waits for the recorded events and returns the summed milliseconds
+ * and the number of spans per phase (arrays of 3); reset != 0 clears the records.
+ */
+int pup_timing_enable(int on);
+int pup_timing_read(double* ms_by_phase, int* count_by_phase, int reset);
+
+/*
  * Exact algorithmic bytes of a window list on a prepared region:
  *   sum over in-bounds windows of 16 + (W+1)*4 + 8*nnz_win (+16*W if balanced) (+16*W if coverage).
  * Computed on the device by a separate counting kernel (not part of the timed path).
