@@ -291,7 +291,8 @@ def main():
             continue
         t = synthetic_region(windows[c]["nb"], depth=args.depth, seed=1234 + ci, device=dev, nan_frac=0.03)
         nnz_total += int(t["col"].shape[0])
-        regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None, stream=stream)
+        regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None,
+                                    ignore_diags=2, flags=0, stream=stream)
         if not args.no_e2e or (rank == 0 and not args.no_cpu):
             host[c] = {k: t[k].cpu().pin_memory() for k in ("indptr", "col", "count", "weight")}
         w = windows[c]
@@ -318,7 +319,7 @@ def main():
         launches = 1
         for c in mine:
             r0, c0, sl = dwin[c]
-            regions[c].accumulate(r0, c0, sl, W, 2, n_slots, flags, acc, stream=stream)
+            regions[c].accumulate(r0, c0, sl, W, n_slots, flags, acc, stream=stream)
             launches += _native.lib().pup_last_launches()
         if dist is not None:
             dist.all_reduce(acc)

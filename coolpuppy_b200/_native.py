@@ -44,13 +44,13 @@ def lib():
     L.pup_last_error.restype = C.c_char_p
     L.pup_last_launches.restype = C.c_int
     L.pup_device_count.argtypes = [C.POINTER(C.c_int)]
-    L.pup_region_create.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.pup_region_create.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, C.c_int, u32, vp, C.POINTER(vp)]
     L.pup_region_destroy.argtypes = [vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
     L.pup_acc_stride.argtypes = [C.c_int]
     L.pup_acc_stride.restype = i64
-    L.pup_accumulate.argtypes = [vp, i64, vp, vp, vp, C.c_int, C.c_int, C.c_int, u32, vp, vp, C.POINTER(i64)]
+    L.pup_accumulate.argtypes = [vp, i64, vp, vp, vp, C.c_int, C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_accumulate_region.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, C.c_int, C.c_int,
                                         C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -117,25 +117,27 @@ def acc_stride(W):
 class Region:
     """A region matrix resident in HBM (``pup_region_t``)."""
 
-    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, stream=0):
+    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, ignore_diags=2,
+                 flags=0, stream=0):
         self._h = C.c_void_p()
         self.nb = int(nb)
         self.nnz = int(col.shape[0]) if col is not None else 0
         self.device = device
         self.balanced = weight is not None
-        check(lib().pup_region_create(device, self.nb, self.nnz, ptr(indptr, np.int32) if isinstance(indptr, np.ndarray) else ptr(indptr),
-                                      ptr(col), ptr(count), ptr(weight), ptr(expected), ptr(coverage), stream,
-                                      C.byref(self._h)))
+        check(lib().pup_region_create(device, self.nb, self.nnz, ptr(indptr), ptr(col), ptr(count), ptr(weight),
+                                      ptr(expected), ptr(coverage), int(ignore_diags),
+                                      int(flags) & (PUP_F_OOE | PUP_F_NODIAG), stream, C.byref(self._h)))
 
     @property
     def device_bytes(self):
         return int(lib().pup_region_device_bytes(self._h))
 
-    def accumulate(self, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream=0, want_n_valid=False):
+    def accumulate(self, r0, c0, slot, W, n_slots, flags, acc, stream=0, want_n_valid=False):
         n = int(r0.shape[0])
         nv = C.c_int64(0)
-        check(lib().pup_accumulate(self._h, n, ptr(r0), ptr(c0), ptr(slot), int(W), int(ignore_diags), int(n_slots),
-                                   int(flags), ptr(acc), stream, C.byref(nv) if want_n_valid else None))
+        check(lib().pup_accumulate(self._h, n, ptr(r0), ptr(c0), ptr(slot), int(W), int(n_slots),
+                                   int(flags) & (PUP_F_EXPCTRL | PUP_F_COVERAGE), ptr(acc), stream,
+                                   C.byref(nv) if want_n_valid else None))
         return nv.value if want_n_valid else None
 
     def algorithmic_bytes(self, r0, c0, W, flags=0, stream=0):
@@ -172,11 +174,11 @@ def timing_enable(on=True):
 
 
 def timing_read(reset=True):
-    """{phase: (milliseconds, spans)} for phases 'plan', 'vector', 'main' recorded since the last reset."""
-    ms = (C.c_double * 3)()
-    cnt = (C.c_int * 3)()
+    """{phase: (milliseconds, spans)} for phases 'plan', 'vector', 'main', 'dense_num' since the last reset."""
+    ms = (C.c_double * 4)()
+    cnt = (C.c_int * 4)()
     check(lib().pup_timing_read(ms, cnt, 1 if reset else 0))
-    return {k: (ms[i], cnt[i]) for i, k in enumerate(("plan", "vector", "main"))}
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(("plan", "vector", "main", "dense_num"))}
 
 
 def acc_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):

@@ -604,12 +604,13 @@ class PileUpper:
         self._last_stats = {"windows": 0, "launches": 0, "regions": 0}
         for b in job["built"]:
             nb, indptr, col, cnt, weight, exp, cov = self._region_arrays(b["name"])
-            region = _native.Region(self._device, nb, indptr, col, cnt, weight, exp, cov, stream=stream)
+            region = _native.Region(self._device, nb, indptr, col, cnt, weight, exp, cov,
+                                    ignore_diags=self.ignore_diags, flags=flags, stream=stream)
             self._last_stats["launches"] += int(_native.lib().pup_last_launches())
             try:
                 nv = region.accumulate(
                     np.ascontiguousarray(b["w_r0"], dtype=np.int32), np.ascontiguousarray(b["w_c0"], dtype=np.int32),
-                    np.ascontiguousarray(b["slot"], dtype=np.int32), W, self.ignore_diags, n_slots, flags, acc,
+                    np.ascontiguousarray(b["slot"], dtype=np.int32), W, n_slots, flags, acc,
                     stream=stream, want_n_valid=True)
             finally:
                 region.close()

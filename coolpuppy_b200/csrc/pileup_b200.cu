@@ -3,18 +3,21 @@
 // Hot path restated for the GPU (reference: coolpup.py:1059-1191 _stream_snips, 1236-1283 accumulate_stream,
 // lib/puputils.py:12-41 _add_snip):
 //
+//   region prep (once per region):  every stored pixel is normalised exactly once
+//       val = (w[row] * w[col]) * count / E[|col-row|];  val = 0 where the reference would produce NaN
+//       (NaN weight, NaN expected, signed diagonal mask) because nansum() adds nothing there
+//   pile-up (k_pileup_main):
 //   for every window (r0, c0, slot):                       # sorted by (slot, r0, c0) on the device
-//     for every window row di:                             # one sub-warp row-group owns row di of the smem tile
+//     for every window row di:                             # one lane-quad owns row di of the shared-memory tile
 //       start = bucket[(c0 >> lb) * nb + r0 + di]          # column-bucket-major row pointer table: no binary search
-//       stream the row's (col, count) pairs from `start` while col < c0 + W     # coalesced 8-byte loads
-//       v = (w[row] * w[col]) * count / E[|col-row|]       # balancing + expected fused; signed diagonal mask
-//       tile[di][col - c0] += v                            # fp64 shared-memory tile, race-free by row ownership
+//       stream the row's (col, val) pairs from `start` while col < c0 + W       # 16-byte loads, 4 windows in flight
+//       tile[di][col - c0] += val                          # fp64 shared-memory tile, race-free by row ownership
 //   flush tile with red.global.add.f64 when the slot changes
 //
 // `num` (count of finite contributions) is dense in the reference (W*W work per window).  Here it is
 //   num = n_fast - rowbad[di] - colbad[dj] + xtile[di][dj]
-// with O(W) vector work per window plus a sparse bad-row x bad-col correction; only windows that touch the
-// masked diagonals / NaN expected values ("slow" windows) take the dense W*W path.
+// with O(W) vector work per window (k_vector) plus a sparse bad-row x bad-col correction; only windows that
+// touch the masked diagonals / NaN expected values ("slow" windows) take the dense W*W path (k_num_slow).
 #include "pileup_b200.h"
 
 #include <cuda_runtime.h>
@@ -22,6 +25,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -33,9 +37,10 @@ thread_local int g_launches = 0;
 
 // optional per-phase device timing (bench.py): CUDA events recorded on the caller's stream
 struct TimedSpan {
-  int tag;  // 0 sort/plan, 1 vector kernel, 2 main kernel
+  int tag;  // 0 sort/plan, 1 vector kernel, 2 main kernel, 3 dense-num kernel
   cudaEvent_t a, b;
 };
+constexpr int N_TAGS = 4;
 thread_local bool g_timing = false;
 thread_local std::vector<TimedSpan> g_spans;
 
@@ -50,11 +55,13 @@ struct SpanGuard {
     cudaEventCreate(&sp.b);
     cudaEventRecord(sp.a, st);
   }
-  ~SpanGuard() {
+  void close() {
     if (!on) return;
     cudaEventRecord(sp.b, st);
     g_spans.push_back(sp);
+    on = false;
   }
+  ~SpanGuard() { close(); }
 };
 
 int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -117,9 +124,31 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-constexpr int NT = 512;   // threads per CTA of the main kernel
-constexpr int VT = 512;   // threads per CTA of the vector kernel
-constexpr int VCH = 256;  // windows per CTA step of the vector kernel
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+int ilog2_ceil(int64_t v) {
+  int b = 0;
+  while ((1ll << b) < v) ++b;
+  return b;
+}
+
+constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel
+constexpr int VT = 512;      // max threads per CTA of the vector kernel
+constexpr int VCH = 256;     // windows per CTA step of the vector kernel
+constexpr int VU = 4;        // windows in flight per thread of the vector kernel
+constexpr int WU = 4;        // windows in flight per row-group of the main kernel
+constexpr int ROW_BAD = -1;  // rowend[] marker of a row whose weight is NaN
+
+// one stored pixel as the main kernel reads it: 16 bytes, one ld.global.nc.v4 per lane
+struct __align__(16) Pix {
+  int col;
+  int pad;
+  double val;
+};
 
 // ------------------------------------------------------------------------------------------ accumulator layout
 struct AccLayout {
@@ -149,13 +178,15 @@ struct pup_region {
   int64_t nnz;
   int lb;   // log2 of the column-bucket width
   int nbk;  // number of column buckets
-  int2* ent;          // [nnz] (col, count) interleaved
+  int ignore_diags;
+  unsigned flags;     // PUP_F_OOE | PUP_F_NODIAG folded into the pixel values
+  Pix* pix;           // [nnz] (col, normalised value)
   int32_t* indptr;    // [nb+1]
+  int32_t* rowend;    // [nb] indptr[r+1], or ROW_BAD when the row's weight is NaN
   int32_t* bucket;    // [nbk][nb] first entry of row r with col >= b << lb
-  double* weight;     // [nb] or null
   double* expected;   // [nb] or null
   double* coverage;   // [nb] or null
-  uint8_t* bad;       // [nb] weight is NaN
+  uint8_t* bad;       // [nb] weight is NaN; null for raw counts
   uint8_t* ebad;      // [nb] expected is NaN or 0
   int32_t* ebadpre;   // [nb+1] exclusive prefix of ebad
   cudaStream_t stream;
@@ -165,15 +196,44 @@ struct pup_region {
 namespace {
 
 // ------------------------------------------------------------------------------------------ prep kernels
-__global__ void k_interleave(const int32_t* __restrict__ col, const int32_t* __restrict__ cnt, int2* __restrict__ ent,
-                             int64_t nnz) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (; i < nnz; i += step) ent[i] = make_int2(col[i], cnt[i]);
+// One warp per matrix row: normalise every stored pixel once and write the 16-byte records.
+__global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
+                                 const int32_t* __restrict__ cnt, const double* __restrict__ weight,
+                                 const double* __restrict__ expected, Pix* __restrict__ pix,
+                                 int32_t* __restrict__ rowend, int nb, int ignore_diags, unsigned flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool ooe = (flags & PUP_F_OOE) && expected != nullptr;
+  const bool nodiag = flags & PUP_F_NODIAG;
+  for (int64_t r = warp; r < nb; r += nwarps) {
+    const int lo = indptr[r], hi = indptr[r + 1];
+    double wr = 1.0;
+    bool rbad = false;
+    if (weight != nullptr) {
+      wr = weight[r];
+      rbad = isnan(wr);
+    }
+    if (lane == 0) rowend[r] = rbad ? ROW_BAD : hi;
+    for (int i = lo + lane; i < hi; i += 32) {
+      const int c = col[i];
+      double v = (double)cnt[i];
+      if (weight != nullptr) v = (wr * weight[c]) * v;  // cooler: bias[row] * bias[col] * count
+      const int d = c - (int)r;
+      if (ooe) v = v / expected[d < 0 ? -d : d];
+      if (!nodiag && d < ignore_diags) v = 0.0;  // signed diagonal mask (coolpup.py:1141-1149)
+      if (v != v) v = 0.0;                       // NaN pixels add nothing to a nansum
+      Pix p;
+      p.col = c;
+      p.pad = 0;
+      p.val = v;
+      pix[i] = p;
+    }
+  }
 }
 
 // bucket[b * nb + r] = first entry index of row r whose column is >= (b << lb)
-__global__ void k_build_buckets(const int2* __restrict__ ent, const int32_t* __restrict__ indptr,
+__global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* __restrict__ indptr,
                                 int32_t* __restrict__ bucket, int nb, int nbk, int lb) {
   int64_t total = (int64_t)nb * nbk;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,7 +245,7 @@ __global__ void k_build_buckets(const int2* __restrict__ ent, const int32_t* __r
     int target = b << lb;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (__ldg(&ent[mid].x) < target)
+      if (__ldg(&col[mid]) < target)
         lo = mid + 1;
       else
         hi = mid;
@@ -202,7 +262,7 @@ __global__ void k_masks(const double* __restrict__ weight, const double* __restr
     ebad32[i] = 0;
     return;
   }
-  bad[i] = (weight != nullptr && isnan(weight[i])) ? 1 : 0;
+  if (bad != nullptr) bad[i] = isnan(weight[i]) ? 1 : 0;
   uint8_t eb = 0;
   if (expected != nullptr) {
     double e = expected[i];
@@ -213,7 +273,7 @@ __global__ void k_masks(const double* __restrict__ weight, const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------ window keys
-// key = [invalid:1][slot][r0:pb][c0:pb]; out-of-region windows get only the invalid bit and sort last.
+// key = [invalid:1][slot][r0:pb][c0:pb]; out-of-region windows get all ones and sort last.
 __global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __restrict__ c0,
                               const int32_t* __restrict__ slot, uint64_t* __restrict__ keys, int64_t n, int nb, int W,
                               int n_slots, int pb) {
@@ -221,12 +281,7 @@ __global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __r
   if (i >= n) return;
   int r = r0[i], c = c0[i], s = slot[i];
   bool ok = r >= 0 && c >= 0 && r + W <= nb && c + W <= nb && s >= 0 && s < n_slots;
-  uint64_t k;
-  if (ok)
-    k = ((uint64_t)s << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c;
-  else
-    k = ~0ull;
-  keys[i] = k;
+  keys[i] = ok ? (((uint64_t)s << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c) : ~0ull;
 }
 
 // slot_start[s] = first sorted window of slot s (s = n_slots: number of valid windows);
@@ -296,9 +351,31 @@ __device__ __forceinline__ bool window_is_slow(const WinCtx& c, int r0, int c0) 
   return false;
 }
 
+// work item -> (slot, window range) through the per-slot chunk table
+struct ChunkTable {
+  const int32_t* slot_start;   // [n_slots+1]
+  const int32_t* chunk_start;  // [n_slots+1] exclusive scan of chunks per slot
+  int n_slots;
+  int ch;  // windows per chunk
+};
+
+__device__ __forceinline__ void locate_chunk(const ChunkTable& t, int chunk, int& slot, int& lo, int& hi) {
+  int a = 0, b = t.n_slots;  // last s with chunk_start[s] <= chunk
+  while (a < b) {
+    int mid = (a + b + 1) >> 1;
+    if (__ldg(&t.chunk_start[mid]) <= chunk)
+      a = mid;
+    else
+      b = mid - 1;
+  }
+  slot = a;
+  lo = __ldg(&t.slot_start[a]) + (chunk - __ldg(&t.chunk_start[a])) * t.ch;
+  hi = min(lo + t.ch, __ldg(&t.slot_start[a + 1]));
+}
+
 // ------------------------------------------------------------------------------------------ vector kernel
 // Per-window O(W) quantities: n, n_fast, bad-row / bad-col counts, coverage sums, Toeplitz sums of the bare
-// expected block.  One CTA walks VCH consecutive sorted windows; thread t owns vector index t.
+// expected block.  One CTA walks VCH consecutive sorted windows, VU at a time; thread t owns vector index t.
 struct VecParams {
   WinCtx ctx;
   const uint64_t* keys;
@@ -308,9 +385,8 @@ struct VecParams {
   const double* expected;    // for EXPCTRL
   const double* coverage;    // for COVERAGE
   double* acc;
+  int* n_slow;               // number of slow windows of this call
 };
-
-constexpr int VU = 4;  // windows in flight per thread of the vector kernel
 
 __global__ void k_vector(const VecParams p) {
   const int n = __ldg(&p.slot_start[p.n_slots]);
@@ -320,6 +396,7 @@ __global__ void k_vector(const VecParams p) {
   const bool has_bad = p.bad != nullptr;
   const bool cov = (p.ctx.flags & PUP_F_COVERAGE) && p.coverage != nullptr;
   const bool ectl = (p.ctx.flags & PUP_F_EXPCTRL) && p.expected != nullptr;
+  int slow_total = 0;
   for (int base = blockIdx.x * VCH; base < n; base += gridDim.x * VCH) {
     const int end = min(base + VCH, n);
     int cur = -1;
@@ -384,7 +461,10 @@ __global__ void k_vector(const VecParams p) {
         }
         if (t == 0) {
           nn += 1;
-          if (!slow[u]) nf += 1;
+          if (!slow[u])
+            nf += 1;
+          else
+            slow_total += 1;
         }
         rb += br[u];
         cb += bc[u];
@@ -400,79 +480,60 @@ __global__ void k_vector(const VecParams p) {
     }
     flush();
   }
+  if (t == 0 && slow_total > 0) atomicAdd(p.n_slow, slow_total);
 }
 
 // ------------------------------------------------------------------------------------------ main kernel
 struct MainParams {
   WinCtx ctx;
-  const int2* ent;
-  const int32_t* indptr;
+  const Pix* pix;
+  const int32_t* rowend;
   const int32_t* bucket;
   int lb;
-  const double* weight;
-  const double* expected;
-  const uint8_t* bad;
-  const uint8_t* ebad;
+  const uint8_t* bad;  // null for raw counts
   const uint64_t* keys;
-  const int32_t* slot_start;   // [n_slots+1]
-  const int32_t* chunk_start;  // [n_slots+1] exclusive scan of chunks per slot
-  int n_slots;
-  int Wb;       // tile rows per band
+  ChunkTable chunks;
+  int Wb;       // tile rows per band (<= row-groups per CTA)
   int n_bands;
-  int ch;       // windows per chunk
   double* acc;
   int* counter;
 };
 
-constexpr int MAXOWN_LIMIT = 4;  // tile rows one row-group can own (Wb <= MAXOWN * row-groups per CTA)
-
-template <int S, bool BAL, bool OOE, int MAXOWN>
-__global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
+// S lanes share one tile row; every row-group owns exactly one row of the band, so the shared-memory
+// read-modify-write needs no atomics.  WU windows are in flight per row-group to hide the L2 latency of the
+// dependent key -> bucket pointer -> pixel chain.
+template <int S>
+__global__ void __launch_bounds__(NT_MAX, 3) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = p.ctx.W;
   const int Wb = p.Wb;
   double* sumT = reinterpret_cast<double*>(smem_raw);
-  int* numT = reinterpret_cast<int*>(sumT + (size_t)Wb * W);
   __shared__ int s_slot, s_lo, s_hi, s_band;
 
   const AccLayout L(W);
+  const int nthreads = blockDim.x;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  constexpr int GPW = 32 / S;           // row-groups per warp
-  constexpr int NG = (NT / 32) * GPW;   // row-groups per CTA
   const int sub = lane / S;
   const int ls = lane % S;
-  const int g = warp * GPW + sub;
+  const int g = (threadIdx.x >> 5) * (32 / S) + sub;  // row-group id == tile row owned
   const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
-  const bool nodiag = p.ctx.flags & PUP_F_NODIAG;
-  const int igd = p.ctx.ignore_diags;
   const int nb = p.ctx.nb;
   const int pb = p.ctx.pb;
   const int tile = Wb * W;
-  const int2 SENTINEL = make_int2(0x7fffffff, 0);
 
-  for (int i = threadIdx.x; i < tile; i += NT) {
-    sumT[i] = 0.0;
-    numT[i] = 0;
-  }
+  for (int i = threadIdx.x; i < tile; i += nthreads) sumT[i] = 0.0;
   int cur_slot = -1, cur_band = 0;
-  const int total_chunks = __ldg(&p.chunk_start[p.n_slots]);
+  const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
 
   auto flush = [&]() {
-    // every thread adds its cells of the tile into the global accumulator, then clears them
     double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)cur_band * Wb * W;
     int rows = min(Wb, W - cur_band * Wb);
     int cells = rows * W;
-    for (int i = threadIdx.x; i < cells; i += NT) {
+    for (int i = threadIdx.x; i < cells; i += nthreads) {
       double v = sumT[i];
       if (v != 0.0) {
         atomicAdd(a + i, v);
         sumT[i] = 0.0;
-      }
-      int c = numT[i];
-      if (c != 0) {
-        atomicAdd(a + L.off_num + i, (double)c);
-        numT[i] = 0;
       }
     }
   };
@@ -485,21 +546,12 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
         s_slot = -1;
       } else {
         int band = item / total_chunks;
-        int chunk = item - band * total_chunks;
-        int lo = 0, hi = p.n_slots;  // last s with chunk_start[s] <= chunk
-        while (lo < hi) {
-          int mid = (lo + hi + 1) >> 1;
-          if (__ldg(&p.chunk_start[mid]) <= chunk)
-            lo = mid;
-          else
-            hi = mid - 1;
-        }
-        int s = lo;
-        int w0 = __ldg(&p.slot_start[s]) + (chunk - __ldg(&p.chunk_start[s])) * p.ch;
-        s_slot = s;
+        int slot, lo, hi;
+        locate_chunk(p.chunks, item - band * total_chunks, slot, lo, hi);
+        s_slot = slot;
         s_band = band;
-        s_lo = w0;
-        s_hi = min(w0 + p.ch, __ldg(&p.slot_start[s + 1]));
+        s_lo = lo;
+        s_hi = hi;
       }
     }
     __syncthreads();
@@ -517,109 +569,159 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
     const int row_lo = band * Wb;
     const int nrows = min(Wb, W - row_lo);
     const int w_lo = s_lo, w_hi = s_hi;
-    const int nown = (g < nrows) ? (nrows - 1 - g) / NG + 1 : 0;  // tile rows dl = g + j * NG owned by this group
+    if (g >= nrows) continue;
 
-    if (nown > 0) {
-      // ---- pass 1: sums.  Row pointers of window w+1 are fetched while window w is being accumulated.
-      int n_idx[MAXOWN], n_end[MAXOWN];
-      int n_r0 = 0, n_c0 = 0;
-      auto fetch_ptrs = [&](int w) {
-        int kslot;
-        decode_key(__ldg(&p.keys[w]), pb, kslot, n_r0, n_c0);
-        const int rbase = n_r0 + row_lo + g;
-        const int32_t* bk = p.bucket + (size_t)(n_c0 >> p.lb) * nb + rbase;
+    double* trow = sumT + g * W;
+    const int di = row_lo + g;
+    for (int w = w_lo; w < w_hi; w += WU) {
+      int idx[WU], pend[WU], c0s[WU];
+      Pix e[WU];
 #pragma unroll
-        for (int j = 0; j < MAXOWN; ++j) {
-          if (j < nown) {
-            n_idx[j] = __ldg(bk + j * NG) + ls;
-            n_end[j] = __ldg(&p.indptr[rbase + j * NG + 1]);
-          } else {
-            n_idx[j] = 0;
-            n_end[j] = 0;
-          }
-        }
-      };
-      fetch_ptrs(w_lo);
-      for (int w = w_lo; w < w_hi; ++w) {
-        int idx[MAXOWN], pend[MAXOWN];
-        double wr[MAXOWN];
-        int2 e[MAXOWN];
-        const int r0 = n_r0, c0 = n_c0;
-#pragma unroll
-        for (int j = 0; j < MAXOWN; ++j) {
-          idx[j] = n_idx[j];
-          pend[j] = n_end[j];
-          e[j] = (idx[j] < pend[j]) ? __ldg(&p.ent[idx[j]]) : SENTINEL;
-          wr[j] = (BAL && j < nown) ? __ldg(&p.weight[r0 + row_lo + g + j * NG]) : 1.0;
-        }
-        if (w + 1 < w_hi) fetch_ptrs(w + 1);
-#pragma unroll
-        for (int j = 0; j < MAXOWN; ++j) {
-          if (j < nown) {
-            const int dl = g + j * NG;
-            const int r = r0 + row_lo + dl;
-            double* trow = sumT + dl * W;
-            int2 ce = e[j];
-            int id = idx[j];
-            const int pe = pend[j];
-            const double w_r = wr[j];
-            if (!(BAL && isnan(w_r))) {
-              for (;;) {
-                const int dj = ce.x - c0;
-                if (dj >= W) break;
-                const int nid = id + S;
-                // dense rows need the next S entries too: start that load before touching shared memory
-                int2 ne = SENTINEL;
-                if (nid < pe && dj + S < W + S / 2) ne = __ldg(&p.ent[nid]);
-                if (dj >= 0) {
-                  const int d = ce.x - r;
-                  if (nodiag || d >= igd) {
-                    double v = (double)ce.y;
-                    if (BAL) v = (w_r * __ldg(&p.weight[ce.x])) * v;
-                    if (OOE) v = v / __ldg(&p.expected[d < 0 ? -d : d]);
-                    if (v == v) trow[dj] += v;
-                  }
-                }
-                if (nid >= pe) break;
-                if (ne.x == 0x7fffffff) ne = __ldg(&p.ent[nid]);
-                ce = ne;
-                id = nid;
-              }
-            }
-            __syncwarp(gmask);
-          }
+      for (int u = 0; u < WU; ++u) {
+        idx[u] = 0;
+        pend[u] = 0;
+        c0s[u] = 0;
+        if (w + u < w_hi) {
+          int kslot, r0, c0;
+          decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, c0);
+          const int r = r0 + di;
+          idx[u] = __ldg(&p.bucket[(size_t)(c0 >> p.lb) * nb + r]) + ls;
+          pend[u] = __ldg(&p.rowend[r]);
+          c0s[u] = c0;
         }
       }
-
-      // ---- pass 2: pixel counts that are not covered by the vector kernel's closed form
-      for (int w = w_lo; w < w_hi; ++w) {
-        int kslot, r0, c0;
-        decode_key(__ldg(&p.keys[w]), pb, kslot, r0, c0);
-        const bool slow = window_is_slow(p.ctx, r0, c0);
-        if (!slow && !BAL) continue;
 #pragma unroll
-        for (int j = 0; j < MAXOWN; ++j) {
-          if (j < nown) {
-            const int dl = g + j * NG;
-            const int r = r0 + row_lo + dl;
-            int* nrow = numT + dl * W;
-            const bool rbad = BAL && __ldg(&p.bad[r]);
-            if (slow) {
-              for (int dj = ls; dj < W; dj += S) {
-                const int c = c0 + dj;
-                const int d = c - r;
-                bool ok = !rbad;
-                if (BAL) ok = ok && !__ldg(&p.bad[c]);
-                if (!nodiag) ok = ok && (d >= igd);
-                if (OOE) ok = ok && !__ldg(&p.ebad[d < 0 ? -d : d]);
-                if (ok) nrow[dj] += 1;
-              }
-            } else if (rbad) {
+      for (int u = 0; u < WU; ++u) {
+        e[u].col = 0x7fffffff;
+        e[u].val = 0.0;
+        if (idx[u] < pend[u]) {
+          const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
+          e[u].col = raw.x;
+          e[u].val = __hiloint2double(raw.w, raw.z);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < WU; ++u) {
+        if (w + u < w_hi) {
+          const int c0 = c0s[u];
+          const int pe = pend[u];
+          if (pe == ROW_BAD) {
+            // masked row: nothing to sum; fast windows need the bad-row x bad-col correction of `num`
+            int kslot, r0, cc;
+            decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, cc);
+            if (p.bad != nullptr && !window_is_slow(p.ctx, r0, c0)) {
+              double* nrow = p.acc + (int64_t)cur_slot * L.stride + L.off_num + (int64_t)di * W;
               for (int dj = ls; dj < W; dj += S)
-                if (__ldg(&p.bad[c0 + dj])) nrow[dj] += 1;
+                if (__ldg(&p.bad[c0 + dj])) atomicAdd(nrow + dj, 1.0);
+            }
+          } else {
+            int col = e[u].col;
+            double val = e[u].val;
+            int id = idx[u];
+            for (;;) {
+              const int dj = col - c0;
+              if (dj >= W) break;
+              const int nid = id + S;
+              // dense rows need the next S pixels too: start that load before touching shared memory
+              int ncol = 0x7fffffff;
+              double nval = 0.0;
+              const bool more = nid < pe;
+              if (more) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + nid));
+                ncol = raw.x;
+                nval = __hiloint2double(raw.w, raw.z);
+              }
+              if (dj >= 0) trow[dj] += val;
+              if (!more) break;
+              col = ncol;
+              val = nval;
+              id = nid;
             }
           }
+          __syncwarp(gmask);
         }
+      }
+    }
+  }
+  __syncthreads();
+  if (cur_slot >= 0) flush();
+}
+
+// ------------------------------------------------------------------------------------------ dense-num kernel
+// `num` of slow windows: every pixel of the window is tested (row / column weight, signed diagonal, expected).
+// One CTA per chunk; thread t owns tile cells t, t + blockDim, ... so the int32 tile needs no atomics.
+struct SlowParams {
+  WinCtx ctx;
+  const uint8_t* bad;   // null for raw
+  const uint8_t* ebad;
+  const uint64_t* keys;
+  ChunkTable chunks;
+  double* acc;
+  const int* n_slow;
+  int* counter;
+};
+
+__global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
+  if (*p.n_slow == 0) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* numT = reinterpret_cast<int*>(smem_raw);
+  __shared__ int s_slot, s_lo, s_hi;
+  const int W = p.ctx.W;
+  const int w2 = W * W;
+  const AccLayout L(W);
+  const bool nodiag = p.ctx.flags & PUP_F_NODIAG;
+  const bool ooe = p.ctx.flags & PUP_F_OOE;
+  const int igd = p.ctx.ignore_diags;
+  for (int i = threadIdx.x; i < w2; i += blockDim.x) numT[i] = 0;
+  int cur_slot = -1;
+  const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
+  auto flush = [&]() {
+    double* a = p.acc + (int64_t)cur_slot * L.stride + L.off_num;
+    for (int i = threadIdx.x; i < w2; i += blockDim.x) {
+      int c = numT[i];
+      if (c != 0) {
+        atomicAdd(a + i, (double)c);
+        numT[i] = 0;
+      }
+    }
+  };
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int item = atomicAdd(p.counter, 1);
+      if (item >= total_chunks) {
+        s_slot = -1;
+      } else {
+        int slot, lo, hi;
+        locate_chunk(p.chunks, item, slot, lo, hi);
+        s_slot = slot;
+        s_lo = lo;
+        s_hi = hi;
+      }
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot < 0) break;
+    if (slot != cur_slot) {
+      if (cur_slot >= 0) {
+        flush();
+        __syncthreads();
+      }
+      cur_slot = slot;
+    }
+    for (int w = s_lo; w < s_hi; ++w) {
+      int kslot, r0, c0;
+      decode_key(__ldg(&p.keys[w]), p.ctx.pb, kslot, r0, c0);
+      if (!window_is_slow(p.ctx, r0, c0)) continue;
+      for (int cell = threadIdx.x; cell < w2; cell += blockDim.x) {
+        const int di = cell / W, dj = cell - di * W;
+        const int r = r0 + di, c = c0 + dj;
+        const int d = c - r;
+        bool ok = true;
+        if (p.bad != nullptr) ok = !__ldg(&p.bad[r]) && !__ldg(&p.bad[c]);
+        if (!nodiag) ok = ok && (d >= igd);
+        if (ooe) ok = ok && !__ldg(&p.ebad[d < 0 ? -d : d]);
+        if (ok) numT[cell] += 1;
       }
     }
   }
@@ -629,7 +731,7 @@ __global__ void __launch_bounds__(NT, 2) k_pileup_main(const MainParams p) {
 
 // ------------------------------------------------------------------------------------------ byte counter
 // Exact algorithmic pixel count of a window list (measurement helper, not on the timed path).
-__global__ void k_count_nnz(const int2* __restrict__ ent, const int32_t* __restrict__ indptr,
+__global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restrict__ indptr,
                             const int32_t* __restrict__ r0, const int32_t* __restrict__ c0, int64_t n, int nb, int W,
                             unsigned long long* out_nnz, unsigned long long* out_valid) {
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -646,7 +748,7 @@ __global__ void k_count_nnz(const int2* __restrict__ ent, const int32_t* __restr
         int a = lo, b = hi;
         while (a < b) {
           int mid = (a + b) >> 1;
-          if (__ldg(&ent[mid].x) < target)
+          if (__ldg(&pix[mid].col) < target)
             a = mid + 1;
           else
             b = mid;
@@ -666,46 +768,24 @@ __global__ void k_count_nnz(const int2* __restrict__ ent, const int32_t* __restr
   }
 }
 
-int ilog2_ceil(int64_t v) {
-  int b = 0;
-  while ((1ll << b) < v) ++b;
-  return b;
-}
-
-template <int S, int MO>
-cudaError_t launch_main2(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe, int* occ) {
-#define PUP_LAUNCH(B, O)                                                                                  \
+// occ != nullptr: only query the occupancy; else launch
+cudaError_t launch_main(int S, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
+#define PUP_LAUNCH(SV)                                                                                    \
   do {                                                                                                    \
-    auto kern = k_pileup_main<S, B, O, MO>;                                                               \
+    auto kern = k_pileup_main<SV>;                                                                        \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
-    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, NT, smem);                   \
-    kern<<<grid, NT, smem, st>>>(p);                                                                      \
+    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);              \
+    kern<<<grid, threads, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                            \
   } while (0)
-  if (bal && ooe) PUP_LAUNCH(true, true);
-  if (bal && !ooe) PUP_LAUNCH(true, false);
-  if (!bal && ooe) PUP_LAUNCH(false, true);
-  PUP_LAUNCH(false, false);
-#undef PUP_LAUNCH
-}
-
-// occ != nullptr: only query the occupancy; else launch
-template <int S>
-cudaError_t launch_main(const MainParams& p, int grid, size_t smem, cudaStream_t st, bool bal, bool ooe, int maxown,
-                        int* occ) {
-  switch (maxown) {
-    case 1: return launch_main2<S, 1>(p, grid, smem, st, bal, ooe, occ);
-    case 2: return launch_main2<S, 2>(p, grid, smem, st, bal, ooe, occ);
-    case 3: return launch_main2<S, 3>(p, grid, smem, st, bal, ooe, occ);
-    default: return launch_main2<S, 4>(p, grid, smem, st, bal, ooe, occ);
+  switch (S) {
+    case 2: PUP_LAUNCH(2);
+    case 8: PUP_LAUNCH(8);
+    case 16: PUP_LAUNCH(16);
+    default: PUP_LAUNCH(4);
   }
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  if (!v || !*v) return dflt;
-  return atoi(v);
+#undef PUP_LAUNCH
 }
 
 }  // namespace
@@ -713,7 +793,7 @@ int env_int(const char* name, int dflt) {
 // =========================================================================================== C ABI
 extern "C" {
 
-int pup_abi_version(void) { return 1; }
+int pup_abi_version(void) { return 2; }
 
 const char* pup_last_error(void) { return g_err.c_str(); }
 
@@ -738,14 +818,14 @@ int pup_timing_enable(int on) {
 }
 
 int pup_timing_read(double* ms_by_tag, int* count_by_tag, int reset) {
-  double ms[3] = {0, 0, 0};
-  int cnt[3] = {0, 0, 0};
+  double ms[N_TAGS] = {0, 0, 0, 0};
+  int cnt[N_TAGS] = {0, 0, 0, 0};
   for (auto& sp : g_spans) {
     float f = 0;
     cudaError_t e = cudaEventSynchronize(sp.b);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&f, sp.a, sp.b);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "pup_timing_read", e);
-    if (sp.tag >= 0 && sp.tag < 3) {
+    if (sp.tag >= 0 && sp.tag < N_TAGS) {
       ms[sp.tag] += f;
       cnt[sp.tag] += 1;
     }
@@ -757,7 +837,7 @@ int pup_timing_read(double* ms_by_tag, int* count_by_tag, int reset) {
     }
     g_spans.clear();
   }
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < N_TAGS; ++i) {
     if (ms_by_tag) ms_by_tag[i] = ms[i];
     if (count_by_tag) count_by_tag[i] = cnt[i];
   }
@@ -773,11 +853,13 @@ int64_t pup_region_device_bytes(const pup_region_t* r) { return r ? r->bytes : 0
 
 int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
                       const int32_t* count, const double* weight, const double* expected, const double* coverage,
-                      void* stream, pup_region_t** out) {
+                      int ignore_diags, unsigned flags, void* stream, pup_region_t** out) {
   if (!out) return fail(PUP_E_ARG, "pup_region_create: null output");
   *out = nullptr;
   if (nb <= 0 || nnz < 0 || nnz >= (1ll << 31) || !indptr || (nnz > 0 && (!col || !count)))
     return fail(PUP_E_ARG, "pup_region_create: bad sizes or null CSR arrays");
+  if ((flags & PUP_F_OOE) && !expected) return fail(PUP_E_ARG, "pup_region_create: PUP_F_OOE needs an expected vector");
+  if (flags & ~(PUP_F_OOE | PUP_F_NODIAG)) return fail(PUP_E_ARG, "pup_region_create: only PUP_F_OOE / PUP_F_NODIAG apply");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
     cudaGetLastError();
@@ -794,6 +876,8 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
   r->nb = nb;
   r->nnz = nnz;
   r->stream = st;
+  r->ignore_diags = ignore_diags;
+  r->flags = flags;
 
   // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
   double avg = (double)nnz / nb;
@@ -804,7 +888,7 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
   } else {
     int lb = (int)floor(log2((double)target * nb / avg));
     if (lb < 3) lb = 3;
-    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)2 * nnz + (64 << 20)) ++lb;  // cap: 25% of pixel bytes
+    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20)) ++lb;  // <= 25% of pixels
     r->lb = lb;
     r->nbk = (nb + (1 << lb) - 1) >> lb;
   }
@@ -821,18 +905,13 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
   } while (0)
 
   size_t n_ent = (size_t)(nnz > 0 ? nnz : 1);
-  RCK(cudaMallocAsync((void**)&r->ent, n_ent * sizeof(int2), st));
+  RCK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
   RCK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
+  RCK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
   RCK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
-  RCK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
   RCK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
   RCK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
-  r->bytes = (int64_t)(n_ent * sizeof(int2) + (size_t)(nb + 1) * 8 + (size_t)r->nbk * nb * 4 + 2 * (size_t)nb);
-  if (weight) {
-    RCK(cudaMallocAsync((void**)&r->weight, (size_t)nb * 8, st));
-    RCK(cudaMemcpyAsync(r->weight, weight, (size_t)nb * 8, cudaMemcpyDefault, st));
-    r->bytes += (int64_t)nb * 8;
-  }
+  r->bytes = (int64_t)(n_ent * sizeof(Pix) + (size_t)(nb + 1) * 12 + (size_t)r->nbk * nb * 4 + (size_t)nb);
   if (expected) {
     RCK(cudaMallocAsync((void**)&r->expected, (size_t)nb * 8, st));
     RCK(cudaMemcpyAsync(r->expected, expected, (size_t)nb * 8, cudaMemcpyDefault, st));
@@ -843,40 +922,53 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
     RCK(cudaMemcpyAsync(r->coverage, coverage, (size_t)nb * 8, cudaMemcpyDefault, st));
     r->bytes += (int64_t)nb * 8;
   }
+  if (weight) {
+    RCK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
+    r->bytes += nb;
+  }
   RCK(cudaMemcpyAsync(r->indptr, indptr, (size_t)(nb + 1) * 4, cudaMemcpyDefault, st));
   {
     Scratch tmp(st);
-    if (nnz > 0) {
-      const int32_t* dcol = col;
-      const int32_t* dcnt = count;
-      if (!is_device_ptr(col)) {
-        int32_t* t;
-        RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
-        RCK(cudaMemcpyAsync(t, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-        dcol = t;
-      }
-      if (!is_device_ptr(count)) {
-        int32_t* t;
-        RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
-        RCK(cudaMemcpyAsync(t, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-        dcnt = t;
-      }
-      int grid = (int)std::min<int64_t>((nnz + 255) / 256, 148 * 32);
-      k_interleave<<<grid, 256, 0, st>>>(dcol, dcnt, r->ent, nnz);
+    const int32_t* dcol = col;
+    const int32_t* dcnt = count;
+    const double* dw = weight;
+    if (nnz > 0 && !is_device_ptr(col)) {
+      int32_t* t;
+      RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
+      RCK(cudaMemcpyAsync(t, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+      dcol = t;
+    }
+    if (nnz > 0 && !is_device_ptr(count)) {
+      int32_t* t;
+      RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
+      RCK(cudaMemcpyAsync(t, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+      dcnt = t;
+    }
+    if (weight && !is_device_ptr(weight)) {
+      double* t;
+      RCK(tmp.alloc((void**)&t, (size_t)nb * 8));
+      RCK(cudaMemcpyAsync(t, weight, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
+      dw = t;
+    }
+    {
+      int warps = nb;
+      int grid = std::min((warps + 7) / 8, 148 * 16);
+      k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
+                                             ignore_diags, flags);
       ++g_launches;
       RCK(cudaGetLastError());
     }
     {
       int64_t total = (int64_t)nb * r->nbk;
       int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-      k_build_buckets<<<grid, 256, 0, st>>>(r->ent, r->indptr, r->bucket, nb, r->nbk, r->lb);
+      k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->bucket, nb, r->nbk, r->lb);
       ++g_launches;
       RCK(cudaGetLastError());
     }
     {
       int32_t* ebad32;
       RCK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
-      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(r->weight, r->expected, r->bad, r->ebad, ebad32, nb);
+      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, r->expected, r->bad, r->ebad, ebad32, nb);
       ++g_launches;
       RCK(cudaGetLastError());
       size_t tb = 0;
@@ -901,7 +993,7 @@ int pup_region_destroy(pup_region_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
-  void* ptrs[] = {r->ent, r->indptr, r->bucket, r->weight, r->expected, r->coverage, r->bad, r->ebad, r->ebadpre};
+  void* ptrs[] = {r->pix, r->indptr, r->rowend, r->bucket, r->expected, r->coverage, r->bad, r->ebad, r->ebadpre};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
   delete r;
@@ -909,16 +1001,18 @@ int pup_region_destroy(pup_region_t* r) {
 }
 
 int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0, const int32_t* slot,
-                   int W, int ignore_diags, int n_slots, unsigned flags, double* acc, void* stream,
-                   int64_t* n_valid_out) {
+                   int W, int n_slots, unsigned flags, double* acc, void* stream, int64_t* n_valid_out) {
   if (!m) return fail(PUP_E_ARG, "pup_accumulate: null region");
-  if (n_win < 0 || n_win >= (1ll << 31) || W <= 0 || W > 4096 || n_slots <= 0 || !acc)
+  if (n_win < 0 || n_win >= (1ll << 31) || W <= 0 || n_slots <= 0 || !acc)
     return fail(PUP_E_ARG, "pup_accumulate: bad sizes or null accumulator");
+  if (2 * W - 1 > VT) return fail(PUP_E_ARG, "pup_accumulate: W too large (max 256 bins)");
   if (n_win > 0 && (!r0 || !c0 || !slot)) return fail(PUP_E_ARG, "pup_accumulate: null window arrays");
-  if ((flags & (PUP_F_OOE | PUP_F_EXPCTRL)) && !m->expected)
+  if (flags & ~(PUP_F_EXPCTRL | PUP_F_COVERAGE))
+    return fail(PUP_E_ARG, "pup_accumulate: only PUP_F_EXPCTRL / PUP_F_COVERAGE apply (the others belong to the region)");
+  if ((flags & PUP_F_EXPCTRL) && !m->expected)
     return fail(PUP_E_ARG, "pup_accumulate: expected requested but the region has none");
-  if ((flags & PUP_F_OOE) && (flags & PUP_F_EXPCTRL))
-    return fail(PUP_E_ARG, "pup_accumulate: PUP_F_OOE and PUP_F_EXPCTRL are exclusive");
+  if ((flags & PUP_F_EXPCTRL) && (m->flags & PUP_F_OOE))
+    return fail(PUP_E_ARG, "pup_accumulate: PUP_F_EXPCTRL on a region prepared with PUP_F_OOE");
   if ((flags & PUP_F_COVERAGE) && !m->coverage)
     return fail(PUP_E_ARG, "pup_accumulate: coverage requested but the region has none");
   const int pb = ilog2_ceil((int64_t)m->nb + 1);
@@ -931,6 +1025,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   if (n_valid_out) *n_valid_out = 0;
   if (n_win == 0) return PUP_OK;
 
+  const unsigned all_flags = flags | m->flags;
   const AccLayout L(W);
   const int64_t acc_len = L.stride * n_slots;
   Scratch tmp(st);
@@ -957,22 +1052,22 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(cudaMemsetAsync(d_acc, 0, (size_t)acc_len * 8, st));
   }
 
-  // 1. sort keys
-  SpanGuard* span = new SpanGuard(0, st);
-  struct SpanDeleter {
-    SpanGuard** g;
-    ~SpanDeleter() {
-      if (*g) delete *g;
-    }
-  } span_deleter{&span};
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const int ch = std::max(1, env_int("PUP_CHUNK", 64));
   uint64_t *keys_a, *keys_b;
-  CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
-  CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
-  k_window_keys<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(d_r0, d_c0, d_slot, keys_a, n_win, m->nb, W, n_slots,
-                                                                  pb);
-  LAUNCH_CHECK("k_window_keys");
-  cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
+  int32_t *slot_start, *nchunks, *chunk_start;
+  int* counters;  // [0] main work counter, [1] dense-num work counter, [2] slow windows of this call
+  const uint64_t* keys;
   {
+    // 1. sort the windows by (slot, r0, c0) and cut every slot into chunks
+    SpanGuard span(0, st);
+    CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
+    CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
+    k_window_keys<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(d_r0, d_c0, d_slot, keys_a, n_win, m->nb, W,
+                                                                    n_slots, pb);
+    LAUNCH_CHECK("k_window_keys");
+    cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
     size_t tb = 0;
     // valid keys use 2*pb+sb bits and have bit (2*pb+sb) clear; the invalid marker (~0) has it set,
     // so sorting bits [0, 2*pb+sb+1) orders everything and puts the invalid windows last.
@@ -982,38 +1077,29 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(tmp.alloc(&t, tb));
     CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, end_bit, st));
     g_launches += (end_bit + 7) / 8 + 1;
-  }
-  const uint64_t* keys = dbuf.Current();
+    keys = dbuf.Current();
 
-  // 2. slot boundaries and chunk table
-  const int ch = std::max(1, env_int("PUP_CHUNK", 64));
-  int32_t *slot_start, *nchunks, *chunk_start;
-  CK(tmp.alloc((void**)&slot_start, (size_t)(n_slots + 1) * 4));
-  CK(tmp.alloc((void**)&nchunks, (size_t)(n_slots + 1) * 4));
-  CK(tmp.alloc((void**)&chunk_start, (size_t)(n_slots + 1) * 4));
-  k_slot_bounds<<<(n_slots + 1 + 127) / 128, 128, 0, st>>>(keys, (int)n_win, n_slots, pb, ch, slot_start, nchunks);
-  LAUNCH_CHECK("k_slot_bounds");
-  {
-    size_t tb = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, nchunks, chunk_start, n_slots + 1, st));
-    void* t;
-    CK(tmp.alloc(&t, tb));
-    CK(cub::DeviceScan::ExclusiveSum(t, tb, nchunks, chunk_start, n_slots + 1, st));
+    CK(tmp.alloc((void**)&slot_start, (size_t)(n_slots + 1) * 4));
+    CK(tmp.alloc((void**)&nchunks, (size_t)(n_slots + 1) * 4));
+    CK(tmp.alloc((void**)&chunk_start, (size_t)(n_slots + 1) * 4));
+    CK(tmp.alloc((void**)&counters, 16));
+    CK(cudaMemsetAsync(counters, 0, 16, st));
+    k_slot_bounds<<<(n_slots + 1 + 127) / 128, 128, 0, st>>>(keys, (int)n_win, n_slots, pb, ch, slot_start, nchunks);
+    LAUNCH_CHECK("k_slot_bounds");
+    size_t tb2 = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, nchunks, chunk_start, n_slots + 1, st));
+    void* t2;
+    CK(tmp.alloc(&t2, tb2));
+    CK(cub::DeviceScan::ExclusiveSum(t2, tb2, nchunks, chunk_start, n_slots + 1, st));
     ++g_launches;
   }
+  WinCtx ctx{m->nb, W, pb, m->ignore_diags, all_flags, m->ebadpre};
+  ChunkTable chunks{slot_start, chunk_start, n_slots, ch};
 
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
-  WinCtx ctx{m->nb, W, pb, ignore_diags, flags, m->ebadpre};
-
-  delete span;
-  span = nullptr;
-
-  // 3. per-window vector quantities
+  // 2. per-window vector quantities
   {
-    SpanGuard vspan(1, st);
-    if (2 * W - 1 > VT) return fail(PUP_E_ARG, "pup_accumulate: W too large for the vector kernel (max 256)");
-    VecParams vp{ctx, keys, slot_start, n_slots, m->weight ? m->bad : nullptr, m->expected, m->coverage, d_acc};
+    SpanGuard span(1, st);
+    VecParams vp{ctx, keys, slot_start, n_slots, m->bad, m->expected, m->coverage, d_acc, counters + 2};
     const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
     const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
     int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
@@ -1021,37 +1107,42 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     LAUNCH_CHECK("k_vector");
   }
 
-  // 4. the pile-up itself
+  // 3. the pile-up itself
   {
-    SpanGuard mspan(2, st);
-    int* counter;
-    CK(tmp.alloc((void**)&counter, 4));
-    CK(cudaMemsetAsync(counter, 0, 4, st));
-    // band height: keep the fp64 + int32 tile within PUP_TILE_KB so that >= 2 CTAs fit per SM
-    const int tile_kb = env_int("PUP_TILE_KB", 100);
-    int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (12ll * W));
-    int S = env_int("PUP_GROUP", 16);
-    if (S != 32) S = 16;
-    Wb = std::min(Wb, MAXOWN_LIMIT * (NT / 32) * (32 / S));
+    SpanGuard span(2, st);
+    int S = env_int("PUP_GROUP", 4);
+    if (S != 2 && S != 8 && S != 16) S = 4;
+    // band height: one tile row per row-group, fp64 tile within PUP_TILE_KB
+    const int tile_kb = env_int("PUP_TILE_KB", 72);
+    int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (8ll * W));
+    Wb = std::min(Wb, NT_MAX / S);
     if (Wb < 1) Wb = 1;
     const int n_bands = (W + Wb - 1) / Wb;
     Wb = (W + n_bands - 1) / n_bands;  // balance the bands
-    const size_t smem = (size_t)Wb * W * 12;
-    MainParams mp{ctx,          m->ent, m->indptr,  m->bucket,   m->lb,   m->weight, m->expected, m->bad, m->ebad,
-                  keys,         slot_start, chunk_start, n_slots, Wb,     n_bands,   ch,          d_acc,  counter};
-    const bool bal = m->weight != nullptr, ooe = (flags & PUP_F_OOE) != 0;
-    const int ngroups = (NT / 32) * (32 / S);
-    const int maxown = (Wb + ngroups - 1) / ngroups;
+    const int threads = std::min(NT_MAX, ((Wb * S + 31) / 32) * 32);
+    const size_t smem = (size_t)Wb * W * 8;
+    MainParams mp{ctx, m->pix, m->rowend, m->bucket, m->lb, m->bad, keys, chunks, Wb, n_bands, d_acc, counters};
     int occ = 1;
-    cudaError_t e = (S == 32) ? launch_main<32>(mp, 0, smem, st, bal, ooe, maxown, &occ)
-                              : launch_main<16>(mp, 0, smem, st, bal, ooe, maxown, &occ);
+    cudaError_t e = launch_main(S, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
-    int grid = n_sm * occ;
-    e = (S == 32) ? launch_main<32>(mp, grid, smem, st, bal, ooe, maxown, nullptr)
-                  : launch_main<16>(mp, grid, smem, st, bal, ooe, maxown, nullptr);
+    e = launch_main(S, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
+  }
+
+  // 4. dense pixel counts of the slow windows (returns at once when the call has none)
+  {
+    SpanGuard span(3, st);
+    const size_t smem = (size_t)W * W * 4;
+    if (smem > 220 * 1024) return fail(PUP_E_ARG, "pup_accumulate: W too large for the dense-num tile");
+    SlowParams sp{ctx, m->bad, m->ebad, keys, chunks, d_acc, counters + 2, counters + 1};
+    CK(cudaFuncSetAttribute(k_num_slow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_num_slow, 512, smem));
+    if (occ < 1) return fail(PUP_E_CUDA, "dense-num kernel does not fit on an SM");
+    k_num_slow<<<n_sm * occ, 512, smem, st>>>(sp);
+    LAUNCH_CHECK("k_num_slow");
   }
 
   // 5. outputs that live on the host
@@ -1078,10 +1169,12 @@ int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* in
                           const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags, double* acc,
                           void* stream, int64_t* n_valid_out) {
   pup_region_t* r = nullptr;
-  int rc = pup_region_create(device, nb, nnz, indptr, col, count, weight, expected, coverage, stream, &r);
+  int rc = pup_region_create(device, nb, nnz, indptr, col, count, weight, expected, coverage, ignore_diags,
+                             flags & (PUP_F_OOE | PUP_F_NODIAG), stream, &r);
   if (rc != PUP_OK) return rc;
   int l0 = g_launches;
-  rc = pup_accumulate(r, n_win, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream, n_valid_out);
+  rc = pup_accumulate(r, n_win, r0, c0, slot, W, n_slots, flags & (PUP_F_EXPCTRL | PUP_F_COVERAGE), acc, stream,
+                      n_valid_out);
   g_launches += l0;
   pup_region_destroy(r);
   return rc;
@@ -1146,7 +1239,7 @@ int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r
   CK(tmp.alloc((void**)&d_out, 16));
   CK(cudaMemsetAsync(d_out, 0, 16, st));
   if (n_win > 0) {
-    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->ent, m->indptr, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
+    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->pix, m->indptr, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_count_nnz", e);
   }
@@ -1154,7 +1247,7 @@ int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r
   CK(cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   int64_t per_win = 16 + (int64_t)(W + 1) * 4;
-  if (m->weight) per_win += 16ll * W;
+  if (m->bad) per_win += 16ll * W;
   if (flags & PUP_F_COVERAGE) per_win += 16ll * W;
   *bytes_out = (int64_t)h[1] * per_win + (int64_t)h[0] * 8;
   if (nnz_out) *nnz_out = (int64_t)h[0];

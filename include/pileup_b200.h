@@ -48,7 +48,8 @@ extern "C" {
 #define PUP_E_OOM (-3)   /* device allocation failed */
 #define PUP_E_NODEV (-4) /* no usable CUDA device */
 
-/* flags for pup_accumulate() */
+/* flags: OOE / NODIAG are properties of a prepared region (pup_region_create), EXPCTRL / COVERAGE of a call
+ * (pup_accumulate); pup_accumulate_region() takes the union. */
 #define PUP_F_OOE 1u      /* divide every pixel by expected[|col-row|]         (coolpup.py:1154-1156) */
 #define PUP_F_EXPCTRL 2u  /* also accumulate the bare expected block per window (coolpup.py:1135-1139, 1190-1191) */
 #define PUP_F_COVERAGE 4u /* accumulate cov_start / cov_end                      (coolpup.py:1151-1153) */
@@ -72,10 +73,16 @@ int pup_device_count(int* n_out);
  *                 pixel value = (weight[row] * weight[col]) * count, as cooler computes it.
  *   expected[nb]  expected value by |col-row| or NULL; entries beyond the table must be NaN
  *   coverage[nb]  per-bin coverage (coverage_norm) or NULL
+ *   ignore_diags  pixels with (col - row) < ignore_diags are masked (signed, coolpup.py:1141-1149)
+ *   flags         PUP_F_OOE: pixel values are divided by expected[|col-row|]; PUP_F_NODIAG: no diagonal mask
+ *
+ * The normalisation (balancing, expected divide, diagonal mask, NaN -> "adds nothing") is applied here, once per
+ * stored pixel, by a streaming kernel; the pile-up kernel then only gathers and adds.
  */
 int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
                       const int32_t* count, const double* weight, const double* expected,
-                      const double* coverage, void* stream, pup_region_t** out);
+                      const double* coverage, int ignore_diags, unsigned flags, void* stream,
+                      pup_region_t** out);
 int pup_region_destroy(pup_region_t* region);
 /* bytes of HBM held by the region, and the algorithmic bytes of its pixels (8 per stored pixel) */
 int64_t pup_region_device_bytes(const pup_region_t* region);
@@ -93,12 +100,12 @@ int64_t pup_acc_stride(int W);
  *   r0[i], c0[i]   region-relative first row / first column bin of window i (W x W bins)
  *   slot[i]        accumulator slot in [0, n_slots)
  * Windows not fully inside [0, nb) are skipped and not counted (coolpup.py:1111-1114).
- * Pixels with (col - row) < ignore_diags are masked (signed, coolpup.py:1141-1149).
+ *   flags          PUP_F_EXPCTRL and/or PUP_F_COVERAGE
  * n_valid_out (host pointer or NULL) receives the number of windows accumulated (forces a stream sync).
  */
 int pup_accumulate(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0,
-                   const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags, double* acc,
-                   void* stream, int64_t* n_valid_out);
+                   const int32_t* slot, int W, int n_slots, unsigned flags, double* acc, void* stream,
+                   int64_t* n_valid_out);
 
 /* One-shot convenience: pup_region_create + pup_accumulate + pup_region_destroy. */
 int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
@@ -125,9 +132,9 @@ int pup_last_launches(void);
 
 /*
  * Optional device-side timing for benchmarks: when enabled (per host thread), every pup_accumulate() records
- * CUDA events on the caller's stream around its three phases: [0] window sort + chunk plan, [1] vector kernel,
- * [2] main pile-up kernel.  pup_timing_read() waits for the recorded events and returns the summed milliseconds
- * and the number of spans per phase (arrays of 3); reset != 0 clears the records.
+ * CUDA events on the caller's stream around its four phases: [0] window sort + chunk plan, [1] vector kernel,
+ * [2] main pile-up kernel, [3] dense-num kernel.  pup_timing_read() waits for the recorded events and returns the
+ * summed milliseconds and the number of spans per phase (arrays of 4); reset != 0 clears the records.
  */
 int pup_timing_enable(int on);
 int pup_timing_read(double* ms_by_phase, int* count_by_phase, int reset);

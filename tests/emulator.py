@@ -28,8 +28,11 @@ def layout(W):
 
 
 class EmuRegion:
-    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, stream=0):
+    def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, ignore_diags=2,
+                 flags=0, stream=0):
         self.nb = int(nb)
+        self.ignore_diags = int(ignore_diags)
+        self.region_flags = int(flags) & (F_OOE | F_NODIAG)
         self.indptr, self.col, self.count = np.asarray(indptr), np.asarray(col), np.asarray(count)
         self.weight, self.expected, self.coverage = weight, expected, coverage
         self.bad = np.isnan(weight) if weight is not None else np.zeros(nb, dtype=bool)
@@ -58,7 +61,9 @@ class EmuRegion:
             return self.ebadpre[b + 1] - self.ebadpre[a] > 0
         return False
 
-    def accumulate(self, r0, c0, slot, W, ignore_diags, n_slots, flags, acc, stream=0, want_n_valid=False):
+    def accumulate(self, r0, c0, slot, W, n_slots, flags, acc, stream=0, want_n_valid=False):
+        ignore_diags = self.ignore_diags
+        flags = (int(flags) & (F_EXPCTRL | F_COVERAGE)) | self.region_flags
         L = layout(W)
         a = acc.numpy() if hasattr(acc, "numpy") else acc
         a = a.reshape(n_slots, L["stride"])

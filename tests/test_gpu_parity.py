@@ -107,12 +107,13 @@ def test_kernel_vs_oracle_random(mode, nb, W, dens, nwin, n_slots, memory):
         tens = [t(x) for x in (ip, col, cnt, weight, expected, coverage, r0, c0, sl)]
         acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], tens[5], stream=stream)
+        reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], tens[5], ignore_diags=2,
+                         flags=cfg["flags"], stream=stream)
         # two calls into the same accumulator: the buffer is purely additive
         half = nwin // 2
-        nv = reg.accumulate(tens[6][:half].contiguous(), tens[7][:half].contiguous(), tens[8][:half].contiguous(), W, 2,
+        nv = reg.accumulate(tens[6][:half].contiguous(), tens[7][:half].contiguous(), tens[8][:half].contiguous(), W,
                             n_slots, cfg["flags"], acc, stream=stream, want_n_valid=True)
-        nv += reg.accumulate(tens[6][half:].contiguous(), tens[7][half:].contiguous(), tens[8][half:].contiguous(), W, 2,
+        nv += reg.accumulate(tens[6][half:].contiguous(), tens[7][half:].contiguous(), tens[8][half:].contiguous(), W,
                              n_slots, cfg["flags"], acc, stream=stream, want_n_valid=True)
         out = nat.acc_export(acc, W, n_slots, device=0, stream=stream, want_expected=True, want_cov=True)
         reg.close()
@@ -179,7 +180,7 @@ def test_linearity_and_permutation_large():
     reg_t = synthetic_region(nb, depth=500.0, seed=11, device=dev, nan_frac=0.03)
     stream = torch.cuda.current_stream(dev).cuda_stream
     reg = nat.Region(0, nb, reg_t["indptr"], reg_t["col"], reg_t["count"], reg_t["weight"], reg_t["expected"], None,
-                     stream=stream)
+                     ignore_diags=2, flags=nat.PUP_F_OOE, stream=stream)
     g = torch.Generator(device="cpu").manual_seed(5)
     n = 200_000
     r0 = torch.randint(0, nb - W, (n,), generator=g, dtype=torch.int32)
@@ -191,7 +192,7 @@ def test_linearity_and_permutation_large():
     def run(parts):
         acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
         for idx in parts:
-            reg.accumulate(r0[idx].contiguous(), c0[idx].contiguous(), sl[idx].contiguous(), W, 2, n_slots, 1, acc, stream=stream)
+            reg.accumulate(r0[idx].contiguous(), c0[idx].contiguous(), sl[idx].contiguous(), W, n_slots, 0, acc, stream=stream)
         return nat.acc_export(acc, W, n_slots, device=0, stream=stream)
 
     base = run([torch.arange(n, device=dev)])
@@ -211,7 +212,7 @@ def test_linearity_and_permutation_large():
     ref = oracle_accumulate(nb, h(reg_t["indptr"]), h(reg_t["col"]), h(reg_t["count"]), h(reg_t["weight"]),
                             h(reg_t["expected"]), None, h(r0[:k]), h(c0[:k]), h(sl[:k]), W, 2, n_slots, ooe=True)
     acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
-    reg.accumulate(r0[:k].contiguous(), c0[:k].contiguous(), sl[:k].contiguous(), W, 2, n_slots, 1, acc, stream=stream)
+    reg.accumulate(r0[:k].contiguous(), c0[:k].contiguous(), sl[:k].contiguous(), W, n_slots, 0, acc, stream=stream)
     out = nat.acc_export(acc, W, n_slots, device=0, stream=stream)
     _check_against_oracle(k, out, ref)
     reg.close()
