@@ -140,7 +140,6 @@ constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel
 constexpr int VT = 512;      // max threads per CTA of the vector kernel
 constexpr int VCH = 256;     // windows per CTA step of the vector kernel
 constexpr int VU = 4;        // windows in flight per thread of the vector kernel
-constexpr int WU = 4;        // windows in flight per row-group of the main kernel
 constexpr int ROW_BAD = -1;  // rowend[] marker of a row whose weight is NaN
 
 // one stored pixel as the main kernel reads it: 16 bytes, one ld.global.nc.v4 per lane
@@ -500,18 +499,18 @@ struct MainParams {
 };
 
 // S lanes share one tile row; every row-group owns exactly one row of the band, so the shared-memory
-// read-modify-write needs no atomics.  WU windows are in flight per row-group to hide the L2 latency of the
-// dependent key -> bucket pointer -> pixel chain.
-template <int S>
-__global__ void __launch_bounds__(NT_MAX, 3) k_pileup_main(const MainParams p) {
+// read-modify-write needs no atomics and -- because a row-group also flushes and clears its own row -- the
+// kernel has no CTA-wide barrier at all: warps drift freely through the CTA's (static, round-robin) chunk list.
+// WU windows are processed in lockstep per row-group, so WU independent 16-byte loads are in flight per lane
+// while the dependent key -> bucket pointer -> pixel chain of each window resolves.
+template <int S, int WU>
+__global__ void __launch_bounds__(NT_MAX, (WU > 4 ? 2 : 3)) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = p.ctx.W;
   const int Wb = p.Wb;
   double* sumT = reinterpret_cast<double*>(smem_raw);
-  __shared__ int s_slot, s_lo, s_hi, s_band;
 
   const AccLayout L(W);
-  const int nthreads = blockDim.x;
   const int lane = threadIdx.x & 31;
   const int sub = lane / S;
   const int ls = lane % S;
@@ -519,63 +518,48 @@ __global__ void __launch_bounds__(NT_MAX, 3) k_pileup_main(const MainParams p) {
   const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
   const int nb = p.ctx.nb;
   const int pb = p.ctx.pb;
-  const int tile = Wb * W;
+  if (g >= Wb) return;  // no barriers below: idle row-groups may leave
 
-  for (int i = threadIdx.x; i < tile; i += nthreads) sumT[i] = 0.0;
+  double* trow = sumT + g * W;
+  for (int dj = ls; dj < W; dj += S) trow[dj] = 0.0;
+  __syncwarp(gmask);
   int cur_slot = -1, cur_band = 0;
   const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
+  const int total_items = total_chunks * p.n_bands;
 
-  auto flush = [&]() {
-    double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)cur_band * Wb * W;
-    int rows = min(Wb, W - cur_band * Wb);
-    int cells = rows * W;
-    for (int i = threadIdx.x; i < cells; i += nthreads) {
-      double v = sumT[i];
-      if (v != 0.0) {
-        atomicAdd(a + i, v);
-        sumT[i] = 0.0;
+  auto flush_row = [&]() {
+    // this row-group's tile row -> global accumulator (red.global.add.f64), then clear it
+    __syncwarp(gmask);
+    const int di = cur_band * Wb + g;
+    if (di < W) {
+      double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)di * W;
+      for (int dj = ls; dj < W; dj += S) {
+        double v = trow[dj];
+        if (v != 0.0) {
+          atomicAdd(a + dj, v);
+          trow[dj] = 0.0;
+        }
       }
     }
+    __syncwarp(gmask);
   };
 
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int item = atomicAdd(p.counter, 1);
-      if (item >= total_chunks * p.n_bands) {
-        s_slot = -1;
-      } else {
-        int band = item / total_chunks;
-        int slot, lo, hi;
-        locate_chunk(p.chunks, item - band * total_chunks, slot, lo, hi);
-        s_slot = slot;
-        s_band = band;
-        s_lo = lo;
-        s_hi = hi;
-      }
-    }
-    __syncthreads();
-    const int slot = s_slot;
-    if (slot < 0) break;
-    const int band = s_band;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    const int band = item / total_chunks;
+    int slot, w_lo, w_hi;
+    locate_chunk(p.chunks, item - band * total_chunks, slot, w_lo, w_hi);
     if (slot != cur_slot || band != cur_band) {
-      if (cur_slot >= 0) {
-        flush();
-        __syncthreads();
-      }
+      if (cur_slot >= 0) flush_row();
       cur_slot = slot;
       cur_band = band;
     }
-    const int row_lo = band * Wb;
-    const int nrows = min(Wb, W - row_lo);
-    const int w_lo = s_lo, w_hi = s_hi;
-    if (g >= nrows) continue;
+    const int di = band * Wb + g;
+    if (di >= W) continue;
 
-    double* trow = sumT + g * W;
-    const int di = row_lo + g;
     for (int w = w_lo; w < w_hi; w += WU) {
-      int idx[WU], pend[WU], c0s[WU];
-      Pix e[WU];
+      int idx[WU], pend[WU], c0s[WU], dj[WU];
+      double val[WU];
+      // stage A: window keys -> row pointers (WU independent chains)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
         idx[u] = 0;
@@ -590,61 +574,61 @@ __global__ void __launch_bounds__(NT_MAX, 3) k_pileup_main(const MainParams p) {
           c0s[u] = c0;
         }
       }
+      // stage B: first pixel of every window's run
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        e[u].col = 0x7fffffff;
-        e[u].val = 0.0;
+        dj[u] = 0x7fffffff;
+        val[u] = 0.0;
         if (idx[u] < pend[u]) {
           const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
-          e[u].col = raw.x;
-          e[u].val = __hiloint2double(raw.w, raw.z);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < WU; ++u) {
-        if (w + u < w_hi) {
-          const int c0 = c0s[u];
-          const int pe = pend[u];
-          if (pe == ROW_BAD) {
-            // masked row: nothing to sum; fast windows need the bad-row x bad-col correction of `num`
-            int kslot, r0, cc;
-            decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, cc);
-            if (p.bad != nullptr && !window_is_slow(p.ctx, r0, c0)) {
-              double* nrow = p.acc + (int64_t)cur_slot * L.stride + L.off_num + (int64_t)di * W;
-              for (int dj = ls; dj < W; dj += S)
-                if (__ldg(&p.bad[c0 + dj])) atomicAdd(nrow + dj, 1.0);
-            }
-          } else {
-            int col = e[u].col;
-            double val = e[u].val;
-            int id = idx[u];
-            for (;;) {
-              const int dj = col - c0;
-              if (dj >= W) break;
-              const int nid = id + S;
-              // dense rows need the next S pixels too: start that load before touching shared memory
-              int ncol = 0x7fffffff;
-              double nval = 0.0;
-              const bool more = nid < pe;
-              if (more) {
-                const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + nid));
-                ncol = raw.x;
-                nval = __hiloint2double(raw.w, raw.z);
-              }
-              if (dj >= 0) trow[dj] += val;
-              if (!more) break;
-              col = ncol;
-              val = nval;
-              id = nid;
-            }
+          dj[u] = raw.x - c0s[u];
+          val[u] = __hiloint2double(raw.w, raw.z);
+        } else if (pend[u] == ROW_BAD && p.bad != nullptr) {
+          // masked row: nothing to sum; fast windows need the bad-row x bad-col correction of `num`
+          int kslot, r0, cc;
+          decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, cc);
+          if (!window_is_slow(p.ctx, r0, cc)) {
+            double* nrow = p.acc + (int64_t)cur_slot * L.stride + L.off_num + (int64_t)di * W;
+            for (int j = ls; j < W; j += S)
+              if (__ldg(&p.bad[cc + j])) atomicAdd(nrow + j, 1.0);
           }
-          __syncwarp(gmask);
         }
       }
+      // stage C: the WU runs advance in lockstep, S pixels per run per iteration
+      for (;;) {
+        bool act[WU];
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          act[u] = dj[u] < W;
+          any = any || act[u];
+        }
+        if (!any) break;
+        int ndj[WU];
+        double nval[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          ndj[u] = 0x7fffffff;
+          nval[u] = 0.0;
+          const int nid = idx[u] + S;
+          if (act[u] && nid < pend[u]) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + nid));
+            ndj[u] = raw.x - c0s[u];
+            nval[u] = __hiloint2double(raw.w, raw.z);
+          }
+          idx[u] = nid;
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          if (act[u] && dj[u] >= 0) trow[dj[u]] += val[u];
+          dj[u] = ndj[u];
+          val[u] = nval[u];
+        }
+      }
+      __syncwarp(gmask);
     }
   }
-  __syncthreads();
-  if (cur_slot >= 0) flush();
+  if (cur_slot >= 0) flush_row();
 }
 
 // ------------------------------------------------------------------------------------------ dense-num kernel
@@ -769,21 +753,30 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
 }
 
 // occ != nullptr: only query the occupancy; else launch
-cudaError_t launch_main(int S, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
-#define PUP_LAUNCH(SV)                                                                                    \
+cudaError_t launch_main(int S, int WU, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
+                        int* occ) {
+#define PUP_LAUNCH(SV, WV)                                                                                \
   do {                                                                                                    \
-    auto kern = k_pileup_main<SV>;                                                                        \
+    auto kern = k_pileup_main<SV, WV>;                                                                    \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
     if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);              \
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                            \
   } while (0)
+  if (WU > 4) {
+    switch (S) {
+      case 2: PUP_LAUNCH(2, 8);
+      case 8: PUP_LAUNCH(8, 8);
+      case 16: PUP_LAUNCH(16, 8);
+      default: PUP_LAUNCH(4, 8);
+    }
+  }
   switch (S) {
-    case 2: PUP_LAUNCH(2);
-    case 8: PUP_LAUNCH(8);
-    case 16: PUP_LAUNCH(16);
-    default: PUP_LAUNCH(4);
+    case 2: PUP_LAUNCH(2, 4);
+    case 8: PUP_LAUNCH(8, 4);
+    case 16: PUP_LAUNCH(16, 4);
+    default: PUP_LAUNCH(4, 4);
   }
 #undef PUP_LAUNCH
 }
@@ -1123,10 +1116,11 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     const size_t smem = (size_t)Wb * W * 8;
     MainParams mp{ctx, m->pix, m->rowend, m->bucket, m->lb, m->bad, keys, chunks, Wb, n_bands, d_acc, counters};
     int occ = 1;
-    cudaError_t e = launch_main(S, mp, 0, threads, smem, st, &occ);
+    const int WUv = env_int("PUP_INFLIGHT", 4) > 4 ? 8 : 4;
+    cudaError_t e = launch_main(S, WUv, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
-    e = launch_main(S, mp, n_sm * occ, threads, smem, st, nullptr);
+    e = launch_main(S, WUv, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
   }
