@@ -140,7 +140,6 @@ constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel
 constexpr int VT = 512;      // max threads per CTA of the vector kernel
 constexpr int VCH = 256;     // windows per CTA step of the vector kernel
 constexpr int VU = 4;        // windows in flight per thread of the vector kernel
-constexpr int ROW_BAD = -1;  // rowend[] marker of a row whose weight is NaN
 
 // one stored pixel as the main kernel reads it: 16 bytes, one ld.global.nc.v4 per lane
 struct __align__(16) Pix {
@@ -181,7 +180,7 @@ struct pup_region {
   unsigned flags;     // PUP_F_OOE | PUP_F_NODIAG folded into the pixel values
   Pix* pix;           // [nnz] (col, normalised value)
   int32_t* indptr;    // [nb+1]
-  int32_t* rowend;    // [nb] indptr[r+1], or ROW_BAD when the row's weight is NaN
+  int32_t* rowend;    // [nb] indptr[r+1], or indptr[r] (empty run) when the row's weight is NaN
   int32_t* bucket;    // [nbk][nb] first entry of row r with col >= b << lb
   double* expected;   // [nb] or null
   double* coverage;   // [nb] or null
@@ -213,7 +212,7 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
       wr = weight[r];
       rbad = isnan(wr);
     }
-    if (lane == 0) rowend[r] = rbad ? ROW_BAD : hi;
+    if (lane == 0) rowend[r] = rbad ? lo : hi;  // masked rows contribute nothing: empty run
     for (int i = lo + lane; i < hi; i += 32) {
       const int c = col[i];
       double v = (double)cnt[i];
@@ -281,6 +280,15 @@ __global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __r
   int r = r0[i], c = c0[i], s = slot[i];
   bool ok = r >= 0 && c >= 0 && r + W <= nb && c + W <= nb && s >= 0 && s < n_slots;
   keys[i] = ok ? (((uint64_t)s << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c) : ~0ull;
+}
+
+// sorted keys -> (r0, c0) records, so that the main kernel does no 64-bit key arithmetic
+__global__ void k_decode_windows(const uint64_t* __restrict__ keys, int2* __restrict__ win, int64_t n, int pb) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t k = keys[i];
+  const uint64_t m = (1ull << pb) - 1;
+  win[i] = make_int2((int)((k >> pb) & m), (int)(k & m));
 }
 
 // slot_start[s] = first sorted window of slot s (s = n_slots: number of valid windows);
@@ -385,6 +393,8 @@ struct VecParams {
   const double* coverage;    // for COVERAGE
   double* acc;
   int* n_slow;               // number of slow windows of this call
+  int* xb;                   // [xb_copies][n_slots][W*W] privatised bad-row x bad-col counts (null when raw)
+  int xb_copies;
 };
 
 __global__ void k_vector(const VecParams p) {
@@ -395,6 +405,7 @@ __global__ void k_vector(const VecParams p) {
   const bool has_bad = p.bad != nullptr;
   const bool cov = (p.ctx.flags & PUP_F_COVERAGE) && p.coverage != nullptr;
   const bool ectl = (p.ctx.flags & PUP_F_EXPCTRL) && p.expected != nullptr;
+  __shared__ unsigned s_colmask[VU][VT / 32];
   int slow_total = 0;
   for (int base = blockIdx.x * VCH; base < n; base += gridDim.x * VCH) {
     const int end = min(base + VCH, n);
@@ -420,7 +431,7 @@ __global__ void k_vector(const VecParams p) {
       rb = cb = cs = ce = ts = tn = nn = nf = 0;
     };
     for (int w = base; w < end; w += VU) {
-      int slot[VU];
+      int slot[VU], c0s[VU];
       bool slow[VU];
       unsigned br[VU], bc[VU];
       double ca[VU], cbv[VU], ev[VU];
@@ -431,9 +442,11 @@ __global__ void k_vector(const VecParams p) {
         ca[u] = cbv[u] = 0.0;
         ev[u] = 0.0;
         slow[u] = false;
+        c0s[u] = 0;
         if (w + u < end) {
           int r0, c0;
           decode_key(__ldg(&p.keys[w + u]), p.ctx.pb, slot[u], r0, c0);
+          c0s[u] = c0;
           slow[u] = window_is_slow(p.ctx, r0, c0);
           if (t < W) {
             if (has_bad && !slow[u]) {
@@ -451,6 +464,15 @@ __global__ void k_vector(const VecParams p) {
           }
         }
       }
+      if (has_bad) {
+        // masked-column bitmask of every window of the batch, shared by the CTA
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          const unsigned cm = __ballot_sync(0xffffffffu, bc[u] != 0);
+          if ((t & 31) == 0) s_colmask[u][t >> 5] = cm;
+        }
+        __syncthreads();
+      }
 #pragma unroll
       for (int u = 0; u < VU; ++u) {
         if (slot[u] < 0) continue;
@@ -467,6 +489,18 @@ __global__ void k_vector(const VecParams p) {
         }
         rb += br[u];
         cb += bc[u];
+        if (br[u]) {
+          // masked row t of a fast window: rb and cb both subtract its masked columns -> add them back once
+          int* nrow = p.xb + ((int64_t)(blockIdx.x % p.xb_copies) * p.n_slots + cur) * L.w2 + (int64_t)t * W;
+          for (int wd = 0; wd * 32 < W; ++wd) {
+            unsigned m = s_colmask[u][wd];
+            while (m) {
+              const int j = wd * 32 + __ffs(m) - 1;
+              m &= m - 1;
+              atomicAdd(nrow + j, 1);
+            }
+          }
+        }
         if (cov && t < W) {
           if (!isnan(ca[u])) cs += ca[u];
           if (!isnan(cbv[u])) ce += cbv[u];
@@ -476,52 +510,69 @@ __global__ void k_vector(const VecParams p) {
           if (isfinite(ev[u])) tn += 1;
         }
       }
+      if (has_bad) __syncthreads();
     }
     flush();
   }
   if (t == 0 && slow_total > 0) atomicAdd(p.n_slow, slow_total);
 }
 
+// acc.num += sum over the privatised copies of the bad-row x bad-col counts
+__global__ void k_xb_reduce(const int* __restrict__ xb, int copies, int n_slots, int W, double* __restrict__ acc) {
+  const AccLayout L(W);
+  const int64_t total = (int64_t)n_slots * L.w2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int sum = 0;
+    for (int c = 0; c < copies; ++c) sum += xb[(int64_t)c * total + i];
+    if (sum != 0) {
+      const int64_t s = i / L.w2, cell = i - s * L.w2;
+      atomicAdd(acc + s * L.stride + L.off_num + cell, (double)sum);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 struct MainParams {
-  WinCtx ctx;
+  int W, nb, lb;
   const Pix* pix;
   const int32_t* rowend;
   const int32_t* bucket;
-  int lb;
-  const uint8_t* bad;  // null for raw counts
-  const uint64_t* keys;
+  const int2* win;  // sorted (r0, c0)
   ChunkTable chunks;
   int Wb;       // tile rows per band (<= row-groups per CTA)
   int n_bands;
   double* acc;
-  int* counter;
 };
+
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 
 // S lanes share one tile row; every row-group owns exactly one row of the band, so the shared-memory
 // read-modify-write needs no atomics and -- because a row-group also flushes and clears its own row -- the
 // kernel has no CTA-wide barrier at all: warps drift freely through the CTA's (static, round-robin) chunk list.
-// WU windows are processed in lockstep per row-group, so WU independent 16-byte loads are in flight per lane
-// while the dependent key -> bucket pointer -> pixel chain of each window resolves.
-template <int S, int WU>
-__global__ void __launch_bounds__(NT_MAX, (WU > 4 ? 2 : 3)) k_pileup_main(const MainParams p) {
+// WU windows advance in lockstep per row-group (two register sets, ping-pong), so WU independent 16-byte loads
+// are in flight per lane while the previous S pixels of every window are added to the tile.
+template <int S, int WU, int MINB>
+__global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int W = p.ctx.W;
+  const int W = p.W;
   const int Wb = p.Wb;
-  double* sumT = reinterpret_cast<double*>(smem_raw);
-
   const AccLayout L(W);
   const int lane = threadIdx.x & 31;
   const int sub = lane / S;
   const int ls = lane % S;
   const int g = (threadIdx.x >> 5) * (32 / S) + sub;  // row-group id == tile row owned
   const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
-  const int nb = p.ctx.nb;
-  const int pb = p.ctx.pb;
+  const int nb = p.nb;
   if (g >= Wb) return;  // no barriers below: idle row-groups may leave
 
-  double* trow = sumT + g * W;
-  for (int dj = ls; dj < W; dj += S) trow[dj] = 0.0;
+  unsigned trow = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(g * W) * 8u;  // my tile row
+  asm volatile("mov.u32 %0, %0;" : "+r"(trow));  // keep the address in a register (no rematerialisation)
+  for (int dj = ls; dj < W; dj += S) sts_f64(trow + dj * 8, 0.0);
   __syncwarp(gmask);
   int cur_slot = -1, cur_band = 0;
   const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
@@ -534,10 +585,10 @@ __global__ void __launch_bounds__(NT_MAX, (WU > 4 ? 2 : 3)) k_pileup_main(const 
     if (di < W) {
       double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)di * W;
       for (int dj = ls; dj < W; dj += S) {
-        double v = trow[dj];
+        const double v = lds_f64(trow + dj * 8);
         if (v != 0.0) {
           atomicAdd(a + dj, v);
-          trow[dj] = 0.0;
+          sts_f64(trow + dj * 8, 0.0);
         }
       }
     }
@@ -557,74 +608,68 @@ __global__ void __launch_bounds__(NT_MAX, (WU > 4 ? 2 : 3)) k_pileup_main(const 
     if (di >= W) continue;
 
     for (int w = w_lo; w < w_hi; w += WU) {
-      int idx[WU], pend[WU], c0s[WU], dj[WU];
-      double val[WU];
-      // stage A: window keys -> row pointers (WU independent chains)
+      int idx[WU], pend[WU], c0s[WU];
+      int djA[WU], djB[WU];
+      double vA[WU], vB[WU];
+#pragma unroll
+      for (int u = 0; u < WU; ++u) vB[u] = 0.0;
+      // stage A: window records -> row pointers (WU independent chains)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
         idx[u] = 0;
         pend[u] = 0;
         c0s[u] = 0;
         if (w + u < w_hi) {
-          int kslot, r0, c0;
-          decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, c0);
-          const int r = r0 + di;
-          idx[u] = __ldg(&p.bucket[(size_t)(c0 >> p.lb) * nb + r]) + ls;
+          const int2 rc = __ldg(&p.win[w + u]);
+          const int r = rc.x + di;
+          idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * nb + r]) + ls;
           pend[u] = __ldg(&p.rowend[r]);
-          c0s[u] = c0;
+          c0s[u] = rc.y;
         }
       }
       // stage B: first pixel of every window's run
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        dj[u] = 0x7fffffff;
-        val[u] = 0.0;
+        djA[u] = 0x7fffffff;
+        vA[u] = 0.0;
         if (idx[u] < pend[u]) {
           const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
-          dj[u] = raw.x - c0s[u];
-          val[u] = __hiloint2double(raw.w, raw.z);
-        } else if (pend[u] == ROW_BAD && p.bad != nullptr) {
-          // masked row: nothing to sum; fast windows need the bad-row x bad-col correction of `num`
-          int kslot, r0, cc;
-          decode_key(__ldg(&p.keys[w + u]), pb, kslot, r0, cc);
-          if (!window_is_slow(p.ctx, r0, cc)) {
-            double* nrow = p.acc + (int64_t)cur_slot * L.stride + L.off_num + (int64_t)di * W;
-            for (int j = ls; j < W; j += S)
-              if (__ldg(&p.bad[cc + j])) atomicAdd(nrow + j, 1.0);
-          }
+          djA[u] = raw.x - c0s[u];
+          vA[u] = __hiloint2double(raw.w, raw.z);
         }
       }
-      // stage C: the WU runs advance in lockstep, S pixels per run per iteration
+      // stage C: the WU runs advance in lockstep, S pixels per run per half-step
+#define PUP_HALF_STEP(CD, CV, ND, NV)                                                        \
+  {                                                                                          \
+    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
+      ND[u] = 0x7fffffff;                                                                    \
+      idx[u] += S;                                                                           \
+      if (CD[u] < W && idx[u] < pend[u]) {                                                   \
+        const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));               \
+        ND[u] = raw.x - c0s[u];                                                              \
+        NV[u] = __hiloint2double(raw.w, raw.z);                                              \
+      }                                                                                      \
+    }                                                                                        \
+    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
+      if ((unsigned)CD[u] < (unsigned)W) {                                                   \
+        const unsigned a = trow + (unsigned)CD[u] * 8u;                                      \
+        sts_f64(a, lds_f64(a) + CV[u]);                                                      \
+      }                                                                                      \
+    }                                                                                        \
+  }
       for (;;) {
-        bool act[WU];
-        bool any = false;
+        int mn = djA[0];
 #pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          act[u] = dj[u] < W;
-          any = any || act[u];
-        }
-        if (!any) break;
-        int ndj[WU];
-        double nval[WU];
+        for (int u = 1; u < WU; ++u) mn = min(mn, djA[u]);
+        if (mn >= W) break;
+        PUP_HALF_STEP(djA, vA, djB, vB)
+        mn = djB[0];
 #pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          ndj[u] = 0x7fffffff;
-          nval[u] = 0.0;
-          const int nid = idx[u] + S;
-          if (act[u] && nid < pend[u]) {
-            const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + nid));
-            ndj[u] = raw.x - c0s[u];
-            nval[u] = __hiloint2double(raw.w, raw.z);
-          }
-          idx[u] = nid;
-        }
-#pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          if (act[u] && dj[u] >= 0) trow[dj[u]] += val[u];
-          dj[u] = ndj[u];
-          val[u] = nval[u];
-        }
+        for (int u = 1; u < WU; ++u) mn = min(mn, djB[u]);
+        if (mn >= W) break;
+        PUP_HALF_STEP(djB, vB, djA, vA)
       }
+#undef PUP_HALF_STEP
       __syncwarp(gmask);
     }
   }
@@ -753,31 +798,23 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
 }
 
 // occ != nullptr: only query the occupancy; else launch
-cudaError_t launch_main(int S, int WU, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
+cudaError_t launch_main(int S, int minb, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
                         int* occ) {
-#define PUP_LAUNCH(SV, WV)                                                                                \
+#define PUP_LAUNCH(SV, MB)                                                                                \
   do {                                                                                                    \
-    auto kern = k_pileup_main<SV, WV>;                                                                    \
+    auto kern = k_pileup_main<SV, 4, MB>;                                                                 \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
     if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);              \
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                            \
   } while (0)
-  if (WU > 4) {
-    switch (S) {
-      case 2: PUP_LAUNCH(2, 8);
-      case 8: PUP_LAUNCH(8, 8);
-      case 16: PUP_LAUNCH(16, 8);
-      default: PUP_LAUNCH(4, 8);
-    }
+  if (minb >= 3) {
+    if (S == 8) PUP_LAUNCH(8, 3);
+    PUP_LAUNCH(4, 3);
   }
-  switch (S) {
-    case 2: PUP_LAUNCH(2, 4);
-    case 8: PUP_LAUNCH(8, 4);
-    case 16: PUP_LAUNCH(16, 4);
-    default: PUP_LAUNCH(4, 4);
-  }
+  if (S == 8) PUP_LAUNCH(8, 2);
+  PUP_LAUNCH(4, 2);
 #undef PUP_LAUNCH
 }
 
@@ -881,7 +918,9 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
   } else {
     int lb = (int)floor(log2((double)target * nb / avg));
     if (lb < 3) lb = 3;
-    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20)) ++lb;  // <= 25% of pixels
+    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20) ||  // <= 25% of pixels
+           ((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb >= (1ll << 31))                           // 32-bit index
+      ++lb;
     r->lb = lb;
     r->nbk = (nb + (1 << lb) - 1) >> lb;
   }
@@ -1052,6 +1091,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   int32_t *slot_start, *nchunks, *chunk_start;
   int* counters;  // [0] main work counter, [1] dense-num work counter, [2] slow windows of this call
   const uint64_t* keys;
+  int2* win;
   {
     // 1. sort the windows by (slot, r0, c0) and cut every slot into chunks
     SpanGuard span(0, st);
@@ -1071,6 +1111,9 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, end_bit, st));
     g_launches += (end_bit + 7) / 8 + 1;
     keys = dbuf.Current();
+    CK(tmp.alloc((void**)&win, (size_t)n_win * 8));
+    k_decode_windows<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(keys, win, n_win, pb);
+    LAUNCH_CHECK("k_decode_windows");
 
     CK(tmp.alloc((void**)&slot_start, (size_t)(n_slots + 1) * 4));
     CK(tmp.alloc((void**)&nchunks, (size_t)(n_slots + 1) * 4));
@@ -1092,19 +1135,32 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   // 2. per-window vector quantities
   {
     SpanGuard span(1, st);
-    VecParams vp{ctx, keys, slot_start, n_slots, m->bad, m->expected, m->coverage, d_acc, counters + 2};
+    int* xb = nullptr;
+    int xb_copies = 1;
+    const int64_t xb_one = (int64_t)n_slots * W * W;
+    if (m->bad) {
+      xb_copies = (int)std::max<int64_t>(1, std::min<int64_t>(64, (64ll << 20) / (xb_one * 4)));
+      CK(tmp.alloc((void**)&xb, (size_t)(xb_one * xb_copies) * 4));
+      CK(cudaMemsetAsync(xb, 0, (size_t)(xb_one * xb_copies) * 4, st));
+    }
+    VecParams vp{ctx, keys, slot_start, n_slots, m->bad, m->expected, m->coverage, d_acc, counters + 2, xb, xb_copies};
     const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
     const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
     int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
     k_vector<<<grid, vthreads, 0, st>>>(vp);
     LAUNCH_CHECK("k_vector");
+    if (m->bad) {
+      int rgrid = (int)std::min<int64_t>((xb_one + 255) / 256, (int64_t)n_sm * 8);
+      k_xb_reduce<<<rgrid, 256, 0, st>>>(xb, xb_copies, n_slots, W, d_acc);
+      LAUNCH_CHECK("k_xb_reduce");
+    }
   }
 
   // 3. the pile-up itself
   {
     SpanGuard span(2, st);
     int S = env_int("PUP_GROUP", 4);
-    if (S != 2 && S != 8 && S != 16) S = 4;
+    if (S != 8) S = 4;
     // band height: one tile row per row-group, fp64 tile within PUP_TILE_KB
     const int tile_kb = env_int("PUP_TILE_KB", 72);
     int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (8ll * W));
@@ -1114,13 +1170,13 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     Wb = (W + n_bands - 1) / n_bands;  // balance the bands
     const int threads = std::min(NT_MAX, ((Wb * S + 31) / 32) * 32);
     const size_t smem = (size_t)Wb * W * 8;
-    MainParams mp{ctx, m->pix, m->rowend, m->bucket, m->lb, m->bad, keys, chunks, Wb, n_bands, d_acc, counters};
+    MainParams mp{W, m->nb, m->lb, m->pix, m->rowend, m->bucket, win, chunks, Wb, n_bands, d_acc};
     int occ = 1;
-    const int WUv = env_int("PUP_INFLIGHT", 4) > 4 ? 8 : 4;
-    cudaError_t e = launch_main(S, WUv, mp, 0, threads, smem, st, &occ);
+    const int minb = env_int("PUP_MINBLOCKS", 2);
+    cudaError_t e = launch_main(S, minb, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
-    e = launch_main(S, WUv, mp, n_sm * occ, threads, smem, st, nullptr);
+    e = launch_main(S, minb, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
   }
