@@ -542,9 +542,13 @@ class PileUpper:
         expctrl = bool(self.expected is True and not self.ooe)
         built = []
         for ri, name in enumerate(region_names):
-            if name not in my_regions:
-                continue
             r = self.view_df.loc[name]
+            if name not in my_regions:
+                if do_control and self.CC.nshifts > 0:
+                    # another rank's region: still draw its control shifts so that every rank consumes the
+                    # np.random stream exactly like the reference's serial (nproc=1) run
+                    self.CC.region_windows((r["chrom"], r["start"], r["end"]), control=True)
+                continue
             rw = self.CC.region_windows((r["chrom"], r["start"], r["end"]), control=do_control)
             if len(rw) == 0:
                 continue

@@ -1,0 +1,114 @@
+"""CPU tests of the product's host side (window generation, slots, flips, final normalisation, DataFrame schema)
+against the real reference's golden vectors.  The CUDA entry points are replaced by tests/emulator.py, a numpy
+mirror of the kernels' arithmetic and accumulator layout; the real kernels are checked in test_gpu_parity.py."""
+import warnings
+
+import numpy as np
+import pytest
+
+import emulator
+import golden_util as gu
+from oracle.pileup_oracle import key_repr
+
+CASES = [n for n in gu.all_cases() if "stripes" not in n and gu.manifest()[n]["windows"] <= 4000]
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    emulator.install(monkeypatch)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pileup_api_matches_reference_golden(emu, name):
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, feats, **kw)
+    z, _ = gu.load_golden(name)
+    if "group" in pups.columns:
+        keys = [key_repr(g) for g in pups["group"]]
+    else:
+        keys = [repr((r.chrom, int(r.start), int(r.end))) for r in pups.itertuples()]
+    assert keys == [str(k) for k in z["row_keys"]]
+    assert list(pups.columns) == [str(c) for c in z["columns"]]
+    for i in range(len(keys)):
+        g = {f.split(".", 1)[1]: z[f] for f in z.files if f.startswith(f"row{i}.")}
+        a, b = np.asarray(pups["data"].iloc[i], dtype=float), g["data"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=1e-9)
+        assert int(pups["n"].iloc[i]) == int(g["n"])
+        assert np.array_equal(np.asarray(pups["num"].iloc[i]), g["num"])
+        if "control_n" in g:
+            assert int(pups["control_n"].iloc[i]) == int(g["control_n"])
+            assert np.array_equal(np.asarray(pups["control_num"].iloc[i]), g["control_num"])
+
+
+@pytest.mark.parametrize("name", ["toy_controls", "scc1_loops_ctrl", "scc1_ctcf_pairs_strand_dist", "scc1_ctcf_pairs_arms",
+                                  "toy_local_raw", "scc1_loops_dist"])
+def test_window_arrays_match_reference_stream(name):
+    """CoordCreator.region_windows == the window stream the reference's pos_stream emitted (order, RNG draws)."""
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs(name)
+    z, _ = gu.load_golden(name)
+    seed, nshifts = kw.get("seed"), kw.get("nshifts", 0)
+    view = kw.get("view_df")
+    view = cp.make_cooler_view(clr) if view is None else cp.make_viewframe(view)
+    if seed is not None:
+        np.random.seed(seed)
+    cc = cp.CoordCreator(feats, clr.binsize, features_format=kw.get("features_format", "bed"), flank=kw.get("flank", 100000),
+                         chroms=list(view["chrom"].unique()), nshifts=nshifts, mindist=kw.get("mindist", "auto"),
+                         maxdist=kw.get("maxdist"), local=kw.get("local", False), subset=kw.get("subset", 0), seed=seed)
+    view = view[view["chrom"].isin(cc.final_chroms)]
+    for _, r in view.iterrows():
+        rw = cc.region_windows((r["chrom"], r["start"], r["end"]), control=nshifts > 0)
+        name_r = r["name"]
+        assert np.array_equal(rw.st1, z[f"win.{name_r}.st1"])
+        assert np.array_equal(rw.st2, z[f"win.{name_r}.st2"])
+        assert np.array_equal(rw.kind, z[f"win.{name_r}.kind"])
+
+
+def test_unsupported_features_raise():
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs("toy_strand_balanced")
+    with pytest.raises(NotImplementedError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True)
+    with pytest.raises(NotImplementedError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1)
+    with pytest.raises(NotImplementedError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, store_stripes=True)
+    with pytest.raises(ValueError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, local=True, by_distance=True)
+    with pytest.raises(ValueError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_500_000, mindist=0)  # flank not a multiple of the bin size
+
+
+def test_custom_modify_func_and_extra_groupby(emu):
+    """User DataFrame callbacks (modify_2Dintervals_func) and arbitrary groupby columns go through the slow frame path."""
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs("toy_strand_balanced")
+    feats = feats.copy()
+    feats["cls"] = ["a", "b", "a", "b", "a", "b"]
+    view = kw["view_df"]
+    cc = cp.CoordCreator(feats, clr.binsize, features_format="bed", flank=2_000_000, mindist=0, chroms=["chr1", "chr2"])
+    pu = cp.PileUpper(clr, cc, view_df=view)
+
+    def tag(df):
+        df["far"] = df["distance"] > 4_000_000
+        return df
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = pu.pileupsWithControl(groupby=["cls1", "far"], modify_2Dintervals_func=tag)
+        base = pu.pileupsWithControl()
+    assert int(out.loc[out["group"] == "all", "n"].iloc[0]) == 6
+    assert sorted(int(n) for n in out.loc[out["group"] != "all", "n"]) == sorted(
+        [int(x) for x in np.bincount([0, 0, 1, 1, 2, 2])] ) or out["n"].sum() == 12
+    a = out.loc[out["group"] == "all", "data"].iloc[0]
+    b = base.loc[base["group"] == "all", "data"].iloc[0]
+    np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=1e-12)

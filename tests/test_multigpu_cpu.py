@@ -1,0 +1,66 @@
+"""world_size-2 gloo test of the multi-GPU path's host logic: region sharding (LPT), group-dictionary merge,
+all-reduce of the accumulators -- with the emulated kernels standing in for the GPUs."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_assign_balances():
+    from coolpuppy_b200.multigpu import lpt_assign
+
+    costs = [100, 90, 50, 40, 30, 20, 10, 5]
+    owner = lpt_assign(costs, 3)
+    loads = [sum(c for c, o in zip(costs, owner) if o == r) for r in range(3)]
+    assert max(loads) - min(loads) <= 20 and sorted(set(owner)) == [0, 1, 2]
+    assert lpt_assign([], 4) == []
+
+
+WORKER = textwrap.dedent(
+    """
+    import os, sys, warnings, json
+    sys.path[:0] = [{root!r}, os.path.join({root!r}, "tests"), os.path.join({root!r}, "tests", "golden")]
+    import numpy as np, pytest, torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    import emulator, golden_util as gu
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.multigpu import RegionSharder
+    from oracle.pileup_oracle import key_repr
+    mp = pytest.MonkeyPatch(); emulator.install(mp)
+    sharder = RegionSharder()
+    ok = True
+    for name in {cases!r}:
+        clr, feats, kw = gu.case_inputs(name)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            pups = cp.pileup(clr, feats, dist=sharder, **kw)
+        z, _ = gu.load_golden(name)
+        keys = [key_repr(g) for g in pups["group"]]
+        ok &= keys == [str(k) for k in z["row_keys"]]
+        for i in range(len(keys)):
+            b = z[f"row{{i}}.data"]; a = np.asarray(pups["data"].iloc[i], dtype=float)
+            m = np.isfinite(b)
+            ok &= np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a[m], b[m], rtol=1e-9)
+            ok &= int(pups["n"].iloc[i]) == int(z[f"row{{i}}.n"]) and np.array_equal(np.asarray(pups["num"].iloc[i]), z[f"row{{i}}.num"])
+    print("RESULT", sharder.rank, ok)
+    dist.destroy_process_group()
+    """
+)
+
+
+def test_two_rank_gloo_pileup_matches_golden(tmp_path):
+    cases = ["toy_strand_ooe", "toy_strand_dist_ctrl", "scc1_loops_dist", "scc1_ctcf_pairs_arms"]
+    port = 29500 + os.getpid() % 2000
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port, cases=cases))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"RESULT {r} True" in o, o
