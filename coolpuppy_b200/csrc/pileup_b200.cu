@@ -911,7 +911,7 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
 
   // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
   double avg = (double)nnz / nb;
-  int target = env_int("PUP_BUCKET_TARGET", 8);
+  int target = env_int("PUP_BUCKET_TARGET", 4);
   if (avg <= 24.0) {
     r->lb = 31;
     r->nbk = 1;
