@@ -16,7 +16,7 @@
 //
 // `num` (count of finite contributions) is dense in the reference (W*W work per window).  Here it is
 //   num = n_fast - rowbad[di] - colbad[dj] + xtile[di][dj]
-// with O(W) vector work per window (k_vector) plus a sparse bad-row x bad-col correction; only windows that
+// with a few masked-bin lookups per window (k_window_counts) incl. a sparse bad-row x bad-col correction; only windows that
 // touch the masked diagonals / NaN expected values ("slow" windows) take the dense W*W path (k_num_slow).
 #include "pileup_b200.h"
 
@@ -88,12 +88,27 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail(PUP_E_CUDA, "launch " name, e_);                        \
   } while (0)
 
+// keep freed stream-ordered allocations in the device's default pool instead of returning them to the driver
+// at every synchronisation (scratch buffers are re-used by the next call)
+void retain_pool_memory(int dev) {
+  static bool done[64] = {};
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  cudaGetLastError();
+  done[dev] = true;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
   explicit DeviceGuard(int dev) {
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     ok = cudaSetDevice(dev) == cudaSuccess;
+    if (ok) retain_pool_memory(dev);
   }
   ~DeviceGuard() {
     if (prev >= 0) cudaSetDevice(prev);
@@ -185,6 +200,8 @@ struct pup_region {
   double* expected;   // [nb] or null
   double* coverage;   // [nb] or null
   uint8_t* bad;       // [nb] weight is NaN; null for raw counts
+  int32_t* badpre;    // [nb+1] exclusive prefix count of masked bins; null for raw counts
+  int32_t* badlist;   // sorted masked bins
   uint8_t* ebad;      // [nb] expected is NaN or 0
   int32_t* ebadpre;   // [nb+1] exclusive prefix of ebad
   cudaStream_t stream;
@@ -252,15 +269,26 @@ __global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* 
   }
 }
 
+__global__ void k_badlist(const uint8_t* __restrict__ bad, const int32_t* __restrict__ badpre,
+                          int32_t* __restrict__ badlist, int nb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nb && bad[i]) badlist[badpre[i]] = i;
+}
+
 __global__ void k_masks(const double* __restrict__ weight, const double* __restrict__ expected, uint8_t* bad,
-                        uint8_t* ebad, int32_t* ebad32, int nb) {
+                        uint8_t* ebad, int32_t* ebad32, int32_t* bad32, int nb) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > nb) return;
   if (i == nb) {
     ebad32[i] = 0;
+    if (bad32 != nullptr) bad32[i] = 0;
     return;
   }
-  if (bad != nullptr) bad[i] = isnan(weight[i]) ? 1 : 0;
+  if (bad != nullptr) {
+    const int b = isnan(weight[i]) ? 1 : 0;
+    bad[i] = (uint8_t)b;
+    bad32[i] = b;
+  }
   uint8_t eb = 0;
   if (expected != nullptr) {
     double e = expected[i];
@@ -380,21 +408,94 @@ __device__ __forceinline__ void locate_chunk(const ChunkTable& t, int chunk, int
   hi = min(lo + t.ch, __ldg(&t.slot_start[a + 1]));
 }
 
+// ------------------------------------------------------------------------------------------ window counts
+// Everything `num` needs from a fast window besides the pixels: which of its rows / columns are masked bins.
+// Masked bins are sparse, so instead of scanning 2W flags per window one thread per window looks its masked rows
+// and columns up in the region's sorted masked-bin list (two prefix-count reads per side) and adds them to
+// privatised int32 tiles: rb[di], cb[dj] and the masked-row x masked-column correction xb[di][dj].
+// Layout of one private copy: [n_slots][W*W + 2*W + 2] ints = xb | rb | cb | n_slow | pad.
+struct CountParams {
+  WinCtx ctx;
+  const uint64_t* keys;
+  const int32_t* slot_start;  // [n_slots+1]
+  int n_slots;
+  const int32_t* badpre;     // [nb+1] exclusive prefix count of masked bins; null for raw counts
+  const int32_t* badlist;    // sorted masked bins
+  int* counts;               // [copies][n_slots][cstride]
+  int copies;
+  int* n_slow;               // number of slow windows of this call
+};
+
+__device__ __forceinline__ int64_t count_stride(int W) { return (int64_t)W * W + 2 * W + 2; }
+
+__global__ void __launch_bounds__(256) k_window_counts(const CountParams p) {
+  const int n = __ldg(&p.slot_start[p.n_slots]);
+  const int W = p.ctx.W;
+  const int64_t cs = count_stride(W);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool slow = false;
+  if (i < n) {
+    int slot, r0, c0;
+    decode_key(__ldg(&p.keys[i]), p.ctx.pb, slot, r0, c0);
+    slow = window_is_slow(p.ctx, r0, c0);
+    int* base = p.counts + ((int64_t)(blockIdx.x % p.copies) * p.n_slots + slot) * cs;
+    if (slow) {
+      atomicAdd(base + (int64_t)W * W + 2 * W, 1);
+    } else if (p.badpre != nullptr) {
+      const int a0 = __ldg(&p.badpre[r0]), a1 = __ldg(&p.badpre[r0 + W]);
+      const int b0 = __ldg(&p.badpre[c0]), b1 = __ldg(&p.badpre[c0 + W]);
+      int* rb = base + (int64_t)W * W;
+      int* cb = rb + W;
+      for (int k = a0; k < a1; ++k) atomicAdd(rb + (__ldg(&p.badlist[k]) - r0), 1);
+      for (int k = b0; k < b1; ++k) atomicAdd(cb + (__ldg(&p.badlist[k]) - c0), 1);
+      for (int k = a0; k < a1; ++k) {
+        const int di = __ldg(&p.badlist[k]) - r0;
+        for (int l = b0; l < b1; ++l) atomicAdd(base + (int64_t)di * W + (__ldg(&p.badlist[l]) - c0), 1);
+      }
+    }
+  }
+  if (__syncthreads_or(slow) && threadIdx.x == 0) atomicAdd(p.n_slow, 1);  // "this call has slow windows"
+}
+
+// acc += private copies; n comes from the slot boundaries, n_fast = n - n_slow
+__global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int n_slots, int W,
+                                const int32_t* __restrict__ slot_start, double* __restrict__ acc) {
+  const AccLayout L(W);
+  const int64_t cs = count_stride(W);
+  const int64_t total = (int64_t)n_slots * cs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int sum = 0;
+    for (int c = 0; c < copies; ++c) sum += counts[(int64_t)c * total + i];
+    const int64_t s = i / cs, j = i - s * cs;
+    double* a = acc + s * L.stride;
+    if (j < L.w2) {
+      if (sum) atomicAdd(a + L.off_num + j, (double)sum);
+    } else if (j < L.w2 + W) {
+      if (sum) atomicAdd(a + L.off_rb + (j - L.w2), (double)sum);
+    } else if (j < L.w2 + 2 * W) {
+      if (sum) atomicAdd(a + L.off_cb + (j - L.w2 - W), (double)sum);
+    } else if (j == L.w2 + 2 * W) {
+      const int nwin = slot_start[s + 1] - slot_start[s];
+      if (nwin) {
+        atomicAdd(a + L.off_n, (double)nwin);
+        atomicAdd(a + L.off_nfast, (double)(nwin - sum));
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ vector kernel
-// Per-window O(W) quantities: n, n_fast, bad-row / bad-col counts, coverage sums, Toeplitz sums of the bare
-// expected block.  One CTA walks VCH consecutive sorted windows, VU at a time; thread t owns vector index t.
+// Per-window O(W) fp64 quantities, only launched when requested: coverage sums (PUP_F_COVERAGE) and the Toeplitz
+// sums of the bare expected block (PUP_F_EXPCTRL).  One CTA walks VCH consecutive sorted windows, VU at a time;
+// thread t owns vector index t.
 struct VecParams {
   WinCtx ctx;
   const uint64_t* keys;
   const int32_t* slot_start;  // [n_slots+1]
   int n_slots;
-  const uint8_t* bad;        // null when raw
   const double* expected;    // for EXPCTRL
   const double* coverage;    // for COVERAGE
   double* acc;
-  int* n_slow;               // number of slow windows of this call
-  int* xb;                   // [xb_copies][n_slots][W*W] privatised bad-row x bad-col counts (null when raw)
-  int xb_copies;
 };
 
 __global__ void k_vector(const VecParams p) {
@@ -402,21 +503,16 @@ __global__ void k_vector(const VecParams p) {
   const int W = p.ctx.W;
   const AccLayout L(W);
   const int t = threadIdx.x;
-  const bool has_bad = p.bad != nullptr;
   const bool cov = (p.ctx.flags & PUP_F_COVERAGE) && p.coverage != nullptr;
   const bool ectl = (p.ctx.flags & PUP_F_EXPCTRL) && p.expected != nullptr;
-  __shared__ unsigned s_colmask[VU][VT / 32];
-  int slow_total = 0;
   for (int base = blockIdx.x * VCH; base < n; base += gridDim.x * VCH) {
     const int end = min(base + VCH, n);
     int cur = -1;
-    double rb = 0, cb = 0, cs = 0, ce = 0, ts = 0, tn = 0, nn = 0, nf = 0;
+    double cs = 0, ce = 0, ts = 0, tn = 0;
     auto flush = [&]() {
       if (cur < 0) return;
       double* a = p.acc + (int64_t)cur * L.stride;
       if (t < W) {
-        if (rb != 0) atomicAdd(a + L.off_rb + t, rb);
-        if (cb != 0) atomicAdd(a + L.off_cb + t, cb);
         if (cs != 0) atomicAdd(a + L.off_covs + t, cs);
         if (ce != 0) atomicAdd(a + L.off_cove + t, ce);
       }
@@ -424,39 +520,22 @@ __global__ void k_vector(const VecParams p) {
         if (ts != 0) atomicAdd(a + L.off_tsum + t, ts);
         if (tn != 0) atomicAdd(a + L.off_tnum + t, tn);
       }
-      if (t == 0) {
-        atomicAdd(a + L.off_n, nn);
-        if (nf != 0) atomicAdd(a + L.off_nfast, nf);
-      }
-      rb = cb = cs = ce = ts = tn = nn = nf = 0;
+      cs = ce = ts = tn = 0;
     };
     for (int w = base; w < end; w += VU) {
-      int slot[VU], c0s[VU];
-      bool slow[VU];
-      unsigned br[VU], bc[VU];
+      int slot[VU];
       double ca[VU], cbv[VU], ev[VU];
 #pragma unroll
       for (int u = 0; u < VU; ++u) {
         slot[u] = -1;
-        br[u] = bc[u] = 0;
         ca[u] = cbv[u] = 0.0;
         ev[u] = 0.0;
-        slow[u] = false;
-        c0s[u] = 0;
         if (w + u < end) {
           int r0, c0;
           decode_key(__ldg(&p.keys[w + u]), p.ctx.pb, slot[u], r0, c0);
-          c0s[u] = c0;
-          slow[u] = window_is_slow(p.ctx, r0, c0);
-          if (t < W) {
-            if (has_bad && !slow[u]) {
-              br[u] = p.bad[r0 + t];
-              bc[u] = p.bad[c0 + t];
-            }
-            if (cov) {
-              ca[u] = __ldg(&p.coverage[r0 + t]);
-              cbv[u] = __ldg(&p.coverage[c0 + t]);
-            }
+          if (cov && t < W) {
+            ca[u] = __ldg(&p.coverage[r0 + t]);
+            cbv[u] = __ldg(&p.coverage[c0 + t]);
           }
           if (ectl && t < 2 * W - 1) {
             int d = c0 - r0 + t - (W - 1);
@@ -464,42 +543,12 @@ __global__ void k_vector(const VecParams p) {
           }
         }
       }
-      if (has_bad) {
-        // masked-column bitmask of every window of the batch, shared by the CTA
-#pragma unroll
-        for (int u = 0; u < VU; ++u) {
-          const unsigned cm = __ballot_sync(0xffffffffu, bc[u] != 0);
-          if ((t & 31) == 0) s_colmask[u][t >> 5] = cm;
-        }
-        __syncthreads();
-      }
 #pragma unroll
       for (int u = 0; u < VU; ++u) {
         if (slot[u] < 0) continue;
         if (slot[u] != cur) {
           flush();
           cur = slot[u];
-        }
-        if (t == 0) {
-          nn += 1;
-          if (!slow[u])
-            nf += 1;
-          else
-            slow_total += 1;
-        }
-        rb += br[u];
-        cb += bc[u];
-        if (br[u]) {
-          // masked row t of a fast window: rb and cb both subtract its masked columns -> add them back once
-          int* nrow = p.xb + ((int64_t)(blockIdx.x % p.xb_copies) * p.n_slots + cur) * L.w2 + (int64_t)t * W;
-          for (int wd = 0; wd * 32 < W; ++wd) {
-            unsigned m = s_colmask[u][wd];
-            while (m) {
-              const int j = wd * 32 + __ffs(m) - 1;
-              m &= m - 1;
-              atomicAdd(nrow + j, 1);
-            }
-          }
         }
         if (cov && t < W) {
           if (!isnan(ca[u])) cs += ca[u];
@@ -510,24 +559,8 @@ __global__ void k_vector(const VecParams p) {
           if (isfinite(ev[u])) tn += 1;
         }
       }
-      if (has_bad) __syncthreads();
     }
     flush();
-  }
-  if (t == 0 && slow_total > 0) atomicAdd(p.n_slow, slow_total);
-}
-
-// acc.num += sum over the privatised copies of the bad-row x bad-col counts
-__global__ void k_xb_reduce(const int* __restrict__ xb, int copies, int n_slots, int W, double* __restrict__ acc) {
-  const AccLayout L(W);
-  const int64_t total = (int64_t)n_slots * L.w2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int sum = 0;
-    for (int c = 0; c < copies; ++c) sum += xb[(int64_t)c * total + i];
-    if (sum != 0) {
-      const int64_t s = i / L.w2, cell = i - s * L.w2;
-      atomicAdd(acc + s * L.stride + L.off_num + cell, (double)sum);
-    }
   }
 }
 
@@ -956,7 +989,9 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
   }
   if (weight) {
     RCK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
-    r->bytes += nb;
+    RCK(cudaMallocAsync((void**)&r->badpre, (size_t)(nb + 1) * 4, st));
+    RCK(cudaMallocAsync((void**)&r->badlist, (size_t)nb * 4, st));
+    r->bytes += (int64_t)nb * 9 + 4;
   }
   RCK(cudaMemcpyAsync(r->indptr, indptr, (size_t)(nb + 1) * 4, cudaMemcpyDefault, st));
   {
@@ -998,9 +1033,10 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
       RCK(cudaGetLastError());
     }
     {
-      int32_t* ebad32;
+      int32_t *ebad32, *bad32 = nullptr;
       RCK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
-      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, r->expected, r->bad, r->ebad, ebad32, nb);
+      if (weight) RCK(tmp.alloc((void**)&bad32, (size_t)(nb + 1) * 4));
+      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, r->expected, r->bad, r->ebad, ebad32, bad32, nb);
       ++g_launches;
       RCK(cudaGetLastError());
       size_t tb = 0;
@@ -1009,6 +1045,12 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
       RCK(tmp.alloc(&t, tb));
       RCK(cub::DeviceScan::ExclusiveSum(t, tb, ebad32, r->ebadpre, nb + 1, st));
       ++g_launches;
+      if (weight) {
+        RCK(cub::DeviceScan::ExclusiveSum(t, tb, bad32, r->badpre, nb + 1, st));
+        k_badlist<<<(nb + 255) / 256, 256, 0, st>>>(r->bad, r->badpre, r->badlist, nb);
+        g_launches += 2;
+        RCK(cudaGetLastError());
+      }
     }
     // host staging buffers must stay valid until the copies have been consumed
     if (!is_device_ptr(indptr) || (nnz > 0 && (!is_device_ptr(col) || !is_device_ptr(count))) ||
@@ -1025,7 +1067,8 @@ int pup_region_destroy(pup_region_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
-  void* ptrs[] = {r->pix, r->indptr, r->rowend, r->bucket, r->expected, r->coverage, r->bad, r->ebad, r->ebadpre};
+  void* ptrs[] = {r->pix,      r->indptr, r->rowend, r->bucket,  r->expected, r->coverage,
+                  r->bad,      r->ebad,   r->ebadpre, r->badpre, r->badlist};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
   delete r;
@@ -1132,27 +1175,28 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   WinCtx ctx{m->nb, W, pb, m->ignore_diags, all_flags, m->ebadpre};
   ChunkTable chunks{slot_start, chunk_start, n_slots, ch};
 
-  // 2. per-window vector quantities
+  // 2. per-window counts (n, n_fast, masked rows / columns) and, on request, the O(W) fp64 vectors
   {
     SpanGuard span(1, st);
-    int* xb = nullptr;
-    int xb_copies = 1;
-    const int64_t xb_one = (int64_t)n_slots * W * W;
-    if (m->bad) {
-      xb_copies = (int)std::max<int64_t>(1, std::min<int64_t>(64, (64ll << 20) / (xb_one * 4)));
-      CK(tmp.alloc((void**)&xb, (size_t)(xb_one * xb_copies) * 4));
-      CK(cudaMemsetAsync(xb, 0, (size_t)(xb_one * xb_copies) * 4, st));
-    }
-    VecParams vp{ctx, keys, slot_start, n_slots, m->bad, m->expected, m->coverage, d_acc, counters + 2, xb, xb_copies};
-    const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
-    const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
-    int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
-    k_vector<<<grid, vthreads, 0, st>>>(vp);
-    LAUNCH_CHECK("k_vector");
-    if (m->bad) {
-      int rgrid = (int)std::min<int64_t>((xb_one + 255) / 256, (int64_t)n_sm * 8);
-      k_xb_reduce<<<rgrid, 256, 0, st>>>(xb, xb_copies, n_slots, W, d_acc);
-      LAUNCH_CHECK("k_xb_reduce");
+    const int64_t cstride = (int64_t)W * W + 2 * W + 2;
+    const int64_t one = (int64_t)n_slots * cstride;
+    const int copies = (int)std::max<int64_t>(1, std::min<int64_t>(64, (64ll << 20) / (one * 4)));
+    int* counts;
+    CK(tmp.alloc((void**)&counts, (size_t)(one * copies) * 4));
+    CK(cudaMemsetAsync(counts, 0, (size_t)(one * copies) * 4, st));
+    CountParams cp{ctx, keys, slot_start, n_slots, m->badpre, m->badlist, counts, copies, counters + 2};
+    k_window_counts<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(cp);
+    LAUNCH_CHECK("k_window_counts");
+    int rgrid = (int)std::min<int64_t>((one + 255) / 256, (int64_t)n_sm * 8);
+    k_counts_reduce<<<rgrid, 256, 0, st>>>(counts, copies, n_slots, W, slot_start, d_acc);
+    LAUNCH_CHECK("k_counts_reduce");
+    if (flags & (PUP_F_EXPCTRL | PUP_F_COVERAGE)) {
+      VecParams vp{ctx, keys, slot_start, n_slots, m->expected, m->coverage, d_acc};
+      const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
+      const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
+      int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
+      k_vector<<<grid, vthreads, 0, st>>>(vp);
+      LAUNCH_CHECK("k_vector");
     }
   }
 
