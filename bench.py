@@ -28,6 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CPU_SAMPLE_REGIONS = ("chr2", "chr9", "chr16", "chr21")
 BINSIZE = 10_000
 FLANK = 410_000
 W = 2 * (FLANK // BINSIZE) + 1
@@ -294,7 +295,9 @@ def main():
         regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None,
                                     ignore_diags=2, flags=0, stream=stream)
         if not args.no_e2e or (rank == 0 and not args.no_cpu):
-            host[c] = {k: t[k].cpu().pin_memory() for k in ("indptr", "col", "count", "weight")}
+            host[c] = {k: t[k].cpu().pin_memory() for k in ("upper_indptr", "upper_col", "upper_count", "weight")}
+            if rank == 0 and not args.no_cpu and c in CPU_SAMPLE_REGIONS:
+                host[c].update({k: t[k].cpu() for k in ("indptr", "col", "count")})
         w = windows[c]
         dwin[c] = tuple(torch.from_numpy(w[k]).to(dev) for k in ("r0", "c0", "slot"))
         del t
@@ -369,17 +372,45 @@ def main():
     if not args.no_e2e:
         hacc = torch.zeros(n_slots * stride, dtype=torch.float64).pin_memory()
         hwin = {c: tuple(torch.from_numpy(windows[c][k]).pin_memory() for k in ("r0", "c0", "slot")) for c in mine}
-        h2d = sum(sum(t.numel() * t.element_size() for t in host[c].values()) for c in mine)
+        h2d = sum(sum(host[c][k].numel() * host[c][k].element_size()
+                      for k in ("upper_indptr", "upper_col", "upper_count", "weight")) for c in mine)
         h2d += sum(sum(t.numel() * t.element_size() for t in hwin[c]) for c in mine)
         d2h = acc.numel() * 8
 
+        s_copy, s_comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        ASYNC = _native.PUP_F_ASYNC
+
         def e2e_step():
-            acc.zero_()
-            for c in mine:
+            # double-buffered: upload + index chromosome k+1 on the copy stream while chromosome k piles up
+            main_stream = torch.cuda.current_stream(dev)
+            s_comp.wait_stream(main_stream)
+            s_copy.wait_stream(main_stream)
+            with torch.cuda.stream(s_comp):
+                acc.zero_()
+            pending = []
+
+            def upload(c):
                 h = host[c]
+                with torch.cuda.stream(s_copy):
+                    reg = _native.Region(local_rank, windows[c]["nb"], h["upper_indptr"], h["upper_col"], h["upper_count"],
+                                         h["weight"], None, None, ignore_diags=2, flags=ASYNC, stream=s_copy.cuda_stream,
+                                         upper=True)
+                    ev = s_copy.record_event()
+                return reg, ev
+
+            nxt = upload(mine[0]) if mine else None
+            for k, c in enumerate(mine):
+                reg, ready = nxt
+                nxt = upload(mine[k + 1]) if k + 1 < len(mine) else None
+                s_comp.wait_event(ready)
                 r0, c0, sl = hwin[c]
-                _native.accumulate_region(local_rank, windows[c]["nb"], h["indptr"], h["col"], h["count"], h["weight"], None,
-                                          None, r0, c0, sl, W, 2, n_slots, flags, acc, stream=stream)
+                reg.accumulate(r0, c0, sl, W, n_slots, flags | ASYNC, acc, stream=s_comp.cuda_stream)
+                done = s_comp.record_event()
+                s_copy.wait_event(done)
+                with torch.cuda.stream(s_copy):
+                    reg.close()
+            main_stream.wait_stream(s_comp)
+            main_stream.wait_stream(s_copy)
             if dist is not None:
                 dist.all_reduce(acc)
             hacc.copy_(acc, non_blocking=True)
@@ -401,8 +432,10 @@ def main():
         e2e = {"value": n_valid_total / (float(ems.item()) / 1e3), "unit": "pile-ups/s", "ms_per_step": float(ems.item()),
                "h2d_bytes_per_step": int(bts[0].item()), "d2h_bytes_per_step": int(bts[1].item()),
                "steps": args.e2e_steps,
-               "what": "pup_accumulate_region() per chromosome with pinned host CSR/weight/window buffers "
-                       "(upload + device indexing + pile-up) and D2H of the accumulators"}
+               "what": "pup_region_create_upper + pup_accumulate per chromosome with pinned HOST buffers: the cooler-style "
+                       "upper-triangle pixels (indptr, col, count), weights and window arrays are uploaded, mirrored / "
+                       "normalised / indexed on the device and piled up; the upload of chromosome k+1 overlaps the "
+                       "pile-up of k on a second stream; D2H of the accumulators at the end"}
 
     if rank != 0:
         if dist is not None:
@@ -436,7 +469,7 @@ def main():
     # ---- CPU baseline: restated reference path on a bounded sample, 1 core
     cpu = None
     if not args.no_cpu and world == 1:
-        sample_regions = [c for c in ("chr2", "chr9", "chr16", "chr21") if c in mine] or mine[:2]
+        sample_regions = [c for c in CPU_SAMPLE_REGIONS if c in mine and "col" in host[c]] or mine[:2]
         per = max(1, args.cpu_sample // len(sample_regions))
         rh = {c: dict(nb=windows[c]["nb"], **{k: host[c][k].numpy() for k in ("indptr", "col", "count", "weight")}) for c in sample_regions}
         cpu_setup(rh, windows, per)

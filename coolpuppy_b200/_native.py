@@ -14,12 +14,14 @@ PUP_F_OOE = 1
 PUP_F_EXPCTRL = 2
 PUP_F_COVERAGE = 4
 PUP_F_NODIAG = 8
+PUP_F_ASYNC = 16
 
 _LIB = None
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200.so")
 
 SYMBOLS = [
-    "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_destroy",
+    "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",
+    "pup_region_destroy",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read",
 ]
@@ -45,6 +47,7 @@ def lib():
     L.pup_last_launches.restype = C.c_int
     L.pup_device_count.argtypes = [C.POINTER(C.c_int)]
     L.pup_region_create.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, C.c_int, u32, vp, C.POINTER(vp)]
+    L.pup_region_create_upper.argtypes = L.pup_region_create.argtypes
     L.pup_region_destroy.argtypes = [vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
@@ -118,15 +121,18 @@ class Region:
     """A region matrix resident in HBM (``pup_region_t``)."""
 
     def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, ignore_diags=2,
-                 flags=0, stream=0):
+                 flags=0, stream=0, upper=False):
+        """``upper=True``: ``indptr/col/count`` hold the upper triangle as cooler stores it (columns >= nb are
+        dropped, the lower triangle is mirrored in on the device); else the symmetric-filled CSR."""
         self._h = C.c_void_p()
         self.nb = int(nb)
         self.nnz = int(col.shape[0]) if col is not None else 0
         self.device = device
         self.balanced = weight is not None
-        check(lib().pup_region_create(device, self.nb, self.nnz, ptr(indptr), ptr(col), ptr(count), ptr(weight),
-                                      ptr(expected), ptr(coverage), int(ignore_diags),
-                                      int(flags) & (PUP_F_OOE | PUP_F_NODIAG), stream, C.byref(self._h)))
+        fn = lib().pup_region_create_upper if upper else lib().pup_region_create
+        check(fn(device, self.nb, self.nnz, ptr(indptr), ptr(col), ptr(count), ptr(weight), ptr(expected),
+                 ptr(coverage), int(ignore_diags), int(flags) & (PUP_F_OOE | PUP_F_NODIAG | PUP_F_ASYNC), stream,
+                 C.byref(self._h)))
 
     @property
     def device_bytes(self):
@@ -136,7 +142,7 @@ class Region:
         n = int(r0.shape[0])
         nv = C.c_int64(0)
         check(lib().pup_accumulate(self._h, n, ptr(r0), ptr(c0), ptr(slot), int(W), int(n_slots),
-                                   int(flags) & (PUP_F_EXPCTRL | PUP_F_COVERAGE), ptr(acc), stream,
+                                   int(flags) & (PUP_F_EXPCTRL | PUP_F_COVERAGE | PUP_F_ASYNC), ptr(acc), stream,
                                    C.byref(nv) if want_n_valid else None))
         return nv.value if want_n_valid else None
 

@@ -196,6 +196,23 @@ class _CoolerBase:
         keep = (row >= i0) & (row < i1) & (col >= j0) & (col < j1)
         return row[keep].astype(np.int64), col[keep].astype(np.int64), val[keep]
 
+    def region_upper_csr(self, lo, hi):
+        """Upper-triangle CSR rows of the bin range [lo, hi) exactly as the cooler stores them.
+
+        Returns ``(indptr int32[nb+1], cols int32[n], counts int32[n])`` with region-relative columns; pixels that
+        leave the region (column >= nb: trans contacts, or cis beyond a view arm) are kept and have to be dropped
+        by the consumer (``pup_region_create_upper`` does).  No sorting or filtering happens on the host.
+        """
+        p0, p1 = int(self._bin1_offset[lo]), int(self._bin1_offset[hi])
+        if p1 - p0 >= 2**30:
+            raise ValueError("region has more than 2^30 stored upper-triangle pixels")
+        indptr = (self._bin1_offset[lo : hi + 1] - p0).astype(np.int32)
+        cols = np.minimum(self._bin2[p0:p1] - lo, 2**31 - 1).astype(np.int32)
+        cnt = self._count[p0:p1]
+        if not np.issubdtype(cnt.dtype, np.integer):
+            raise NotImplementedError("floating-point pixel counts are not supported by the CUDA path")
+        return indptr, cols, np.ascontiguousarray(cnt, dtype=np.int32)
+
     def region_csr(self, lo, hi):
         """Symmetric-filled raw-count CSR of the square bin range [lo, hi).
 

@@ -434,8 +434,10 @@ class PileUpper:
         r = self.view_df.loc[region_name]
         lo, hi = self.clr.extent((r["chrom"], r["start"], r["end"]))
         nb = hi - lo
-        if hasattr(self.clr, "region_csr"):
-            indptr, col, cnt = self.clr.region_csr(lo, hi)
+        upper = False
+        if hasattr(self.clr, "region_upper_csr"):
+            indptr, col, cnt = self.clr.region_upper_csr(lo, hi)  # mirrored into a symmetric CSR on the device
+            upper = True
         else:  # a real cooler.Cooler
             m = self.clr.matrix(sparse=True, balance=False).fetch((r["chrom"], r["start"], r["end"])).tocsr()
             m.sort_indices()
@@ -450,7 +452,7 @@ class PileUpper:
             e = self._expected_values[region_name]
             exp = np.full(nb, np.nan)
             exp[: min(nb, len(e))] = e[:nb]
-        return nb, indptr, col, cnt, weight, exp, cov
+        return nb, indptr, col, cnt, weight, exp, cov, upper
 
     # -- the hot path -----------------------------------------------------------------------------
     def _plan(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func):
@@ -607,9 +609,9 @@ class PileUpper:
         stream = _native.current_stream(self._device)
         self._last_stats = {"windows": 0, "launches": 0, "regions": 0}
         for b in job["built"]:
-            nb, indptr, col, cnt, weight, exp, cov = self._region_arrays(b["name"])
+            nb, indptr, col, cnt, weight, exp, cov, upper = self._region_arrays(b["name"])
             region = _native.Region(self._device, nb, indptr, col, cnt, weight, exp, cov,
-                                    ignore_diags=self.ignore_diags, flags=flags, stream=stream)
+                                    ignore_diags=self.ignore_diags, flags=flags, stream=stream, upper=upper)
             self._last_stats["launches"] += int(_native.lib().pup_last_launches())
             try:
                 nv = region.accumulate(

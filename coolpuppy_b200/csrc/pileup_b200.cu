@@ -102,6 +102,20 @@ void retain_pool_memory(int dev) {
   done[dev] = true;
 }
 
+// Host->device uploads run on an internal per-device copy stream so that they overlap whatever the caller's
+// stream is still busy with (e.g. indexing the previous region); the caller's stream then waits on an event.
+cudaStream_t copy_stream(int dev) {
+  static cudaStream_t streams[64] = {};
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev]) {
+    if (cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      streams[dev] = nullptr;
+    }
+  }
+  return streams[dev];
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -245,6 +259,84 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
       pix[i] = p;
     }
   }
+}
+
+// ---- symmetric fill on the device (cooler stores the upper triangle only; coolpup.py:1053-1057 relies on
+// cooler's fetch to mirror it).  Input: upper CSR rows of the region, columns sorted, columns >= nb (pixels that
+// leave the region, i.e. trans or beyond a view arm) are dropped.
+__global__ void k_upper_counts(const int32_t* __restrict__ indptr_u, const int32_t* __restrict__ col_u, int nb,
+                               int32_t* __restrict__ up_cnt, int32_t* __restrict__ lo_cnt,
+                               int32_t* __restrict__ sort_key, int32_t* __restrict__ sort_val) {
+  // one warp per row; sort_key/sort_val get the strictly-upper in-region entries' (col, entry index); entries that
+  // are not mirrored get key nb (sorted last)
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nb; r += nwarps) {
+    const int lo = indptr_u[r], hi = indptr_u[r + 1];
+    int cnt = 0;
+    for (int i = lo + lane; i < hi; i += 32) {
+      const int c = col_u[i];
+      const bool in = c >= 0 && c < nb;
+      cnt += in;
+      const bool mirror = in && c != (int)r;
+      sort_key[i] = mirror ? c : nb;
+      sort_val[i] = i;
+      if (mirror) atomicAdd(&lo_cnt[c], 1);
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0) up_cnt[r] = cnt;
+  }
+}
+
+__global__ void k_add_counts(const int32_t* a, const int32_t* b, int32_t* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+  if (i == n) out[i] = 0;
+}
+
+// row id of every upper entry (needed as the mirrored entry's column)
+__global__ void k_expand_rows(const int32_t* __restrict__ indptr_u, int32_t* __restrict__ row_of, int nb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nb; r += nwarps)
+    for (int i = indptr_u[r] + lane; i < indptr_u[r + 1]; i += 32) row_of[i] = (int)r;
+}
+
+// upper part of every symmetric row: after the mirrored entries, same order as the input
+__global__ void k_place_upper(const int32_t* __restrict__ indptr_u, const int32_t* __restrict__ col_u,
+                              const int32_t* __restrict__ cnt_u, const int32_t* __restrict__ sym_indptr,
+                              const int32_t* __restrict__ lo_cnt, int nb, int32_t* __restrict__ col_s,
+                              int32_t* __restrict__ cnt_s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nb; r += nwarps) {
+    const int lo = indptr_u[r], hi = indptr_u[r + 1];
+    const int dst = sym_indptr[r] + lo_cnt[r];
+    for (int i = lo + lane; i < hi; i += 32) {
+      const int c = col_u[i];
+      if (c >= 0 && c < nb) {  // in-region columns form a prefix of the sorted row
+        col_s[dst + (i - lo)] = c;
+        cnt_s[dst + (i - lo)] = cnt_u[i];
+      }
+    }
+  }
+}
+
+// mirrored part: entries stably sorted by column arrive grouped by target row, source rows ascending
+__global__ void k_place_lower(const int32_t* __restrict__ sorted_key, const int32_t* __restrict__ sorted_val,
+                              const int32_t* __restrict__ row_of, const int32_t* __restrict__ cnt_u,
+                              const int32_t* __restrict__ sym_indptr, const int32_t* __restrict__ lo_start,
+                              int nb, int32_t* __restrict__ col_s, int32_t* __restrict__ cnt_s) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= lo_start[nb]) return;  // lo_start[nb] = number of mirrored entries (they sort first)
+  const int c = sorted_key[j];
+  const int src = sorted_val[j];
+  const int dst = sym_indptr[c] + (int)(j - lo_start[c]);
+  col_s[dst] = row_of[src];
+  cnt_s[dst] = cnt_u[src];
 }
 
 // bucket[b * nb + r] = first entry index of row r whose column is >= (b << lb)
@@ -914,151 +1006,299 @@ int64_t pup_acc_stride(int W) {
 
 int64_t pup_region_device_bytes(const pup_region_t* r) { return r ? r->bytes : 0; }
 
+}  // extern "C"
+
+namespace {
+
+int choose_bucket_bits(int32_t nb, int64_t nnz, int* nbk_out) {
+  // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
+  double avg = (double)nnz / nb;
+  int target = env_int("PUP_BUCKET_TARGET", 4);
+  if (avg <= 24.0) {
+    *nbk_out = 1;
+    return 31;
+  }
+  int lb = (int)floor(log2((double)target * nb / avg));
+  if (lb < 3) lb = 3;
+  while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20) ||  // <= 25% of pixels
+         ((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb >= (1ll << 31))                           // 32-bit index
+    ++lb;
+  *nbk_out = (nb + (1 << lb) - 1) >> lb;
+  return lb;
+}
+
+// Everything after the symmetric CSR (indptr in r->indptr, DEVICE col/count) is known: normalise pixels, build the
+// bucket table and the masks.  `weight` may be host or device.
+int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const double* weight, Scratch& tmp) {
+  // `weight` is DEVICE memory here (staged by the caller)
+  cudaStream_t st = r->stream;
+  const int32_t nb = r->nb;
+  const int64_t nnz = r->nnz;
+  r->lb = choose_bucket_bits(nb, nnz, &r->nbk);
+  size_t n_ent = (size_t)(nnz > 0 ? nnz : 1);
+  CK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
+  CK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
+  CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
+  CK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
+  CK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
+  r->bytes += (int64_t)(n_ent * sizeof(Pix) + (size_t)(nb + 1) * 12 + (size_t)r->nbk * nb * 4 + (size_t)nb);
+  const double* dw = weight;
+  if (weight) {
+    CK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
+    CK(cudaMallocAsync((void**)&r->badpre, (size_t)(nb + 1) * 4, st));
+    CK(cudaMallocAsync((void**)&r->badlist, (size_t)nb * 4, st));
+    r->bytes += (int64_t)nb * 9 + 4;
+  }
+  {
+    int grid = std::min((nb + 7) / 8, 148 * 16);
+    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
+                                           r->ignore_diags, r->flags);
+    LAUNCH_CHECK("k_prepare_pixels");
+  }
+  {
+    int64_t total = (int64_t)nb * r->nbk;
+    int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
+    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->bucket, nb, r->nbk, r->lb);
+    LAUNCH_CHECK("k_build_buckets");
+  }
+  {
+    int32_t *ebad32, *bad32 = nullptr;
+    CK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
+    if (weight) CK(tmp.alloc((void**)&bad32, (size_t)(nb + 1) * 4));
+    k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, r->expected, r->bad, r->ebad, ebad32, bad32, nb);
+    LAUNCH_CHECK("k_masks");
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ebad32, r->ebadpre, nb + 1, st));
+    void* t;
+    CK(tmp.alloc(&t, tb));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, ebad32, r->ebadpre, nb + 1, st));
+    ++g_launches;
+    if (weight) {
+      CK(cub::DeviceScan::ExclusiveSum(t, tb, bad32, r->badpre, nb + 1, st));
+      k_badlist<<<(nb + 255) / 256, 256, 0, st>>>(r->bad, r->badpre, r->badlist, nb);
+      ++g_launches;
+      LAUNCH_CHECK("k_badlist");
+    }
+  }
+  return PUP_OK;
+}
+
+int new_region(int device, int32_t nb, const double* expected, const double* coverage, int ignore_diags,
+               unsigned flags, cudaStream_t st, pup_region** out) {
+  pup_region* r = new pup_region();
+  memset(r, 0, sizeof *r);
+  r->device = device;
+  r->nb = nb;
+  r->stream = st;
+  r->ignore_diags = ignore_diags;
+  r->flags = flags;
+  *out = r;
+  CK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
+  if (expected) {
+    CK(cudaMallocAsync((void**)&r->expected, (size_t)nb * 8, st));
+    CK(cudaMemcpyAsync(r->expected, expected, (size_t)nb * 8, cudaMemcpyDefault, st));
+    r->bytes += (int64_t)nb * 8;
+  }
+  if (coverage) {
+    CK(cudaMallocAsync((void**)&r->coverage, (size_t)nb * 8, st));
+    CK(cudaMemcpyAsync(r->coverage, coverage, (size_t)nb * 8, cudaMemcpyDefault, st));
+    r->bytes += (int64_t)nb * 8;
+  }
+  return PUP_OK;
+}
+
+int check_region_args(const char* who, int device, int32_t nb, int64_t nnz, const void* indptr, const void* col,
+                      const void* count, const double* expected, unsigned flags) {
+  if (nb <= 0 || nnz < 0 || nnz >= (1ll << 31) || !indptr || (nnz > 0 && (!col || !count)))
+    return fail(PUP_E_ARG, "region create: bad sizes or null CSR arrays");
+  if ((flags & PUP_F_OOE) && !expected) return fail(PUP_E_ARG, "region create: PUP_F_OOE needs an expected vector");
+  if (flags & ~(PUP_F_OOE | PUP_F_NODIAG | PUP_F_ASYNC))
+    return fail(PUP_E_ARG, "region create: only PUP_F_OOE / PUP_F_NODIAG / PUP_F_ASYNC apply");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(PUP_E_NODEV, "region create: no such CUDA device");
+  }
+  (void)who;
+  return PUP_OK;
+}
+
+// Device copies of host input arrays: allocated and filled on the internal copy stream (so the upload does not
+// queue behind the caller's stream), released on the caller's stream after use.
+struct Uploader {
+  cudaStream_t user, copy;
+  std::vector<void*> ptrs;
+  bool used = false;
+  Uploader(cudaStream_t user_, int dev) : user(user_), copy(copy_stream(dev)) {
+    if (!copy) copy = user;
+  }
+  ~Uploader() {
+    for (void* p : ptrs) cudaFreeAsync(p, user);
+  }
+  // *dst = src if src is device memory, else a staged device copy
+  int stage(const void* src, size_t bytes, const void** dst) {
+    *dst = src;
+    if (bytes == 0 || src == nullptr || is_device_ptr(src)) return PUP_OK;
+    void* t;
+    CK(cudaMallocAsync(&t, bytes, copy));
+    ptrs.push_back(t);
+    CK(cudaMemcpyAsync(t, src, bytes, cudaMemcpyHostToDevice, copy));
+    *dst = t;
+    used = true;
+    return PUP_OK;
+  }
+  // make the caller's stream wait for all uploads issued so far
+  int join() {
+    if (!used || copy == user) return PUP_OK;
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, copy);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(user, ev, 0);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "upload join", e);
+    return PUP_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
 int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
                       const int32_t* count, const double* weight, const double* expected, const double* coverage,
                       int ignore_diags, unsigned flags, void* stream, pup_region_t** out) {
   if (!out) return fail(PUP_E_ARG, "pup_region_create: null output");
   *out = nullptr;
-  if (nb <= 0 || nnz < 0 || nnz >= (1ll << 31) || !indptr || (nnz > 0 && (!col || !count)))
-    return fail(PUP_E_ARG, "pup_region_create: bad sizes or null CSR arrays");
-  if ((flags & PUP_F_OOE) && !expected) return fail(PUP_E_ARG, "pup_region_create: PUP_F_OOE needs an expected vector");
-  if (flags & ~(PUP_F_OOE | PUP_F_NODIAG)) return fail(PUP_E_ARG, "pup_region_create: only PUP_F_OOE / PUP_F_NODIAG apply");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
-    cudaGetLastError();
-    return fail(PUP_E_NODEV, "pup_region_create: no such CUDA device");
-  }
+  int rc = check_region_args("pup_region_create", device, nb, nnz, indptr, col, count, expected, flags);
+  if (rc != PUP_OK) return rc;
+  const bool async = flags & PUP_F_ASYNC;
+  flags &= ~PUP_F_ASYNC;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(PUP_E_NODEV, "pup_region_create: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
   g_launches = 0;
-
-  pup_region* r = new pup_region();
-  memset(r, 0, sizeof *r);
-  r->device = device;
-  r->nb = nb;
-  r->nnz = nnz;
-  r->stream = st;
-  r->ignore_diags = ignore_diags;
-  r->flags = flags;
-
-  // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
-  double avg = (double)nnz / nb;
-  int target = env_int("PUP_BUCKET_TARGET", 4);
-  if (avg <= 24.0) {
-    r->lb = 31;
-    r->nbk = 1;
-  } else {
-    int lb = (int)floor(log2((double)target * nb / avg));
-    if (lb < 3) lb = 3;
-    while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20) ||  // <= 25% of pixels
-           ((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb >= (1ll << 31))                           // 32-bit index
-      ++lb;
-    r->lb = lb;
-    r->nbk = (nb + (1 << lb) - 1) >> lb;
-  }
-
-  auto cleanup = [&](int code) {
-    pup_region_destroy(r);
-    return code;
-  };
-#define RCK(call)                                                                                            \
-  do {                                                                                                       \
-    cudaError_t e_ = (call);                                                                                 \
-    if (e_ != cudaSuccess)                                                                                   \
-      return cleanup(fail(e_ == cudaErrorMemoryAllocation ? PUP_E_OOM : PUP_E_CUDA, #call, e_));             \
-  } while (0)
-
-  size_t n_ent = (size_t)(nnz > 0 ? nnz : 1);
-  RCK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
-  RCK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
-  RCK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
-  RCK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
-  RCK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
-  RCK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
-  r->bytes = (int64_t)(n_ent * sizeof(Pix) + (size_t)(nb + 1) * 12 + (size_t)r->nbk * nb * 4 + (size_t)nb);
-  if (expected) {
-    RCK(cudaMallocAsync((void**)&r->expected, (size_t)nb * 8, st));
-    RCK(cudaMemcpyAsync(r->expected, expected, (size_t)nb * 8, cudaMemcpyDefault, st));
-    r->bytes += (int64_t)nb * 8;
-  }
-  if (coverage) {
-    RCK(cudaMallocAsync((void**)&r->coverage, (size_t)nb * 8, st));
-    RCK(cudaMemcpyAsync(r->coverage, coverage, (size_t)nb * 8, cudaMemcpyDefault, st));
-    r->bytes += (int64_t)nb * 8;
-  }
-  if (weight) {
-    RCK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
-    RCK(cudaMallocAsync((void**)&r->badpre, (size_t)(nb + 1) * 4, st));
-    RCK(cudaMallocAsync((void**)&r->badlist, (size_t)nb * 4, st));
-    r->bytes += (int64_t)nb * 9 + 4;
-  }
-  RCK(cudaMemcpyAsync(r->indptr, indptr, (size_t)(nb + 1) * 4, cudaMemcpyDefault, st));
-  {
+  pup_region* r = nullptr;
+  rc = new_region(device, nb, expected, coverage, ignore_diags, flags, st, &r);
+  if (rc == PUP_OK) {
+    r->nnz = nnz;
     Scratch tmp(st);
-    const int32_t* dcol = col;
-    const int32_t* dcnt = count;
-    const double* dw = weight;
-    if (nnz > 0 && !is_device_ptr(col)) {
-      int32_t* t;
-      RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
-      RCK(cudaMemcpyAsync(t, col, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-      dcol = t;
+    Uploader up(st, device);
+    const void *dip = nullptr, *dcol = nullptr, *dcnt = nullptr, *dw = nullptr;
+    rc = up.stage(indptr, (size_t)(nb + 1) * 4, &dip);
+    if (rc == PUP_OK) rc = up.stage(col, (size_t)nnz * 4, &dcol);
+    if (rc == PUP_OK) rc = up.stage(count, (size_t)nnz * 4, &dcnt);
+    if (rc == PUP_OK) rc = up.stage(weight, (size_t)nb * 8, &dw);
+    if (rc == PUP_OK) rc = up.join();
+    if (rc == PUP_OK) {
+      cudaError_t e = cudaMemcpyAsync(r->indptr, dip, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) rc = fail(PUP_E_CUDA, "pup_region_create: indptr copy", e);
     }
-    if (nnz > 0 && !is_device_ptr(count)) {
-      int32_t* t;
-      RCK(tmp.alloc((void**)&t, (size_t)nnz * 4));
-      RCK(cudaMemcpyAsync(t, count, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
-      dcnt = t;
+    if (rc == PUP_OK)
+      rc = finish_region(r, (const int32_t*)dcol, (const int32_t*)dcnt, (const double*)dw, tmp);
+    cudaError_t e = cudaSuccess;
+    const bool host_in = !is_device_ptr(indptr) || (nnz > 0 && (!is_device_ptr(col) || !is_device_ptr(count))) ||
+                         (weight && !is_device_ptr(weight)) || (expected && !is_device_ptr(expected)) ||
+                         (coverage && !is_device_ptr(coverage));
+    if (rc == PUP_OK && host_in && !async) {
+      e = cudaStreamSynchronize(st);  // host staging buffers must stay valid until the copies have been consumed
+      if (e != cudaSuccess) rc = fail(PUP_E_CUDA, "pup_region_create: synchronize", e);
     }
-    if (weight && !is_device_ptr(weight)) {
-      double* t;
-      RCK(tmp.alloc((void**)&t, (size_t)nb * 8));
-      RCK(cudaMemcpyAsync(t, weight, (size_t)nb * 8, cudaMemcpyHostToDevice, st));
-      dw = t;
-    }
-    {
-      int warps = nb;
-      int grid = std::min((warps + 7) / 8, 148 * 16);
-      k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
-                                             ignore_diags, flags);
-      ++g_launches;
-      RCK(cudaGetLastError());
-    }
-    {
-      int64_t total = (int64_t)nb * r->nbk;
-      int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-      k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->bucket, nb, r->nbk, r->lb);
-      ++g_launches;
-      RCK(cudaGetLastError());
-    }
-    {
-      int32_t *ebad32, *bad32 = nullptr;
-      RCK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
-      if (weight) RCK(tmp.alloc((void**)&bad32, (size_t)(nb + 1) * 4));
-      k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, r->expected, r->bad, r->ebad, ebad32, bad32, nb);
-      ++g_launches;
-      RCK(cudaGetLastError());
-      size_t tb = 0;
-      RCK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ebad32, r->ebadpre, nb + 1, st));
-      void* t;
-      RCK(tmp.alloc(&t, tb));
-      RCK(cub::DeviceScan::ExclusiveSum(t, tb, ebad32, r->ebadpre, nb + 1, st));
-      ++g_launches;
-      if (weight) {
-        RCK(cub::DeviceScan::ExclusiveSum(t, tb, bad32, r->badpre, nb + 1, st));
-        k_badlist<<<(nb + 255) / 256, 256, 0, st>>>(r->bad, r->badpre, r->badlist, nb);
-        g_launches += 2;
-        RCK(cudaGetLastError());
-      }
-    }
-    // host staging buffers must stay valid until the copies have been consumed
-    if (!is_device_ptr(indptr) || (nnz > 0 && (!is_device_ptr(col) || !is_device_ptr(count))) ||
-        (weight && !is_device_ptr(weight)) || (expected && !is_device_ptr(expected)) ||
-        (coverage && !is_device_ptr(coverage)))
-      RCK(cudaStreamSynchronize(st));
   }
-#undef RCK
+  if (rc != PUP_OK) {
+    pup_region_destroy(r);
+    return rc;
+  }
+  *out = r;
+  return PUP_OK;
+}
+
+int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper,
+                            const int32_t* col_upper, const int32_t* count_upper, const double* weight,
+                            const double* expected, const double* coverage, int ignore_diags, unsigned flags,
+                            void* stream, pup_region_t** out) {
+  if (!out) return fail(PUP_E_ARG, "pup_region_create_upper: null output");
+  *out = nullptr;
+  int rc = check_region_args("pup_region_create_upper", device, nb, nnz_upper, indptr_upper, col_upper, count_upper,
+                             expected, flags);
+  if (rc != PUP_OK) return rc;
+  if (2 * nnz_upper >= (1ll << 31)) return fail(PUP_E_ARG, "pup_region_create_upper: symmetric matrix exceeds 2^31 pixels");
+  const bool async = flags & PUP_F_ASYNC;
+  flags &= ~PUP_F_ASYNC;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_region_create_upper: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches = 0;
+  pup_region* r = nullptr;
+  rc = new_region(device, nb, expected, coverage, ignore_diags, flags, st, &r);
+  auto body = [&]() -> int {
+    Scratch tmp(st);
+    Uploader up(st, device);
+    const void *v_ip, *v_col, *v_cnt, *v_w;
+    int rc2;
+    if ((rc2 = up.stage(indptr_upper, ((size_t)nb + 1) * 4, &v_ip)) != PUP_OK) return rc2;
+    if ((rc2 = up.stage(col_upper, (size_t)nnz_upper * 4, &v_col)) != PUP_OK) return rc2;
+    if ((rc2 = up.stage(count_upper, (size_t)nnz_upper * 4, &v_cnt)) != PUP_OK) return rc2;
+    if ((rc2 = up.stage(weight, weight ? (size_t)nb * 8 : 0, &v_w)) != PUP_OK) return rc2;
+    if ((rc2 = up.join()) != PUP_OK) return rc2;
+    const int32_t *d_ip = (const int32_t*)v_ip, *d_col = (const int32_t*)v_col, *d_cnt = (const int32_t*)v_cnt;
+    const size_t nu = (size_t)(nnz_upper > 0 ? nnz_upper : 1);
+    int32_t *up_cnt, *lo_cnt, *lo_start, *tot_cnt, *key_a, *key_b, *val_a, *val_b, *row_of;
+    CK(tmp.alloc((void**)&up_cnt, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&lo_cnt, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&lo_start, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&tot_cnt, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&key_a, nu * 4));
+    CK(tmp.alloc((void**)&key_b, nu * 4));
+    CK(tmp.alloc((void**)&val_a, nu * 4));
+    CK(tmp.alloc((void**)&val_b, nu * 4));
+    CK(tmp.alloc((void**)&row_of, nu * 4));
+    CK(cudaMemsetAsync(lo_cnt, 0, (size_t)(nb + 1) * 4, st));
+    CK(cudaMemsetAsync(up_cnt, 0, (size_t)(nb + 1) * 4, st));
+    const int wgrid = std::min((nb + 7) / 8, 148 * 16);
+    k_upper_counts<<<wgrid, 256, 0, st>>>(d_ip, d_col, nb, up_cnt, lo_cnt, key_a, val_a);
+    LAUNCH_CHECK("k_upper_counts");
+    k_expand_rows<<<wgrid, 256, 0, st>>>(d_ip, row_of, nb);
+    LAUNCH_CHECK("k_expand_rows");
+    k_add_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(up_cnt, lo_cnt, tot_cnt, nb);
+    LAUNCH_CHECK("k_add_counts");
+    size_t tb = 0, tb2 = 0;
+    cub::DoubleBuffer<int32_t> dk(key_a, key_b), dv(val_a, val_b);
+    const int bits = ilog2_ceil((int64_t)nb + 1);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, tot_cnt, r->indptr, nb + 1, st));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int)nnz_upper, 0, bits, st));
+    void* t;
+    CK(tmp.alloc(&t, std::max(tb, tb2)));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, tot_cnt, r->indptr, nb + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, lo_cnt, lo_start, nb + 1, st));
+    if (nnz_upper > 0) CK(cub::DeviceRadixSort::SortPairs(t, tb2, dk, dv, (int)nnz_upper, 0, bits, st));
+    g_launches += 2 + (bits + 7) / 8;
+    // the symmetric matrix has at most 2 * nnz_upper pixels: allocate for that bound instead of reading the exact
+    // size back (no host synchronisation, so uploads can overlap the previous region's pile-up)
+    r->nnz = 2 * nnz_upper;
+    int32_t *col_s, *cnt_s;
+    CK(tmp.alloc((void**)&col_s, (size_t)std::max<int64_t>(r->nnz, 1) * 4));
+    CK(tmp.alloc((void**)&cnt_s, (size_t)std::max<int64_t>(r->nnz, 1) * 4));
+    k_place_upper<<<wgrid, 256, 0, st>>>(d_ip, d_col, d_cnt, r->indptr, lo_cnt, nb, col_s, cnt_s);
+    LAUNCH_CHECK("k_place_upper");
+    if (nnz_upper > 0) {
+      k_place_lower<<<(unsigned)((nnz_upper + 255) / 256), 256, 0, st>>>(dk.Current(), dv.Current(), row_of, d_cnt,
+                                                                          r->indptr, lo_start, nb, col_s, cnt_s);
+      LAUNCH_CHECK("k_place_lower");
+    }
+    return finish_region(r, col_s, cnt_s, (const double*)v_w, tmp);
+  };
+  if (rc == PUP_OK) rc = body();
+  const bool host_in = !is_device_ptr(indptr_upper) || (nnz_upper > 0 && (!is_device_ptr(col_upper) || !is_device_ptr(count_upper))) ||
+                       (weight && !is_device_ptr(weight)) || (expected && !is_device_ptr(expected)) ||
+                       (coverage && !is_device_ptr(coverage));
+  if (rc == PUP_OK && host_in && !async) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(PUP_E_CUDA, "pup_region_create_upper: synchronize", e);
+  }
+  if (rc != PUP_OK) {
+    pup_region_destroy(r);
+    return rc;
+  }
   *out = r;
   return PUP_OK;
 }
@@ -1082,8 +1322,11 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     return fail(PUP_E_ARG, "pup_accumulate: bad sizes or null accumulator");
   if (2 * W - 1 > VT) return fail(PUP_E_ARG, "pup_accumulate: W too large (max 256 bins)");
   if (n_win > 0 && (!r0 || !c0 || !slot)) return fail(PUP_E_ARG, "pup_accumulate: null window arrays");
-  if (flags & ~(PUP_F_EXPCTRL | PUP_F_COVERAGE))
-    return fail(PUP_E_ARG, "pup_accumulate: only PUP_F_EXPCTRL / PUP_F_COVERAGE apply (the others belong to the region)");
+  if (flags & ~(PUP_F_EXPCTRL | PUP_F_COVERAGE | PUP_F_ASYNC))
+    return fail(PUP_E_ARG, "pup_accumulate: only PUP_F_EXPCTRL / PUP_F_COVERAGE / PUP_F_ASYNC apply (the others belong to the region)");
+  const bool async = flags & PUP_F_ASYNC;
+  flags &= ~PUP_F_ASYNC;
+  if (async && n_valid_out) return fail(PUP_E_ARG, "pup_accumulate: PUP_F_ASYNC cannot return n_valid");
   if ((flags & PUP_F_EXPCTRL) && !m->expected)
     return fail(PUP_E_ARG, "pup_accumulate: expected requested but the region has none");
   if ((flags & PUP_F_EXPCTRL) && (m->flags & PUP_F_OOE))
@@ -1122,6 +1365,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
 
   double* d_acc = acc;
   const bool host_acc = !is_device_ptr(acc);
+  if (host_acc && async) return fail(PUP_E_ARG, "pup_accumulate: PUP_F_ASYNC needs a device accumulator");
   if (host_acc) {
     CK(tmp.alloc((void**)&d_acc, (size_t)acc_len * 8));
     CK(cudaMemsetAsync(d_acc, 0, (size_t)acc_len * 8, st));
@@ -1251,7 +1495,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(cudaMemcpyAsync(&nv, slot_start + n_slots, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *n_valid_out = nv;
-  } else if (host_inputs && !host_acc) {
+  } else if (host_inputs && !host_acc && !async) {
     CK(cudaStreamSynchronize(st));
   }
   return PUP_OK;
@@ -1263,6 +1507,7 @@ int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* in
                           const int32_t* slot, int W, int ignore_diags, int n_slots, unsigned flags, double* acc,
                           void* stream, int64_t* n_valid_out) {
   pup_region_t* r = nullptr;
+  if (flags & PUP_F_ASYNC) return fail(PUP_E_ARG, "pup_accumulate_region: PUP_F_ASYNC needs the two-call form");
   int rc = pup_region_create(device, nb, nnz, indptr, col, count, weight, expected, coverage, ignore_diags,
                              flags & (PUP_F_OOE | PUP_F_NODIAG), stream, &r);
   if (rc != PUP_OK) return rc;

@@ -64,6 +64,10 @@ def synthetic_region(nb, depth=500.0, seed=0, device="cuda", nan_frac=0.03, rows
     raw_sum = torch.zeros(nb, dtype=torch.float64, device=dev).scatter_add_(0, d, c.to(torch.float64))
     expected_raw = raw_sum / torch.arange(nb, 0, -1, device=dev, dtype=torch.float64)
     expected_raw[:2] = float("nan")
+    # the upper triangle as a cooler stores it (row-major, columns sorted): input of pup_region_create_upper
+    up_indptr = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
+    up_indptr[1:] = torch.cumsum(torch.bincount(i, minlength=nb), 0)
+    upper = {"upper_indptr": up_indptr.to(torch.int32), "upper_col": j.to(torch.int32), "upper_count": c.clone()}
     # symmetric fill + sort into CSR
     off = i != j
     row = torch.cat([i, j[off]])
@@ -83,7 +87,7 @@ def synthetic_region(nb, depth=500.0, seed=0, device="cuda", nan_frac=0.03, rows
     if int(indptr[-1]) >= 2**31:
         raise ValueError("region has more than 2^31 stored pixels")
     return {"nb": nb, "indptr": indptr.to(torch.int32), "col": col.contiguous(), "count": cnt.contiguous(),
-            "weight": w, "expected": expected, "expected_raw": expected_raw}
+            "weight": w, "expected": expected, "expected_raw": expected_raw, **upper}
 
 
 def chrom_bins(chromsizes=None, binsize=10_000):

@@ -54,6 +54,9 @@ extern "C" {
 #define PUP_F_EXPCTRL 2u  /* also accumulate the bare expected block per window (coolpup.py:1135-1139, 1190-1191) */
 #define PUP_F_COVERAGE 4u /* accumulate cov_start / cov_end                      (coolpup.py:1151-1153) */
 #define PUP_F_NODIAG 8u   /* do NOT apply the signed diagonal mask (trans; unused by the cis path) */
+#define PUP_F_ASYNC 16u   /* pup_region_create / pup_accumulate with HOST input buffers: do not synchronise the
+                             stream before returning; the caller keeps the (pinned) buffers alive and unchanged until
+                             the stream has passed this call.  Lets uploads of region k+1 overlap the pile-up of k. */
 
 typedef struct pup_region pup_region_t; /* opaque: a region matrix prepared in HBM */
 
@@ -83,6 +86,17 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
                       const int32_t* count, const double* weight, const double* expected,
                       const double* coverage, int ignore_diags, unsigned flags, void* stream,
                       pup_region_t** out);
+/*
+ * Same, from the UPPER triangle as cooler stores it (replaces the symmetric fill that cooler's
+ * matrix(...).fetch() performs on the CPU, coolpup.py:1053-1057): row r of the region holds its stored pixels with
+ * region-relative columns >= r, sorted; columns >= nb (pixels that leave the region: trans, or beyond a view arm)
+ * are dropped.  The lower triangle is mirrored in on the device (stable radix sort by column), which halves the
+ * host->device traffic; device arrays are sized for the 2 * nnz_upper bound so no size is read back.
+ */
+int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper,
+                            const int32_t* col_upper, const int32_t* count_upper, const double* weight,
+                            const double* expected, const double* coverage, int ignore_diags, unsigned flags,
+                            void* stream, pup_region_t** out);
 int pup_region_destroy(pup_region_t* region);
 /* bytes of HBM held by the region, and the algorithmic bytes of its pixels (8 per stored pixel) */
 int64_t pup_region_device_bytes(const pup_region_t* region);

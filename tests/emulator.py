@@ -27,9 +27,25 @@ def layout(W):
     return L
 
 
+def symmetrise(nb, indptr_u, col_u, cnt_u):
+    row = np.repeat(np.arange(nb), np.diff(indptr_u))
+    keep = (col_u >= 0) & (col_u < nb)
+    row, col, cnt = row[keep], col_u[keep].astype(np.int64), cnt_u[keep]
+    off = row != col
+    r = np.concatenate([row, col[off]])
+    c = np.concatenate([col, row[off]])
+    v = np.concatenate([cnt, cnt[off]])
+    order = np.lexsort((c, r))
+    ip = np.zeros(nb + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r, minlength=nb), out=ip[1:])
+    return ip.astype(np.int32), c[order].astype(np.int32), v[order].astype(np.int32)
+
+
 class EmuRegion:
     def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, ignore_diags=2,
-                 flags=0, stream=0):
+                 flags=0, stream=0, upper=False):
+        if upper:  # mirror the stored upper triangle like pup_region_create_upper
+            indptr, col, count = symmetrise(int(nb), np.asarray(indptr), np.asarray(col), np.asarray(count))
         self.nb = int(nb)
         self.ignore_diags = int(ignore_diags)
         self.region_flags = int(flags) & (F_OOE | F_NODIAG)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_acc_stride_and_flags():
     for W in (5, 21, 83, 203):
         assert _native.acc_stride(W) == 2 * W * W + 8 * W + 8
-    assert (_native.PUP_F_OOE, _native.PUP_F_EXPCTRL, _native.PUP_F_COVERAGE, _native.PUP_F_NODIAG) == (1, 2, 4, 8)
+    assert (_native.PUP_F_OOE, _native.PUP_F_EXPCTRL, _native.PUP_F_COVERAGE, _native.PUP_F_NODIAG, _native.PUP_F_ASYNC) == (1, 2, 4, 8, 16)
 
 
 def test_no_cpu_fallback_without_gpu():

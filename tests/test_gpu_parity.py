@@ -126,6 +126,53 @@ def test_kernel_vs_oracle_random(mode, nb, W, dens, nwin, n_slots, memory):
         np.testing.assert_allclose(out["cov_end"], ref["cov_end"], rtol=RTOL)
 
 
+@pytest.mark.parametrize("nb,W,dens", [(300, 21, 30), (900, 83, 300), (64, 5, 2), (2000, 11, 1)])
+def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens):
+    """pup_region_create_upper (cooler's stored upper triangle, incl. pixels that leave the region) gives the same
+    accumulators as the symmetric-CSR entry point and as the oracle."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    n_slots = 3
+    ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb, nan_frac=0.05, with_expected=True)
+    r0, c0, sl = random_windows(nb, W, 600, n_slots, seed=nb + 1)
+    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+    # build the upper triangle the way a cooler holds it: rows of a LARGER matrix, so some columns are >= nb
+    rows = np.repeat(np.arange(nb), np.diff(ip))
+    up = col >= rows
+    rng = np.random.default_rng(nb)
+    extra_rows = rng.integers(0, nb, nb // 2)
+    extra_cols = rng.integers(nb, nb + 500, nb // 2)
+    ur = np.concatenate([rows[up], extra_rows])
+    uc = np.concatenate([col[up], extra_cols])
+    uv = np.concatenate([cnt[up], np.full(nb // 2, 7, dtype=np.int32)])
+    o = np.lexsort((uc, ur))
+    ur, uc, uv = ur[o], uc[o].astype(np.int32), uv[o].astype(np.int32)
+    uip = np.zeros(nb + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ur, minlength=nb), out=uip[1:])
+    uip = uip.astype(np.int32)
+    stride = nat.acc_stride(W)
+    for memory in ("host", "device"):
+        if memory == "host":
+            reg = nat.Region(0, nb, uip, uc, uv, w, e, None, ignore_diags=2, flags=nat.PUP_F_OOE, upper=True)
+            acc = np.zeros(n_slots * stride)
+            nv = reg.accumulate(r0, c0, sl, W, n_slots, 0, acc, want_n_valid=True)
+        else:
+            import torch
+
+            dev = torch.device("cuda", 0)
+            t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            tens = [t(x) for x in (uip, uc, uv, w, e, r0, c0, sl)]
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], None, ignore_diags=2,
+                             flags=nat.PUP_F_OOE, stream=stream, upper=True)
+            acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
+            nv = reg.accumulate(tens[5], tens[6], tens[7], W, n_slots, 0, acc, stream=stream, want_n_valid=True)
+        out = nat.acc_export(acc, W, n_slots)
+        reg.close()
+        _check_against_oracle(nv, out, ref)
+
+
 @pytest.mark.parametrize("ignore_diags", [0, 2, 5, -1000000])
 def test_ignore_diags_variants(ignore_diags):
     nat = _cuda()
