@@ -23,7 +23,7 @@ SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",
     "pup_region_destroy",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
-    "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read",
+    "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
 ]
 
 
@@ -58,6 +58,7 @@ def lib():
                                         C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pup_algorithmic_bytes.argtypes = [vp, i64, vp, vp, C.c_int, u32, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.pup_stripes.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp]
     L.pup_timing_enable.argtypes = [C.c_int]
     L.pup_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     _LIB = L
@@ -145,6 +146,14 @@ class Region:
                                    int(flags) & (PUP_F_EXPCTRL | PUP_F_COVERAGE | PUP_F_ASYNC), ptr(acc), stream,
                                    C.byref(nv) if want_n_valid else None))
         return nv.value if want_n_valid else None
+
+    def stripes(self, r0, c0, W, stream=0):
+        """(horizontal, vertical) centre stripes of every window as host arrays [n, W]."""
+        n = int(r0.shape[0])
+        hor = np.empty((n, int(W)), dtype=np.float64)
+        ver = np.empty((n, int(W)), dtype=np.float64)
+        check(lib().pup_stripes(self._h, n, ptr(r0), ptr(c0), int(W), ptr(hor), ptr(ver), stream))
+        return hor, ver
 
     def algorithmic_bytes(self, r0, c0, W, flags=0, stream=0):
         b, z = C.c_int64(0), C.c_int64(0)

@@ -15,8 +15,8 @@ the result unchanged.  What differs is how the work is done:
   and the per-GPU accumulators are merged with a single all-reduce.
 
 There is no CPU fallback.  Not supported (raises ``NotImplementedError``):
-``trans``, ``rescale``, ``store_stripes``, arbitrary ``postprocess_func`` /
-``extra_sum_funcs`` callbacks ("out of scope").
+``trans``, ``rescale``, arbitrary ``postprocess_func`` / ``extra_sum_funcs``
+callbacks ("out of scope").
 """
 from __future__ import annotations
 
@@ -362,8 +362,6 @@ class PileUpper:
         self._device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
         if rescale:
             raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
-        if store_stripes:
-            raise NotImplementedError("store_stripes is not supported by the B200 path yet")
         if self.CC.flank % self.resolution != 0:
             raise ValueError("flank must be a multiple of the cooler's bin size")  # reference fails on shape mismatch
 
@@ -618,6 +616,12 @@ class PileUpper:
                     np.ascontiguousarray(b["w_r0"], dtype=np.int32), np.ascontiguousarray(b["w_c0"], dtype=np.int32),
                     np.ascontiguousarray(b["slot"], dtype=np.int32), W, n_slots, flags, acc,
                     stream=stream, want_n_valid=True)
+                if self.store_stripes:
+                    # per-ROI centre row / column (coolpup.py:1164-1182); a by-window pair is computed once
+                    sel = np.nonzero(b["valid"] & (b["rw"].kind == 0))[0]
+                    hor, ver = region.stripes(np.ascontiguousarray(b["r0"][sel], dtype=np.int32),
+                                              np.ascontiguousarray(b["c0"][sel], dtype=np.int32), W, stream=stream)
+                    b["stripes"] = (sel, hor, ver)
             finally:
                 region.close()
             self._last_stats["windows"] += int(nv)
@@ -631,8 +635,53 @@ class PileUpper:
         out = _native.acc_export(acc, W, n_slots, device=self._device, stream=stream, want_expected=job["expctrl"],
                                  want_cov=bool(self.coverage_norm))
         plan = job["plan"]
-        return self._slots_to_pups(out, job["groups"], job["nk"], job["nf"], W, job["expctrl"], job["do_control"],
-                                   grouped=bool(plan["groupby"]) or plan["by_window"], all_pos=job["all_pos"])
+        roi, ctrl = self._slots_to_pups(out, job["groups"], job["nk"], job["nf"], W, job["expctrl"], job["do_control"],
+                                        grouped=bool(plan["groupby"]) or plan["by_window"], all_pos=job["all_pos"])
+        if self.store_stripes:
+            if dist is not None and dist.world_size > 1:
+                raise NotImplementedError("store_stripes is a per-ROI output and is not gathered across ranks")
+            self._attach_stripes(job, roi)
+        return roi, ctrl
+
+    def _attach_stripes(self, job, roi):
+        """Per-group lists of stripes / coordinates in the reference's order: regions in view order; within a region
+        the groups in order of first appearance, each in stream order; "all" concatenates the region's groups
+        (sum_pups list concatenation, lib/puputils.py:105-107; coolpup.py:1272-1275)."""
+        grouped = bool(job["plan"]["groupby"]) or job["plan"]["by_window"]
+        groups = job["groups"]
+        lists = {k: {"horizontal_stripe": [], "vertical_stripe": [], "coordinates": []} for k in roi}
+        for b in job["built"]:
+            if "stripes" not in b:
+                continue
+            sel, hor, ver = b["stripes"]
+            rw = b["rw"]
+            s_ = rw.sel
+            if rw.paired:
+                cols = [s_["chrom"].to_numpy()[rw.idx1[sel]], s_["start"].to_numpy()[rw.idx1[sel]], s_["end"].to_numpy()[rw.idx1[sel]],
+                        s_["chrom"].to_numpy()[rw.idx2[sel]], s_["start"].to_numpy()[rw.idx2[sel]], s_["end"].to_numpy()[rw.idx2[sel]]]
+            else:
+                cols = [s_[c].to_numpy()[rw.idx1[sel]] for c in ("chrom1", "start1", "end1", "chrom2", "start2", "end2")]
+            coords = [".".join(str(x.item() if isinstance(x, np.generic) else x) for x in row) for row in zip(*cols)]
+            gid = b["gid"].reshape(len(rw), -1)[sel]  # [n_sel, targets]
+            per_group = {}
+            order = []
+            for j in range(len(sel)):
+                for g in gid[j]:
+                    key = groups[int(g)] if grouped else "all"
+                    if key not in per_group:
+                        per_group[key] = []
+                        order.append(key)
+                    per_group[key].append(j)
+            for key in order:
+                if key not in lists:
+                    continue
+                for j in per_group[key]:
+                    for dst in ([key, "all"] if grouped else [key]):
+                        lists[dst]["horizontal_stripe"].append(hor[j])
+                        lists[dst]["vertical_stripe"].append(ver[j])
+                        lists[dst]["coordinates"].append(coords[j])
+        for k, p in roi.items():
+            p.update(lists[k])
 
     def _region_cost(self, name):
         """Predicted relative cost of a region (for LPT sharding): number of feature pairs."""
@@ -833,9 +882,34 @@ class PileUpper:
                 rows["num"].append(p["num"])
         if not has_ctrl:
             del rows["control_n"], rows["control_num"]
+        if self.store_stripes:  # coolpup.py:1556-1600
+            W = 2 * self.pad_bins + 1
+            cntr = W // 2
+            rows["coordinates"], rows["horizontal_stripe"], rows["vertical_stripe"] = [], [], []
+            with np.errstate(divide="ignore", invalid="ignore"):
+                if has_ctrl:
+                    call = ctrl["all"]
+                    cnorm = call["data"] / call["num"]
+                    ch, cv = cnorm[cntr, :], cnorm[:, cntr][::-1]
+                for k, p in roi.items():
+                    hs = np.vstack(p["horizontal_stripe"]) if p["horizontal_stripe"] else np.zeros((0, W))
+                    vs = np.vstack(p["vertical_stripe"]) if p["vertical_stripe"] else np.zeros((0, W))
+                    if has_ctrl:
+                        hs, vs = hs / ch, vs / cv
+                    if self.local:  # numutils._copy_array_halves
+                        vs[:, : cntr + 1] = np.fliplr(vs[:, cntr:])
+                        hs[:, : cntr + 1] = np.fliplr(hs[:, cntr:])
+                    rows["coordinates"].append(np.vstack([c.split(".") for c in p["coordinates"]])
+                                               if p["coordinates"] else np.zeros((0, 6), dtype=str))
+                    rows["horizontal_stripe"].append(hs)
+                    rows["vertical_stripe"].append(vs)
         n = roi["all"]["n"]
         normalized_roi = pd.DataFrame({k: _objcol(v) if k in ("group", "data", "num", "control_num") else v
-                                       for k, v in rows.items()})
+                                       for k, v in rows.items()
+                                       if k not in ("coordinates", "horizontal_stripe", "vertical_stripe")})
+        if self.store_stripes:
+            for c in ("coordinates", "horizontal_stripe", "vertical_stripe"):
+                normalized_roi[c] = _objcol(rows[c])
         if groupby:
             glist = [("all",) * len(groupby) if (isinstance(i, str) and i == "all") else i
                      for i in normalized_roi["group"].to_list()]

@@ -883,6 +883,56 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
   if (cur_slot >= 0) flush();
 }
 
+// ------------------------------------------------------------------------------------------ stripes
+// Per-window centre row / centre column (store_stripes, coolpup.py:1164-1169): a per-ROI output, not a reduction.
+// One warp per window; every lane looks its pixel up by binary search in the (unnormalised-NaN-aware) row.
+struct StripeParams {
+  const Pix* pix;
+  const int32_t* indptr;
+  const uint8_t* bad;       // null for raw
+  const double* expected;   // null unless the region was prepared with PUP_F_OOE
+  int nb, W, ignore_diags;
+  unsigned flags;
+};
+
+__device__ __forceinline__ double snippet_pixel(const StripeParams& p, int r, int c) {
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  if (p.bad != nullptr && (p.bad[r] || p.bad[c])) return nan;
+  const int d = c - r;
+  if (!(p.flags & PUP_F_NODIAG) && d < p.ignore_diags) return nan;
+  int lo = p.indptr[r], hi = p.indptr[r + 1];
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(&p.pix[mid].col) < c)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const bool stored = lo < p.indptr[r + 1] && p.pix[lo].col == c;
+  const double v = stored ? p.pix[lo].val : 0.0;
+  if ((p.flags & PUP_F_OOE) && p.expected != nullptr) {
+    const double e = p.expected[d < 0 ? -d : d];
+    if (isnan(e)) return nan;
+    if (e == 0.0) return (stored && isinf(v)) ? v : nan;  // x/0 = inf, 0/0 = NaN
+  }
+  return v;
+}
+
+__global__ void k_stripes(const StripeParams p, const int32_t* __restrict__ r0, const int32_t* __restrict__ c0,
+                          int64_t n, double* __restrict__ hor, double* __restrict__ ver) {
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n) return;
+  const int W = p.W, cn = W / 2;
+  const int r = r0[w], c = c0[w];
+  const bool ok = r >= 0 && c >= 0 && r + W <= p.nb && c + W <= p.nb;
+  for (int k = lane; k < W; k += 32) {
+    hor[w * W + k] = ok ? snippet_pixel(p, r + cn, c + k) : nan;           // data[cntr, :]
+    ver[w * W + k] = ok ? snippet_pixel(p, r + (W - 1 - k), c + cn) : nan;  // data[:, cntr][::-1]
+  }
+}
+
 // ------------------------------------------------------------------------------------------ byte counter
 // Exact algorithmic pixel count of a window list (measurement helper, not on the timed path).
 __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restrict__ indptr,
@@ -1551,6 +1601,43 @@ int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stre
       }
     }
   }
+  return PUP_OK;
+}
+
+int pup_stripes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0, int W, double* horizontal,
+                double* vertical, void* stream) {
+  if (!m || n_win < 0 || W <= 0 || !horizontal || !vertical) return fail(PUP_E_ARG, "pup_stripes: bad arguments");
+  if (n_win == 0) return PUP_OK;
+  if (!r0 || !c0) return fail(PUP_E_ARG, "pup_stripes: null window arrays");
+  DeviceGuard guard(m->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_stripes: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch tmp(st);
+  const int32_t *d_r0 = r0, *d_c0 = c0;
+  if (!is_device_ptr(r0)) {
+    int32_t* t;
+    CK(tmp.alloc((void**)&t, (size_t)n_win * 4));
+    CK(cudaMemcpyAsync(t, r0, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+    d_r0 = t;
+  }
+  if (!is_device_ptr(c0)) {
+    int32_t* t;
+    CK(tmp.alloc((void**)&t, (size_t)n_win * 4));
+    CK(cudaMemcpyAsync(t, c0, (size_t)n_win * 4, cudaMemcpyHostToDevice, st));
+    d_c0 = t;
+  }
+  const size_t bytes = (size_t)n_win * W * 8;
+  double *d_h = horizontal, *d_v = vertical;
+  const bool host_h = !is_device_ptr(horizontal), host_v = !is_device_ptr(vertical);
+  if (host_h) CK(tmp.alloc((void**)&d_h, bytes));
+  if (host_v) CK(tmp.alloc((void**)&d_v, bytes));
+  StripeParams sp{m->pix, m->indptr, m->bad, (m->flags & PUP_F_OOE) ? m->expected : nullptr, m->nb, W,
+                  m->ignore_diags, m->flags};
+  k_stripes<<<(unsigned)((n_win * 32 + 255) / 256), 256, 0, st>>>(sp, d_r0, d_c0, n_win, d_h, d_v);
+  LAUNCH_CHECK("k_stripes");
+  if (host_h) CK(cudaMemcpyAsync(horizontal, d_h, bytes, cudaMemcpyDeviceToHost, st));
+  if (host_v) CK(cudaMemcpyAsync(vertical, d_v, bytes, cudaMemcpyDeviceToHost, st));
+  if (host_h || host_v || !is_device_ptr(r0) || !is_device_ptr(c0)) CK(cudaStreamSynchronize(st));
   return PUP_OK;
 }
 

@@ -140,6 +140,15 @@ int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* in
 int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stream, double* sum, int64_t* num,
                    int64_t* n, double* cov_start, double* cov_end, double* exp_sum, int64_t* exp_num);
 
+/*
+ * store_stripes (coolpup.py:1164-1169): for every window the centre row `data[W/2, :]` ("horizontal") and the
+ * reversed centre column `data[:, W/2][::-1]` ("vertical") of the snippet exactly as _stream_snips builds it
+ * (NaN for masked bins / masked diagonals / NaN expected, x/0 = inf).  horizontal, vertical: [n_win][W] doubles,
+ * host or device, in the order of the input windows; out-of-region windows give NaN rows.
+ */
+int pup_stripes(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0, int W,
+                double* horizontal, double* vertical, void* stream);
+
 /* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
  * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */
 int pup_last_launches(void);

@@ -475,6 +475,11 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
                     vs = [np.divide(x, cn[:, cntr][::-1]) for x in vs]
                 row["horizontal_stripe"] = np.vstack(hs)
                 row["vertical_stripe"] = np.vstack(vs)
+                if local:  # numutils._copy_array_halves (coolpup.py:1594-1600, lib/numutils.py:6-9)
+                    cn = int(np.floor(row["vertical_stripe"].shape[1] / 2))
+                    for f in ("vertical_stripe", "horizontal_stripe"):
+                        x = row[f]
+                        x[:, : cn + 1] = np.fliplr(x[:, cn:])
             if local:
                 import warnings
 

@@ -138,6 +138,39 @@ class EmuRegion:
                     N[di] += self.bad[c : c + W]
         return nv if want_n_valid else None
 
+    def stripes(self, r0, c0, W, stream=0):
+        n = len(r0)
+        hor = np.full((n, W), np.nan)
+        ver = np.full((n, W), np.nan)
+        cn = W // 2
+        flags, igd = self.region_flags, self.ignore_diags
+
+        def pixel(r, c):
+            if self.bad[r] or self.bad[c]:
+                return np.nan
+            d = c - r
+            if not (flags & F_NODIAG) and d < igd:
+                return np.nan
+            lo, hi = self.indptr[r], self.indptr[r + 1]
+            k = lo + np.searchsorted(self.col[lo:hi], c)
+            stored = k < hi and self.col[k] == c
+            v = float(self.count[k]) if stored else 0.0
+            if self.balanced:
+                v = (self.weight[r] * self.weight[c]) * v
+            if flags & F_OOE:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    v = np.float64(v) / self.expected[abs(d)]
+            return v
+
+        for i in range(n):
+            r, c = int(r0[i]), int(c0[i])
+            if r < 0 or c < 0 or r + W > self.nb or c + W > self.nb:
+                continue
+            for k in range(W):
+                hor[i, k] = pixel(r + cn, c + k)
+                ver[i, k] = pixel(r + (W - 1 - k), c + cn)
+        return hor, ver
+
     def algorithmic_bytes(self, r0, c0, W, flags=0, stream=0):
         return 0, 0
 

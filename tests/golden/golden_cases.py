@@ -30,6 +30,12 @@ CASES = {
                        "kwargs": {**TOYKW, "nshifts": 2, "seed": 5}},
     "toy_bywindow": {**TOY, "kwargs": {**TOYKW, "by_window": True}},
     "toy_stripes": {**TOY, "kwargs": {**TOYKW, "store_stripes": True, "clr_weight_name": None, "min_diag": 0}},
+    "toy_stripes_strand_ooe": {**TOY, "expected": "CN.mm9.toy_expected.tsv",
+                               "kwargs": {**TOYKW, "by_strand": True, "ooe": True, "store_stripes": True}},
+    "toy_stripes_notooe": {**TOY, "expected": "CN.mm9.toy_expected.tsv",
+                           "kwargs": {**TOYKW, "by_distance": True, "ooe": False, "store_stripes": True}},
+    "toy_stripes_ctrl_local": {**TOY, "kwargs": {"features_format": "bed", "flank": 3_000_000, "local": True, "nshifts": 2,
+                                                  "seed": 9, "store_stripes": True}},
     "toy_wholechrom": {**{k: v for k, v in TOY.items() if k != "view"}, "kwargs": {"features_format": "bed", "flank": 3_000_000, "mindist": 0}},
     "toy_local_ooe": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "kwargs": {"features_format": "bed", "flank": 2_000_000, "local": True, "ooe": True}},
     "toy_local_raw": {**TOY, "kwargs": {"features_format": "bed", "flank": 3_000_000, "local": True, "clr_weight_name": None, "nshifts": 2, "seed": 2}},
@@ -57,6 +63,9 @@ CASES = {
     "scc1_ctcf_pairs_flip_ooe": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "expected": "compute:count.avg",
                                  "kwargs": dict(features_format="bed", clr_weight_name=None, flank=100_000, by_strand=True,
                                                 flip_negative_strand=True, expected_value_col="count.avg", ooe=True, maxdist=5_000_000)},
+    "scc1_loops_stripes_ctrl": {**SCC1, "features": "CH12_loops_Rao.bed", "features_schema": "bedpe6",
+                                "kwargs": dict(features_format="bedpe", clr_weight_name=None, flank=50_000, nshifts=1, seed=5,
+                                               maxdist=400_000, store_stripes=True)},
     "scc1_ctcf_pairs_arms": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "view": "scc1_arms_view.bed",
                              "kwargs": dict(features_format="bed", clr_weight_name=None, flank=50_000, mindist=0, maxdist=2_000_000,
                                             nshifts=1, seed=4)},

@@ -42,9 +42,13 @@ def _compare_rows(pups, name):
         if "control_n" in g:
             assert int(pups["control_n"].iloc[i]) == int(g["control_n"])
             assert np.array_equal(np.asarray(pups["control_num"].iloc[i]), g["control_num"])
+        if "vertical_stripe" in g:
+            for f in ("vertical_stripe", "horizontal_stripe"):
+                np.testing.assert_allclose(np.asarray(pups[f].iloc[i], dtype=float), g[f], rtol=RTOL, equal_nan=True)
+            assert np.array_equal(np.asarray(pups["coordinates"].iloc[i]).astype(str), g["coordinates"])
 
 
-@pytest.mark.parametrize("name", [n for n in gu.all_cases() if "stripes" not in n])
+@pytest.mark.parametrize("name", gu.all_cases())
 def test_golden_case_through_cuda(name):
     """coolpuppy_b200.pileup() on the GPU == the real reference's stored output (tests/golden)."""
     _cuda()

@@ -10,7 +10,7 @@ import emulator
 import golden_util as gu
 from oracle.pileup_oracle import key_repr
 
-CASES = [n for n in gu.all_cases() if "stripes" not in n and gu.manifest()[n]["windows"] <= 4000]
+CASES = [n for n in gu.all_cases() if gu.manifest()[n]["windows"] <= 4000]
 
 
 @pytest.fixture()
@@ -44,6 +44,10 @@ def test_pileup_api_matches_reference_golden(emu, name):
         if "control_n" in g:
             assert int(pups["control_n"].iloc[i]) == int(g["control_n"])
             assert np.array_equal(np.asarray(pups["control_num"].iloc[i]), g["control_num"])
+        if "vertical_stripe" in g:
+            for f in ("vertical_stripe", "horizontal_stripe"):
+                np.testing.assert_allclose(np.asarray(pups[f].iloc[i], dtype=float), g[f], rtol=1e-9, equal_nan=True)
+            assert np.array_equal(np.asarray(pups["coordinates"].iloc[i]).astype(str), g["coordinates"])
 
 
 @pytest.mark.parametrize("name", ["toy_controls", "scc1_loops_ctrl", "scc1_ctcf_pairs_strand_dist", "scc1_ctcf_pairs_arms",
@@ -79,8 +83,6 @@ def test_unsupported_features_raise():
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True)
     with pytest.raises(NotImplementedError):
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1)
-    with pytest.raises(NotImplementedError):
-        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, store_stripes=True)
     with pytest.raises(ValueError):
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, local=True, by_distance=True)
     with pytest.raises(ValueError):

@@ -88,8 +88,8 @@ def _check_oracle_case(name):
             assert int(o["control_n"]) == int(g["control_n"])
             assert np.array_equal(np.asarray(o["control_num"]), g["control_num"])
         if "vertical_stripe" in g:
-            np.testing.assert_allclose(np.asarray(o["vertical_stripe"], dtype=float), g["vertical_stripe"])
-            np.testing.assert_allclose(np.asarray(o["horizontal_stripe"], dtype=float), g["horizontal_stripe"])
+            np.testing.assert_allclose(np.asarray(o["vertical_stripe"], dtype=float), g["vertical_stripe"], equal_nan=True)
+            np.testing.assert_allclose(np.asarray(o["horizontal_stripe"], dtype=float), g["horizontal_stripe"], equal_nan=True)
     # window streams (pair order, distance filter, np.random control-shift order) and per-region accumulators
     for r in z["regions"]:
         r = str(r)
