@@ -333,11 +333,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     _native.timing_enable(True)
     _native.timing_read(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -456,9 +456,19 @@ def main():
     slow_b, slow_ms = max(per_rank, key=lambda x: x[1])
     achieved = (slow_b / 1e9) / (slow_ms / 1e3) if slow_ms > 0 else 0.0
     n_main = max(1, phases["main"][1])
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r1_k_pileup_main_ncu.md): the
+    # chr1 launch moved 4.82 GB (read+write) for 16.6 GB of algorithmic bytes; scaled to the average launch here
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        traffic = int(tr["dram_bytes"] / tr["algorithmic_bytes"] * (slow_b / max(1, len(mine))))
+    except Exception:
+        pass
     roofline = {
         "kernel": "k_pileup_main", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "traffic_source": "ncu --set full capture of the chr1 launch (profiles/r1_k_pileup_main_ncu.md), scaled by "
+                          "algorithmic bytes to the average launch",
         "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1, len(mine))),
         "kernel_ms_per_step": slow_ms, "launches_per_step": n_main // args.steps,
         "avg_launch_ms": slow_ms / max(1, n_main // args.steps),

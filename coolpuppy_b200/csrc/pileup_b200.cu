@@ -973,23 +973,29 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
 }
 
 // occ != nullptr: only query the occupancy; else launch
-cudaError_t launch_main(int S, int minb, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
-                        int* occ) {
-#define PUP_LAUNCH(SV, MB)                                                                                \
+cudaError_t launch_main(int S, int wu, int minb, const MainParams& p, int grid, int threads, size_t smem,
+                        cudaStream_t st, int* occ) {
+#define PUP_LAUNCH(SV, WV, MB)                                                                            \
   do {                                                                                                    \
-    auto kern = k_pileup_main<SV, 4, MB>;                                                                 \
+    auto kern = k_pileup_main<SV, WV, MB>;                                                                \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
     if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);              \
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                            \
   } while (0)
-  if (minb >= 3) {
-    if (S == 8) PUP_LAUNCH(8, 3);
-    PUP_LAUNCH(4, 3);
+  if (wu == 2) {
+    if (S == 8) PUP_LAUNCH(8, 2, 3);
+    PUP_LAUNCH(4, 2, 3);
   }
-  if (S == 8) PUP_LAUNCH(8, 2);
-  PUP_LAUNCH(4, 2);
+  if (S == 32) PUP_LAUNCH(32, 4, 2);
+  if (S == 16) PUP_LAUNCH(16, 4, 2);
+  if (minb >= 3) {
+    if (S == 8) PUP_LAUNCH(8, 4, 3);
+    PUP_LAUNCH(4, 4, 3);
+  }
+  if (S == 8) PUP_LAUNCH(8, 4, 2);
+  PUP_LAUNCH(4, 4, 2);
 #undef PUP_LAUNCH
 }
 
@@ -1498,7 +1504,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   {
     SpanGuard span(2, st);
     int S = env_int("PUP_GROUP", 4);
-    if (S != 8) S = 4;
+    if (S != 8 && S != 16 && S != 32) S = 4;
     // band height: one tile row per row-group, fp64 tile within PUP_TILE_KB
     const int tile_kb = env_int("PUP_TILE_KB", 72);
     int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (8ll * W));
@@ -1511,10 +1517,11 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     MainParams mp{W, m->nb, m->lb, m->pix, m->rowend, m->bucket, win, chunks, Wb, n_bands, d_acc};
     int occ = 1;
     const int minb = env_int("PUP_MINBLOCKS", 2);
-    cudaError_t e = launch_main(S, minb, mp, 0, threads, smem, st, &occ);
+    const int wu = env_int("PUP_INFLIGHT", 4) == 2 ? 2 : 4;
+    cudaError_t e = launch_main(S, wu, minb, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
-    e = launch_main(S, minb, mp, n_sm * occ, threads, smem, st, nullptr);
+    e = launch_main(S, wu, minb, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
   }
