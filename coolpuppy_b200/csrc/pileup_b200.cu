@@ -208,7 +208,8 @@ struct pup_region {
   int ignore_diags;
   unsigned flags;     // PUP_F_OOE | PUP_F_NODIAG folded into the pixel values
   Pix* pix;           // [nnz] (col, normalised value)
-  int32_t* indptr;    // [nb+1]
+  int32_t* indptr;    // [nb+1] CSR row pointers of the symmetric matrix (input order, unpadded)
+  int32_t* prow;      // [nb+1] row starts inside pix[]: every row is padded to a multiple of 4 pixels (64 bytes)
   int32_t* rowend;    // [nb] indptr[r+1], or indptr[r] (empty run) when the row's weight is NaN
   int32_t* bucket;    // [nbk][nb] first entry of row r with col >= b << lb
   double* expected;   // [nb] or null
@@ -225,11 +226,21 @@ struct pup_region {
 namespace {
 
 // ------------------------------------------------------------------------------------------ prep kernels
-// One warp per matrix row: normalise every stored pixel once and write the 16-byte records.
-__global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col,
-                                 const int32_t* __restrict__ cnt, const double* __restrict__ weight,
-                                 const double* __restrict__ expected, Pix* __restrict__ pix,
-                                 int32_t* __restrict__ rowend, int nb, int ignore_diags, unsigned flags) {
+// padded row length (multiple of PIX_ALIGN pixels) -> scanned into prow[]
+constexpr int PIX_ALIGN = 4;  // pixels; 4 x 16 B = one 64-byte segment per lane-quad load, never straddling a line
+__global__ void k_padded_len(const int32_t* __restrict__ indptr, int32_t* __restrict__ plen, int nb) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < nb) plen[r] = (indptr[r + 1] - indptr[r] + PIX_ALIGN - 1) & ~(PIX_ALIGN - 1);
+  if (r == nb) plen[r] = 0;
+}
+
+// One warp per matrix row: normalise every stored pixel once and write the 16-byte records; the row is padded with
+// sentinel pixels (col = INT_MAX, sorted last) so that every row starts on a 64-byte boundary.
+__global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32_t* __restrict__ prow,
+                                 const int32_t* __restrict__ col, const int32_t* __restrict__ cnt,
+                                 const double* __restrict__ weight, const double* __restrict__ expected,
+                                 Pix* __restrict__ pix, int32_t* __restrict__ rowend, int nb, int ignore_diags,
+                                 unsigned flags) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -237,13 +248,14 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
   const bool nodiag = flags & PUP_F_NODIAG;
   for (int64_t r = warp; r < nb; r += nwarps) {
     const int lo = indptr[r], hi = indptr[r + 1];
+    const int dst = prow[r], dend = prow[r + 1];
     double wr = 1.0;
     bool rbad = false;
     if (weight != nullptr) {
       wr = weight[r];
       rbad = isnan(wr);
     }
-    if (lane == 0) rowend[r] = rbad ? lo : hi;  // masked rows contribute nothing: empty run
+    if (lane == 0) rowend[r] = rbad ? dst : dst + (hi - lo);  // masked rows contribute nothing: empty run
     for (int i = lo + lane; i < hi; i += 32) {
       const int c = col[i];
       double v = (double)cnt[i];
@@ -256,7 +268,14 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
       p.col = c;
       p.pad = 0;
       p.val = v;
-      pix[i] = p;
+      pix[dst + (i - lo)] = p;
+    }
+    for (int k = dst + (hi - lo) + lane; k < dend; k += 32) {
+      Pix p;
+      p.col = 0x7fffffff;
+      p.pad = 0;
+      p.val = 0.0;
+      pix[k] = p;
     }
   }
 }
@@ -339,16 +358,19 @@ __global__ void k_place_lower(const int32_t* __restrict__ sorted_key, const int3
   cnt_s[dst] = cnt_u[src];
 }
 
-// bucket[b * nb + r] = first entry index of row r whose column is >= (b << lb)
+// bucket[b * nb + r] = position in pix[] (rounded down to a 64-byte boundary inside the row) of the first pixel of
+// row r whose column is >= (b << lb)
 __global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* __restrict__ indptr,
-                                int32_t* __restrict__ bucket, int nb, int nbk, int lb) {
+                                const int32_t* __restrict__ prow, int32_t* __restrict__ bucket, int nb, int nbk,
+                                int lb) {
   int64_t total = (int64_t)nb * nbk;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
   for (; i < total; i += step) {
     int r = (int)(i % nb);
     int b = (int)(i / nb);
-    int lo = indptr[r], hi = indptr[r + 1];
+    const int base = indptr[r];
+    int lo = base, hi = indptr[r + 1];
     int target = b << lb;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
@@ -357,7 +379,7 @@ __global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* 
       else
         hi = mid;
     }
-    bucket[i] = lo;
+    bucket[i] = (prow[r] + (lo - base)) & ~(PIX_ALIGN - 1);
   }
 }
 
@@ -1091,9 +1113,22 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   const int32_t nb = r->nb;
   const int64_t nnz = r->nnz;
   r->lb = choose_bucket_bits(nb, nnz, &r->nbk);
-  size_t n_ent = (size_t)(nnz > 0 ? nnz : 1);
+  size_t n_ent = (size_t)nnz + (size_t)(PIX_ALIGN - 1) * nb + 1;  // rows padded to 64-byte boundaries
   CK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
+  CK(cudaMallocAsync((void**)&r->prow, (size_t)(nb + 1) * 4, st));
   CK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
+  {
+    int32_t* plen;
+    CK(tmp.alloc((void**)&plen, (size_t)(nb + 1) * 4));
+    k_padded_len<<<(nb + 1 + 255) / 256, 256, 0, st>>>(r->indptr, plen, nb);
+    LAUNCH_CHECK("k_padded_len");
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, plen, r->prow, nb + 1, st));
+    void* t;
+    CK(tmp.alloc(&t, tb));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, plen, r->prow, nb + 1, st));
+    ++g_launches;
+  }
   CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
   CK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
   CK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
@@ -1107,14 +1142,14 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   }
   {
     int grid = std::min((nb + 7) / 8, 148 * 16);
-    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
+    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, r->prow, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
                                            r->ignore_diags, r->flags);
     LAUNCH_CHECK("k_prepare_pixels");
   }
   {
     int64_t total = (int64_t)nb * r->nbk;
     int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->bucket, nb, r->nbk, r->lb);
+    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->prow, r->bucket, nb, r->nbk, r->lb);
     LAUNCH_CHECK("k_build_buckets");
   }
   {
@@ -1363,7 +1398,7 @@ int pup_region_destroy(pup_region_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
-  void* ptrs[] = {r->pix,      r->indptr, r->rowend, r->bucket,  r->expected, r->coverage,
+  void* ptrs[] = {r->pix,      r->indptr, r->prow,   r->rowend,  r->bucket,   r->expected, r->coverage,
                   r->bad,      r->ebad,   r->ebadpre, r->badpre, r->badlist};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
@@ -1638,7 +1673,7 @@ int pup_stripes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const i
   const bool host_h = !is_device_ptr(horizontal), host_v = !is_device_ptr(vertical);
   if (host_h) CK(tmp.alloc((void**)&d_h, bytes));
   if (host_v) CK(tmp.alloc((void**)&d_v, bytes));
-  StripeParams sp{m->pix, m->indptr, m->bad, (m->flags & PUP_F_OOE) ? m->expected : nullptr, m->nb, W,
+  StripeParams sp{m->pix, m->prow, m->bad, (m->flags & PUP_F_OOE) ? m->expected : nullptr, m->nb, W,
                   m->ignore_diags, m->flags};
   k_stripes<<<(unsigned)((n_win * 32 + 255) / 256), 256, 0, st>>>(sp, d_r0, d_c0, n_win, d_h, d_v);
   LAUNCH_CHECK("k_stripes");
@@ -1672,7 +1707,7 @@ int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r
   CK(tmp.alloc((void**)&d_out, 16));
   CK(cudaMemsetAsync(d_out, 0, 16, st));
   if (n_win > 0) {
-    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->pix, m->indptr, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
+    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->pix, m->prow, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_count_nnz", e);
   }
