@@ -152,3 +152,29 @@ def synthetic_loops(n_loops, chromsizes=None, binsize=10_000, flank=410_000, see
     df = pd.DataFrame({"chrom1": np.array(names)[ch], "start1": a, "end1": a + binsize,
                        "chrom2": np.array(names)[ch], "start2": b, "end2": b + binsize})
     return df[keep].reset_index(drop=True)
+
+
+def synthetic_cooler(chromsizes, binsize=10_000, depth=50.0, seed=0, device="cuda", nan_frac=0.03):
+    """A :class:`~coolpuppy_b200.coolio.MemCooler` holding a small synthetic genome (cis pixels only) with a
+    ``weight`` column, plus a matching expected table (``balanced.avg`` / ``count.avg``) for the whole-chromosome
+    view.  Used by the mid-size parity tests of BASELINE configs[2] and configs[4]."""
+    from .coolio import MemCooler
+
+    bins = chrom_bins(chromsizes, binsize)
+    b1, b2, cnt, ws, exp_rows = [], [], [], [], []
+    off = 0
+    for ci, (c, nb) in enumerate(bins.items()):
+        t = synthetic_region(nb, depth=depth, seed=seed + ci, device=device, nan_frac=nan_frac)
+        ip = t["upper_indptr"].cpu().numpy().astype(np.int64)
+        rows = np.repeat(np.arange(nb, dtype=np.int64), np.diff(ip))
+        b1.append(rows + off)
+        b2.append(t["upper_col"].cpu().numpy().astype(np.int64) + off)
+        cnt.append(t["upper_count"].cpu().numpy().astype(np.int32))
+        ws.append(t["weight"].cpu().numpy())
+        exp_rows.append(pd.DataFrame({"region1": c, "region2": c, "dist": np.arange(nb), "n_valid": nb - np.arange(nb),
+                                      "balanced.avg": t["expected"].cpu().numpy(),
+                                      "count.avg": t["expected_raw"].cpu().numpy()}))
+        off += nb
+    clr = MemCooler(chromsizes, binsize, np.concatenate(b1), np.concatenate(b2), np.concatenate(cnt),
+                    {"weight": np.concatenate(ws)}, filename="synthetic.cool")
+    return clr, pd.concat(exp_rows, ignore_index=True)

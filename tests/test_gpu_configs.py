@@ -1,0 +1,91 @@
+"""GPU parity of the BASELINE.json configurations that are not the bench line, at sizes the oracle finishes in
+seconds, through the public Python API on a synthetic cooler:
+  configs[2]: bedpe loops, pad = 41, balanced, expected ooe
+  configs[4]: all-vs-all stranded sites, by_strand + by_distance, pad = 101 (W = 203: the tile is split in row bands)
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6
+
+
+def _compare(pups, ref):
+    from oracle.pileup_oracle import key_repr
+
+    # the wrappers re-sort the rows (coolpup.py:1826-1832, 1910-1918; pinned by tests/golden): compare by group key
+    by_key = ref.by_key()
+    assert sorted(key_repr(g) for g in pups["group"]) == sorted(by_key)
+    for _, row in pups.iterrows():
+        o = by_key[key_repr(row["group"])]
+        assert int(row["n"]) == int(o["n"])
+        assert np.array_equal(np.asarray(row["num"]), np.asarray(o["num"]))
+        a, b = np.asarray(row["data"], dtype=float), np.asarray(o["data"], dtype=float)
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=RTOL)
+        if "control_n" in o:
+            assert int(row["control_n"]) == int(o["control_n"])
+            assert np.array_equal(np.asarray(row["control_num"]), np.asarray(o["control_num"]))
+
+
+@pytest.fixture(scope="module")
+def genome():
+    from coolpuppy_b200 import _native
+    from coolpuppy_b200.synthetic import synthetic_cooler
+
+    if _native.device_count() < 1:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    sizes = {"chr1": 52_000_000, "chr2": 38_000_000, "chr3": 9_000_000}
+    return synthetic_cooler(sizes, binsize=10_000, depth=60.0, seed=77, device="cuda"), sizes
+
+
+def test_config2_bedpe_loops_pad41_ooe(genome):
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.synthetic import synthetic_loops
+    from oracle.pileup_oracle import oracle_pileup
+
+    (clr, exp), sizes = genome
+    loops = synthetic_loops(1500, chromsizes=sizes, binsize=10_000, flank=410_000, seed=5, dmin=900_000, dmax=8_000_000)
+    kw = dict(features_format="bedpe", flank=410_000, expected_df=exp, ooe=True, clr_weight_name="weight")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, loops, **kw)
+        ref = oracle_pileup(clr, loops, **kw)
+    assert int(pups["n"].iloc[0]) > 1000
+    _compare(pups, ref)
+
+
+def test_config4_strand_distance_pad101(genome):
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.synthetic import synthetic_sites
+    from oracle.pileup_oracle import oracle_pileup
+
+    (clr, exp), sizes = genome
+    sites, npairs = synthetic_sites(1500, chromsizes=sizes, binsize=10_000, flank=1_010_000, seed=3)
+    kw = dict(features_format="bed", flank=1_010_000, by_strand=True, by_distance=True, expected_df=exp, ooe=True,
+              clr_weight_name="weight")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, sites, **kw)
+        ref = oracle_pileup(clr, sites, **kw)
+    assert pups["data"].iloc[0].shape == (203, 203) and len(pups) > 5
+    _compare(pups, ref)
+
+
+def test_config3_shape_controls_allpairs_pad41(genome):
+    """The bench configuration (all-vs-all pairs, nshifts controls, balanced, no expected) at oracle-checkable size."""
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.synthetic import synthetic_sites
+    from oracle.pileup_oracle import oracle_pileup
+
+    (clr, exp), sizes = genome
+    sites, npairs = synthetic_sites(400, chromsizes=sizes, binsize=10_000, flank=410_000, seed=9)
+    kw = dict(features_format="bed", flank=410_000, nshifts=3, seed=0, clr_weight_name="weight")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, sites, **kw)
+        ref = oracle_pileup(clr, sites, **kw)
+    _compare(pups, ref)
