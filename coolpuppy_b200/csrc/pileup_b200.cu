@@ -165,7 +165,7 @@ int ilog2_ceil(int64_t v) {
   return b;
 }
 
-constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel
+constexpr int NT_MAX = 352;  // max threads per CTA of the main kernel (11 warps: 88 lane-quads >= 83 tile rows)
 constexpr int VT = 512;      // max threads per CTA of the vector kernel
 constexpr int VCH = 256;     // windows per CTA step of the vector kernel
 constexpr int VU = 4;        // windows in flight per thread of the vector kernel
@@ -228,9 +228,12 @@ namespace {
 // ------------------------------------------------------------------------------------------ prep kernels
 // padded row length (multiple of PIX_ALIGN pixels) -> scanned into prow[]
 constexpr int PIX_ALIGN = 4;  // pixels; 4 x 16 B = one 64-byte segment per lane-quad load, never straddling a line
+constexpr int PIX_GROUP = 8;  // sentinel padding granularity (covers lane groups of up to 8 lanes)
 __global__ void k_padded_len(const int32_t* __restrict__ indptr, int32_t* __restrict__ plen, int nb) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < nb) plen[r] = (indptr[r + 1] - indptr[r] + PIX_ALIGN - 1) & ~(PIX_ALIGN - 1);
+  // at least one complete group of sentinel pixels follows the last stored pixel of every row, so a lane that steps
+  // past the end of its row always reads a sentinel (col = INT_MAX) and the pile-up loop needs no end-of-row test
+  if (r < nb) plen[r] = ((indptr[r + 1] - indptr[r] + PIX_GROUP - 1) / PIX_GROUP + 1) * PIX_GROUP;
   if (r == nb) plen[r] = 0;
 }
 
@@ -361,8 +364,8 @@ __global__ void k_place_lower(const int32_t* __restrict__ sorted_key, const int3
 // bucket[b * nb + r] = position in pix[] (rounded down to a 64-byte boundary inside the row) of the first pixel of
 // row r whose column is >= (b << lb)
 __global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* __restrict__ indptr,
-                                const int32_t* __restrict__ prow, int32_t* __restrict__ bucket, int nb, int nbk,
-                                int lb) {
+                                const int32_t* __restrict__ prow, const int32_t* __restrict__ rowend,
+                                int32_t* __restrict__ bucket, int nb, int nbk, int lb) {
   int64_t total = (int64_t)nb * nbk;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t step = (int64_t)gridDim.x * blockDim.x;
@@ -379,7 +382,9 @@ __global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* 
       else
         hi = mid;
     }
-    bucket[i] = (prow[r] + (lo - base)) & ~(PIX_ALIGN - 1);
+    // masked rows (rowend == row start) contribute nothing: point them at their sentinel group
+    const int first = (rowend[r] == prow[r] && indptr[r + 1] > base) ? prow[r + 1] - PIX_GROUP : prow[r] + (lo - base);
+    bucket[i] = first & ~(PIX_ALIGN - 1);
   }
 }
 
@@ -682,7 +687,6 @@ __global__ void k_vector(const VecParams p) {
 struct MainParams {
   int W, nb, lb;
   const Pix* pix;
-  const int32_t* rowend;
   const int32_t* bucket;
   const int2* win;  // sorted (r0, c0)
   ChunkTable chunks;
@@ -755,22 +759,18 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
     if (di >= W) continue;
 
     for (int w = w_lo; w < w_hi; w += WU) {
-      int idx[WU], pend[WU], c0s[WU];
+      int idx[WU], c0s[WU];
       int djA[WU], djB[WU];
       double vA[WU], vB[WU];
-#pragma unroll
-      for (int u = 0; u < WU; ++u) vB[u] = 0.0;
       // stage A: window records -> row pointers (WU independent chains)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        idx[u] = 0;
-        pend[u] = 0;
+        idx[u] = -1;
         c0s[u] = 0;
+        vB[u] = 0.0;
         if (w + u < w_hi) {
           const int2 rc = __ldg(&p.win[w + u]);
-          const int r = rc.x + di;
-          idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * nb + r]) + ls;
-          pend[u] = __ldg(&p.rowend[r]);
+          idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * nb + rc.x + di]) + ls;
           c0s[u] = rc.y;
         }
       }
@@ -779,19 +779,20 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
       for (int u = 0; u < WU; ++u) {
         djA[u] = 0x7fffffff;
         vA[u] = 0.0;
-        if (idx[u] < pend[u]) {
+        if (idx[u] >= 0) {
           const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
           djA[u] = raw.x - c0s[u];
           vA[u] = __hiloint2double(raw.w, raw.z);
         }
       }
-      // stage C: the WU runs advance in lockstep, S pixels per run per half-step
+      // stage C: the WU runs advance in lockstep, S pixels per run per half-step.  Rows end with a full group of
+      // sentinel pixels (col = INT_MAX), so "dj >= W" is the only termination test.
 #define PUP_HALF_STEP(CD, CV, ND, NV)                                                        \
   {                                                                                          \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
       ND[u] = 0x7fffffff;                                                                    \
       idx[u] += S;                                                                           \
-      if (CD[u] < W && idx[u] < pend[u]) {                                                   \
+      if (CD[u] < W) {                                                                       \
         const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));               \
         ND[u] = raw.x - c0s[u];                                                              \
         NV[u] = __hiloint2double(raw.w, raw.z);                                              \
@@ -1010,17 +1011,14 @@ cudaError_t launch_main(int S, int wu, int minb, const MainParams& p, int grid, 
     kern<<<grid, threads, smem, st>>>(p);                                                                 \
     return cudaGetLastError();                                                                            \
   } while (0)
-  if (wu == 2) {
-    if (S == 8) PUP_LAUNCH(8, 2, 3);
-    PUP_LAUNCH(4, 2, 3);
+  (void)minb;
+  if (S == 8) {
+    if (wu == 6) PUP_LAUNCH(8, 6, 2);
+    PUP_LAUNCH(8, 4, 2);
   }
-  if (S == 32) PUP_LAUNCH(32, 4, 2);
-  if (S == 16) PUP_LAUNCH(16, 4, 2);
-  if (minb >= 3) {
-    if (S == 8) PUP_LAUNCH(8, 4, 3);
-    PUP_LAUNCH(4, 4, 3);
-  }
-  if (S == 8) PUP_LAUNCH(8, 4, 2);
+  if (wu == 8) PUP_LAUNCH(4, 8, 2);
+  if (wu == 6) PUP_LAUNCH(4, 6, 2);
+  if (wu == 2) PUP_LAUNCH(4, 2, 3);
   PUP_LAUNCH(4, 4, 2);
 #undef PUP_LAUNCH
 }
@@ -1117,7 +1115,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   const int32_t nb = r->nb;
   const int64_t nnz = r->nnz;
   r->lb = choose_bucket_bits(nb, nnz, &r->nbk);
-  size_t n_ent = (size_t)nnz + (size_t)(PIX_ALIGN - 1) * nb + 1;  // rows padded to 64-byte boundaries
+  size_t n_ent = (size_t)nnz + (size_t)(2 * PIX_GROUP) * nb + PIX_GROUP;  // rows padded with sentinel groups
   CK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
   CK(cudaMallocAsync((void**)&r->prow, (size_t)(nb + 1) * 4, st));
   CK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
@@ -1153,7 +1151,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   {
     int64_t total = (int64_t)nb * r->nbk;
     int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->prow, r->bucket, nb, r->nbk, r->lb);
+    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->prow, r->rowend, r->bucket, nb, r->nbk, r->lb);
     LAUNCH_CHECK("k_build_buckets");
   }
   {
@@ -1543,7 +1541,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   {
     SpanGuard span(2, st);
     int S = env_int("PUP_GROUP", 4);
-    if (S != 8 && S != 16 && S != 32) S = 4;
+    if (S != 8) S = 4;
     // band height: one tile row per row-group, fp64 tile within PUP_TILE_KB
     const int tile_kb = env_int("PUP_TILE_KB", 72);
     int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (8ll * W));
@@ -1553,10 +1551,10 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     Wb = (W + n_bands - 1) / n_bands;  // balance the bands
     const int threads = std::min(NT_MAX, ((Wb * S + 31) / 32) * 32);
     const size_t smem = (size_t)Wb * W * 8;
-    MainParams mp{W, m->nb, m->lb, m->pix, m->rowend, m->bucket, win, chunks, Wb, n_bands, d_acc};
+    MainParams mp{W, m->nb, m->lb, m->pix, m->bucket, win, chunks, Wb, n_bands, d_acc};
     int occ = 1;
     const int minb = env_int("PUP_MINBLOCKS", 2);
-    const int wu = env_int("PUP_INFLIGHT", 4) == 2 ? 2 : 4;
+    const int wu = env_int("PUP_INFLIGHT", 4);
     cudaError_t e = launch_main(S, wu, minb, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
