@@ -707,7 +707,7 @@ __device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st
 // kernel has no CTA-wide barrier at all: warps drift freely through the CTA's (static, round-robin) chunk list.
 // WU windows advance in lockstep per row-group (two register sets, ping-pong), so WU independent 16-byte loads
 // are in flight per lane while the previous S pixels of every window are added to the tile.
-template <int S, int WU, int MINB>
+template <int S, int WU, int MINB, int PF = 0>
 __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int W = p.W;
@@ -796,6 +796,8 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
         const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));               \
         ND[u] = raw.x - c0s[u];                                                              \
         NV[u] = __hiloint2double(raw.w, raw.z);                                              \
+        if (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pix + idx[u] + S));     \
+        if (PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pix + idx[u] + 2 * S)); \
       }                                                                                      \
     }                                                                                        \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
@@ -1012,13 +1014,27 @@ cudaError_t launch_main(int S, int wu, int minb, const MainParams& p, int grid, 
     return cudaGetLastError();                                                                            \
   } while (0)
   (void)minb;
-  if (S == 8) {
-    if (wu == 6) PUP_LAUNCH(8, 6, 2);
-    PUP_LAUNCH(8, 4, 2);
-  }
-  if (wu == 8) PUP_LAUNCH(4, 8, 2);
-  if (wu == 6) PUP_LAUNCH(4, 6, 2);
+  if (S == 8) PUP_LAUNCH(8, 4, 2);
   if (wu == 2) PUP_LAUNCH(4, 2, 3);
+  {
+    const int pf = env_int("PUP_PREFETCH", 2);
+    if (pf == 1) {
+      auto kern = k_pileup_main<4, 4, 2, 1>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
+      kern<<<grid, threads, smem, st>>>(p);
+      return cudaGetLastError();
+    }
+    if (pf == 2) {
+      auto kern = k_pileup_main<4, 4, 2, 2>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
+      kern<<<grid, threads, smem, st>>>(p);
+      return cudaGetLastError();
+    }
+  }
   PUP_LAUNCH(4, 4, 2);
 #undef PUP_LAUNCH
 }
