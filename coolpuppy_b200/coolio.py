@@ -211,6 +211,17 @@ class _CoolerBase:
         cnt = self._count[p0:p1]
         if not np.issubdtype(cnt.dtype, np.integer):
             raise NotImplementedError("floating-point pixel counts are not supported by the CUDA path")
+        if cols.size > 1:
+            # the format requires pixels sorted by (bin1, bin2); some files in the wild (e.g. the reference's
+            # CN.mm9.1000kb.cool test fixture) have out-of-order tails inside a row: sort those rows here
+            desc = np.diff(cols) <= 0
+            if indptr.size > 2:
+                inner = indptr[1:-1]
+                desc[inner[(inner > 0) & (inner < cols.size)] - 1] = False  # row boundaries may descend
+            if desc.any():
+                rows = np.repeat(np.arange(hi - lo, dtype=np.int64), np.diff(indptr))
+                order = np.lexsort((cols, rows))
+                cols, cnt = cols[order], cnt[order]
         return indptr, cols, np.ascontiguousarray(cnt, dtype=np.int32)
 
     def region_csr(self, lo, hi):

@@ -29,6 +29,11 @@ def layout(W):
 
 def symmetrise(nb, indptr_u, col_u, cnt_u):
     row = np.repeat(np.arange(nb), np.diff(indptr_u))
+    # the device code requires sorted columns within every row (it mirrors by a stable sort and takes the
+    # in-region columns as a prefix): enforce the same contract here
+    if col_u.size > 1:
+        same_row = row[1:] == row[:-1]
+        assert np.all(np.diff(col_u.astype(np.int64))[same_row] > 0), "upper CSR rows must have sorted, unique columns"
     keep = (col_u >= 0) & (col_u < nb)
     row, col, cnt = row[keep], col_u[keep].astype(np.int64), cnt_u[keep]
     off = row != col
