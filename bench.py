@@ -379,31 +379,39 @@ def main():
 
         s_copy, s_comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         ASYNC = _native.PUP_F_ASYNC
+        # upload order: one small chromosome first (its upload is the only one nothing overlaps), then big to small
+        e2e_order = sorted(mine, key=lambda c: -windows[c]["nb"])
+        if len(e2e_order) > 2:
+            e2e_order = [e2e_order[-1]] + e2e_order[:-1]
+        # persistent device landing buffers for the window arrays (filled from the pinned host arrays every step)
+        dwin_e2e = {c: tuple(torch.empty_like(t, device=dev) for t in hwin[c]) for c in mine}
 
         def e2e_step():
-            # double-buffered: upload + index chromosome k+1 on the copy stream while chromosome k piles up
+            # every upload (matrices via pup_region_create_upper, window arrays via pup_upload) travels on the
+            # library's upload stream in consumption order and runs ahead of the kernels; chromosome k+1 is
+            # mirrored / normalised / indexed on s_copy while chromosome k piles up on s_comp
             main_stream = torch.cuda.current_stream(dev)
             s_comp.wait_stream(main_stream)
             s_copy.wait_stream(main_stream)
             with torch.cuda.stream(s_comp):
                 acc.zero_()
-            pending = []
 
             def upload(c):
                 h = host[c]
-                with torch.cuda.stream(s_copy):
-                    reg = _native.Region(local_rank, windows[c]["nb"], h["upper_indptr"], h["upper_col"], h["upper_count"],
-                                         h["weight"], None, None, ignore_diags=2, flags=ASYNC, stream=s_copy.cuda_stream,
-                                         upper=True)
-                    ev = s_copy.record_event()
+                reg = _native.Region(local_rank, windows[c]["nb"], h["upper_indptr"], h["upper_col"], h["upper_count"],
+                                     h["weight"], None, None, ignore_diags=2, flags=ASYNC, stream=s_copy.cuda_stream,
+                                     upper=True)
+                for d, hsrc in zip(dwin_e2e[c], hwin[c]):
+                    _native.upload(local_rank, d, hsrc, stream=s_copy.cuda_stream)
+                ev = s_copy.record_event()  # matrix indexed and window arrays landed
                 return reg, ev
 
-            nxt = upload(mine[0]) if mine else None
-            for k, c in enumerate(mine):
+            nxt = upload(e2e_order[0]) if e2e_order else None
+            for k, c in enumerate(e2e_order):
                 reg, ready = nxt
-                nxt = upload(mine[k + 1]) if k + 1 < len(mine) else None
+                nxt = upload(e2e_order[k + 1]) if k + 1 < len(e2e_order) else None
                 s_comp.wait_event(ready)
-                r0, c0, sl = hwin[c]
+                r0, c0, sl = dwin_e2e[c]
                 reg.accumulate(r0, c0, sl, W, n_slots, flags | ASYNC, acc, stream=s_comp.cuda_stream)
                 done = s_comp.record_event()
                 s_copy.wait_event(done)
@@ -434,8 +442,8 @@ def main():
                "steps": args.e2e_steps,
                "what": "pup_region_create_upper + pup_accumulate per chromosome with pinned HOST buffers: the cooler-style "
                        "upper-triangle pixels (indptr, col, count), weights and window arrays are uploaded, mirrored / "
-                       "normalised / indexed on the device and piled up; the upload of chromosome k+1 overlaps the "
-                       "pile-up of k on a second stream; D2H of the accumulators at the end"}
+                       "normalised / indexed on the device and piled up; uploads run ahead on copy streams in consumption "
+                       "order, chromosome k+1 is indexed while chromosome k piles up; D2H of the accumulators at the end"}
 
     if rank != 0:
         if dist is not None:

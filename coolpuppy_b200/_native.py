@@ -21,7 +21,7 @@ _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200
 
 SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",
-    "pup_region_destroy",
+    "pup_region_destroy", "pup_upload",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
 ]
@@ -49,6 +49,7 @@ def lib():
     L.pup_region_create.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, C.c_int, u32, vp, C.POINTER(vp)]
     L.pup_region_create_upper.argtypes = L.pup_region_create.argtypes
     L.pup_region_destroy.argtypes = [vp]
+    L.pup_upload.argtypes = [C.c_int, vp, vp, i64, vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
     L.pup_acc_stride.argtypes = [C.c_int]
@@ -182,6 +183,13 @@ def accumulate_region(device, nb, indptr, col, count, weight, expected, coverage
                                       ptr(slot), int(W), int(ignore_diags), int(n_slots), int(flags), ptr(acc),
                                       stream, C.byref(nv)))
     return nv.value
+
+
+def upload(device, dst, src, stream=0):
+    """``pup_upload``: async H2D copy of ``src`` (host tensor / array, pinned for real asynchrony) into the device
+    tensor ``dst`` through the library's upload stream (FIFO with the region matrices); ``stream`` waits for it."""
+    nbytes = src.numel() * src.element_size() if hasattr(src, "numel") else src.nbytes
+    check(lib().pup_upload(device, ptr(dst), ptr(src), int(nbytes), stream))
 
 
 def timing_enable(on=True):

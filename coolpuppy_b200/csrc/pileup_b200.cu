@@ -6,13 +6,16 @@
 //   region prep (once per region):  every stored pixel is normalised exactly once
 //       val = (w[row] * w[col]) * count / E[|col-row|];  val = 0 where the reference would produce NaN
 //       (NaN weight, NaN expected, signed diagonal mask) because nansum() adds nothing there
+//   storage: the matrix is cut into strips of R consecutive rows (R = 2 by default); inside a strip the pixels of
+//       the R rows are merged and sorted by (col, row), so the part of a strip that a window needs is ONE
+//       contiguous run R times longer than a CSR row run, read with full 128-byte lines
 //   pile-up (k_pileup_main):
-//   for every window (r0, c0, slot):                       # sorted by (slot, r0, c0) on the device
-//     for every window row di:                             # one lane-quad owns row di of the shared-memory tile
-//       start = bucket[(c0 >> lb) * nb + r0 + di]          # column-bucket-major row pointer table: no binary search
-//       stream the row's (col, val) pairs from `start` while col < c0 + W       # 16-byte loads, 4 windows in flight
-//       tile[di][col - c0] += val                          # fp64 shared-memory tile, race-free by row ownership
-//   flush tile with red.global.add.f64 when the slot changes
+//   for every window (r0, c0, slot):                       # sorted by (slot, r0 mod R, r0, c0) on the device
+//     for every strip G the window touches:                # one lane group (S = 4R lanes) owns R rows of the tile
+//       start = bucket[(c0 >> lb) * ns + (r0 / R) + G]     # column-bucket-major strip pointer table: no binary search
+//       stream the strip's (col, q, val) records from `start` while col < c0 + W   # 16-byte loads, 4 windows in flight
+//       tile[G * R + q][col - c0] += val                   # fp64 shared-memory tile, race-free by row ownership
+//   flush tile rows (tile row t = window row di + r0 mod R) with red.global.add.f64 when the slot changes
 //
 // `num` (count of finite contributions) is dense in the reference (W*W work per window).  Here it is
 //   num = n_fast - rowbad[di] - colbad[dj] + xtile[di][dj]
@@ -88,6 +91,12 @@ int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     if (e_ != cudaSuccess) return fail(PUP_E_CUDA, "launch " name, e_);                        \
   } while (0)
 
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
 // keep freed stream-ordered allocations in the device's default pool instead of returning them to the driver
 // at every synchronisation (scratch buffers are re-used by the next call)
 void retain_pool_memory(int dev) {
@@ -97,6 +106,12 @@ void retain_pool_memory(int dev) {
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     uint64_t thr = ~0ull;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // never make one stream wait for another just to recycle a freed block: the upload stream of region k+1 must
+    // not be chained behind the pile-up of region k (blocks whose free has already completed are still reused)
+    if (env_int("PUP_POOL_DEPS", 0) == 0) {
+      int off = 0;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
+    }
   }
   cudaGetLastError();
   done[dev] = true;
@@ -144,6 +159,20 @@ struct Scratch {
   }
 };
 
+// Zero-fill by a kernel, not cudaMemsetAsync: memsets are executed by a copy engine, where they queue behind the
+// (hundreds of MB) host->device uploads of the following regions and stall the pile-up of the current one.
+__global__ void k_zero(uint32_t* __restrict__ p, size_t n_words) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+cudaError_t zero_async(void* p, size_t bytes, cudaStream_t st) {
+  const size_t n = (bytes + 3) / 4;  // all callers pass 4-byte-aligned buffers whose size is a multiple of 4
+  if (n == 0) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+  k_zero<<<grid, 256, 0, st>>>(reinterpret_cast<uint32_t*>(p), n);
+  return cudaGetLastError();
+}
+
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -153,11 +182,6 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  if (!v || !*v) return dflt;
-  return atoi(v);
-}
 
 int ilog2_ceil(int64_t v) {
   int b = 0;
@@ -165,7 +189,7 @@ int ilog2_ceil(int64_t v) {
   return b;
 }
 
-constexpr int NT_MAX = 352;  // max threads per CTA of the main kernel (11 warps: 88 lane-quads >= 83 tile rows)
+constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel (12 warps)
 constexpr int VT = 512;      // max threads per CTA of the vector kernel
 constexpr int VCH = 256;     // windows per CTA step of the vector kernel
 constexpr int VU = 4;        // windows in flight per thread of the vector kernel
@@ -173,7 +197,7 @@ constexpr int VU = 4;        // windows in flight per thread of the vector kerne
 // one stored pixel as the main kernel reads it: 16 bytes, one ld.global.nc.v4 per lane
 struct __align__(16) Pix {
   int col;
-  int pad;
+  int q;  // row inside its strip (row & (R - 1))
   double val;
 };
 
@@ -205,13 +229,16 @@ struct pup_region {
   int64_t nnz;
   int lb;   // log2 of the column-bucket width
   int nbk;  // number of column buckets
+  int R;    // rows per strip (power of two)
+  int lr;   // log2 R
+  int S;    // lanes per strip run in the main kernel; strips are aligned / padded to S pixels
+  int32_t ns;  // number of strips = ceil(nb / R)
   int ignore_diags;
   unsigned flags;     // PUP_F_OOE | PUP_F_NODIAG folded into the pixel values
-  Pix* pix;           // [nnz] (col, normalised value)
+  Pix* pix;           // strip-major pixels: (col, q, normalised value), sorted by (col, q) inside a strip
   int32_t* indptr;    // [nb+1] CSR row pointers of the symmetric matrix (input order, unpadded)
-  int32_t* prow;      // [nb+1] row starts inside pix[]: every row is padded to a multiple of 4 pixels (64 bytes)
-  int32_t* rowend;    // [nb] indptr[r+1], or indptr[r] (empty run) when the row's weight is NaN
-  int32_t* bucket;    // [nbk][nb] first entry of row r with col >= b << lb
+  int32_t* prow;      // [ns+1] strip starts inside pix[]: multiples of S pixels, >= S sentinel pixels close a strip
+  int32_t* bucket;    // [nbk][ns] first entry (rounded down to S) of strip s with col >= b << lb
   double* expected;   // [nb] or null
   double* coverage;   // [nb] or null
   uint8_t* bad;       // [nb] weight is NaN; null for raw counts
@@ -226,57 +253,111 @@ struct pup_region {
 namespace {
 
 // ------------------------------------------------------------------------------------------ prep kernels
-// padded row length (multiple of PIX_ALIGN pixels) -> scanned into prow[]
-constexpr int PIX_ALIGN = 4;  // pixels; 4 x 16 B = one 64-byte segment per lane-quad load, never straddling a line
-constexpr int PIX_GROUP = 8;  // sentinel padding granularity (covers lane groups of up to 8 lanes)
-__global__ void k_padded_len(const int32_t* __restrict__ indptr, int32_t* __restrict__ plen, int nb) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  // at least one complete group of sentinel pixels follows the last stored pixel of every row, so a lane that steps
-  // past the end of its row always reads a sentinel (col = INT_MAX) and the pile-up loop needs no end-of-row test
-  if (r < nb) plen[r] = ((indptr[r + 1] - indptr[r] + PIX_GROUP - 1) / PIX_GROUP + 1) * PIX_GROUP;
-  if (r == nb) plen[r] = 0;
+// padded strip length (multiple of S pixels) -> scanned into prow[]
+__global__ void k_padded_len(const int32_t* __restrict__ indptr, int32_t* __restrict__ plen, int nb, int ns, int lr,
+                             int S) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  // at least one complete group of S sentinel pixels follows the last stored pixel of every strip, so a lane that
+  // steps past the end of its strip always reads a sentinel (col = INT_MAX) and the pile-up loop needs no
+  // end-of-strip test
+  if (s < ns) {
+    const int r_lo = s << lr, r_hi = min(nb, r_lo + (1 << lr));
+    plen[s] = ((indptr[r_hi] - indptr[r_lo] + S - 1) / S + 1) * S;
+  }
+  if (s == ns) plen[s] = 0;
 }
 
-// One warp per matrix row: normalise every stored pixel once and write the 16-byte records; the row is padded with
-// sentinel pixels (col = INT_MAX, sorted last) so that every row starts on a 64-byte boundary.
+// first index in [lo, hi) of the sorted array `col` with col[idx] >= target (hi if none); the search gallops away
+// from `hint` (neighbouring matrix rows have nearly the same profile, so the answer is a few entries from the hint)
+__device__ __forceinline__ int lower_bound_hint(const int32_t* __restrict__ col, int lo, int hi, int hint, int target) {
+  int pos = min(max(hint, lo), hi);
+  int L, H;
+  if (pos < hi && __ldg(&col[pos]) < target) {
+    L = pos + 1;
+    int step = 1;
+    for (;;) {
+      H = L + step;
+      if (H >= hi) {
+        H = hi;
+        break;
+      }
+      if (__ldg(&col[H]) >= target) break;
+      L = H + 1;
+      step <<= 1;
+    }
+  } else {
+    H = pos;
+    int step = 1;
+    for (;;) {
+      L = H - step;
+      if (L <= lo) {
+        L = lo;
+        break;
+      }
+      if (__ldg(&col[L]) < target) {
+        L = L + 1;
+        break;
+      }
+      H = L;
+      step <<= 1;
+    }
+  }
+  while (L < H) {
+    const int mid = (L + H) >> 1;
+    if (__ldg(&col[mid]) < target)
+      L = mid + 1;
+    else
+      H = mid;
+  }
+  return L;
+}
+
+// One warp per strip: normalise every stored pixel once and write the 16-byte records of the strip's R rows merged
+// in (col, row) order -- the position of a pixel is its index in its own row plus, for every other row of the
+// strip, the number of that row's pixels that sort before it.  The strip is closed with sentinel pixels
+// (col = INT_MAX, sorted last) up to the next multiple of S.
 __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32_t* __restrict__ prow,
                                  const int32_t* __restrict__ col, const int32_t* __restrict__ cnt,
                                  const double* __restrict__ weight, const double* __restrict__ expected,
-                                 Pix* __restrict__ pix, int32_t* __restrict__ rowend, int nb, int ignore_diags,
-                                 unsigned flags) {
+                                 Pix* __restrict__ pix, int nb, int ns, int lr, int ignore_diags, unsigned flags) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool ooe = (flags & PUP_F_OOE) && expected != nullptr;
   const bool nodiag = flags & PUP_F_NODIAG;
-  for (int64_t r = warp; r < nb; r += nwarps) {
-    const int lo = indptr[r], hi = indptr[r + 1];
-    const int dst = prow[r], dend = prow[r + 1];
-    double wr = 1.0;
-    bool rbad = false;
-    if (weight != nullptr) {
-      wr = weight[r];
-      rbad = isnan(wr);
+  for (int64_t s = warp; s < ns; s += nwarps) {
+    const int r_lo = (int)s << lr, r_hi = min(nb, r_lo + (1 << lr));
+    const int dst = prow[s], dend = prow[s + 1];
+    const int len = indptr[r_hi] - indptr[r_lo];
+    for (int r = r_lo; r < r_hi; ++r) {
+      const int lo = indptr[r], hi = indptr[r + 1];
+      double wr = 1.0;
+      if (weight != nullptr) wr = weight[r];
+      for (int i = lo + lane; i < hi; i += 32) {
+        const int c = col[i];
+        double v = (double)cnt[i];
+        if (weight != nullptr) v = (wr * weight[c]) * v;  // cooler: bias[row] * bias[col] * count
+        const int d = c - r;
+        if (ooe) v = v / expected[d < 0 ? -d : d];
+        if (!nodiag && d < ignore_diags) v = 0.0;  // signed diagonal mask (coolpup.py:1141-1149)
+        if (v != v) v = 0.0;                       // NaN pixels (masked row / column bin, NaN expected) add nothing
+        int rank = i - lo;
+        for (int r2 = r_lo; r2 < r_hi; ++r2) {
+          if (r2 == r) continue;
+          const int lo2 = indptr[r2], hi2 = indptr[r2 + 1];
+          rank += lower_bound_hint(col, lo2, hi2, lo2 + (i - lo), c + (r2 < r ? 1 : 0)) - lo2;
+        }
+        Pix p;
+        p.col = c;
+        p.q = r - r_lo;
+        p.val = v;
+        pix[dst + rank] = p;
+      }
     }
-    if (lane == 0) rowend[r] = rbad ? dst : dst + (hi - lo);  // masked rows contribute nothing: empty run
-    for (int i = lo + lane; i < hi; i += 32) {
-      const int c = col[i];
-      double v = (double)cnt[i];
-      if (weight != nullptr) v = (wr * weight[c]) * v;  // cooler: bias[row] * bias[col] * count
-      const int d = c - (int)r;
-      if (ooe) v = v / expected[d < 0 ? -d : d];
-      if (!nodiag && d < ignore_diags) v = 0.0;  // signed diagonal mask (coolpup.py:1141-1149)
-      if (v != v) v = 0.0;                       // NaN pixels add nothing to a nansum
-      Pix p;
-      p.col = c;
-      p.pad = 0;
-      p.val = v;
-      pix[dst + (i - lo)] = p;
-    }
-    for (int k = dst + (hi - lo) + lane; k < dend; k += 32) {
+    for (int k = dst + len + lane; k < dend; k += 32) {
       Pix p;
       p.col = 0x7fffffff;
-      p.pad = 0;
+      p.q = 0;
       p.val = 0.0;
       pix[k] = p;
     }
@@ -361,30 +442,26 @@ __global__ void k_place_lower(const int32_t* __restrict__ sorted_key, const int3
   cnt_s[dst] = cnt_u[src];
 }
 
-// bucket[b * nb + r] = position in pix[] (rounded down to a 64-byte boundary inside the row) of the first pixel of
-// row r whose column is >= (b << lb)
-__global__ void k_build_buckets(const int32_t* __restrict__ col, const int32_t* __restrict__ indptr,
-                                const int32_t* __restrict__ prow, const int32_t* __restrict__ rowend,
-                                int32_t* __restrict__ bucket, int nb, int nbk, int lb) {
-  int64_t total = (int64_t)nb * nbk;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (; i < total; i += step) {
-    int r = (int)(i % nb);
-    int b = (int)(i / nb);
-    const int base = indptr[r];
-    int lo = base, hi = indptr[r + 1];
-    int target = b << lb;
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (__ldg(&col[mid]) < target)
-        lo = mid + 1;
-      else
-        hi = mid;
+// bucket[b * ns + s] = position in pix[] (rounded down to a multiple of S pixels inside the strip) of the first
+// pixel of strip s whose column is >= (b << lb).  One streaming pass over the strip-major pixels: wherever the
+// column bucket changes between neighbouring pixels, the thread of the later pixel writes the entries of all
+// buckets in between; the sentinel that closes a strip (col = INT_MAX) fills the strip's remaining buckets.
+__global__ void k_build_buckets(const Pix* __restrict__ pix, const int32_t* __restrict__ prow,
+                                int32_t* __restrict__ bucket, int ns, int nbk, int lb, int S) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp; s < ns; s += nwarps) {
+    const int lo = prow[s], hi = prow[s + 1];
+    for (int base = lo; base < hi; base += 32) {
+      const int i = base + lane;
+      if (i >= hi) break;
+      const int c = __ldg(&pix[i].col);
+      const int bc = min(c >> lb, nbk - 1);
+      const int bp = (i == lo) ? -1 : min(__ldg(&pix[i - 1].col) >> lb, nbk - 1);
+      for (int b = bp + 1; b <= bc; ++b) bucket[(int64_t)b * ns + s] = i & ~(S - 1);
+      if (c == 0x7fffffff) break;  // first sentinel reached: all buckets of this strip are written
     }
-    // masked rows (rowend == row start) contribute nothing: point them at their sentinel group
-    const int first = (rowend[r] == prow[r] && indptr[r + 1] > base) ? prow[r + 1] - PIX_GROUP : prow[r] + (lo - base);
-    bucket[i] = first & ~(PIX_ALIGN - 1);
   }
 }
 
@@ -418,15 +495,18 @@ __global__ void k_masks(const double* __restrict__ weight, const double* __restr
 }
 
 // ------------------------------------------------------------------------------------------ window keys
-// key = [invalid:1][slot][r0:pb][c0:pb]; out-of-region windows get all ones and sort last.
+// key = [invalid:1][slot][r0 mod R : lr][r0:pb][c0:pb]; out-of-region windows get all ones and sort last.
+// (slot, r0 mod R) is the "extended slot": all windows of one extended slot map matrix rows to tile rows the same
+// way (tile row = window row + r0 mod R), so the main kernel treats a change of either like a change of slot.
 __global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __restrict__ c0,
                               const int32_t* __restrict__ slot, uint64_t* __restrict__ keys, int64_t n, int nb, int W,
-                              int n_slots, int pb) {
+                              int n_slots, int pb, int lr) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int r = r0[i], c = c0[i], s = slot[i];
   bool ok = r >= 0 && c >= 0 && r + W <= nb && c + W <= nb && s >= 0 && s < n_slots;
-  keys[i] = ok ? (((uint64_t)s << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c) : ~0ull;
+  const uint64_t es = ((uint64_t)s << lr) | (uint64_t)(r & ((1 << lr) - 1));
+  keys[i] = ok ? ((es << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c) : ~0ull;
 }
 
 // sorted keys -> (r0, c0) records, so that the main kernel does no 64-bit key arithmetic
@@ -438,8 +518,8 @@ __global__ void k_decode_windows(const uint64_t* __restrict__ keys, int2* __rest
   win[i] = make_int2((int)((k >> pb) & m), (int)(k & m));
 }
 
-// slot_start[s] = first sorted window of slot s (s = n_slots: number of valid windows);
-// nchunks[s] = ceil(count / ch)
+// slot_start[s] = first sorted window of extended slot s (s = n_slots: number of valid windows);
+// nchunks[s] = ceil(count / ch).  n_slots counts EXTENDED slots here.
 __global__ void k_slot_bounds(const uint64_t* __restrict__ keys, int n, int n_slots, int pb, int ch,
                               int32_t* __restrict__ slot_start, int32_t* __restrict__ nchunks) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,16 +548,17 @@ __global__ void k_slot_bounds(const uint64_t* __restrict__ keys, int n, int n_sl
 
 // ------------------------------------------------------------------------------------------ shared device helpers
 struct WinCtx {
-  int nb, W, pb, ignore_diags;
+  int nb, W, pb, lr, ignore_diags;
   unsigned flags;
   const int32_t* ebadpre;
 };
 
-__device__ __forceinline__ void decode_key(uint64_t k, int pb, int& slot, int& r0, int& c0) {
-  uint64_t m = (1ull << pb) - 1;
+// sorted key -> accumulator slot (the r0 mod R bits of the extended slot are dropped), r0, c0
+__device__ __forceinline__ void decode_key(uint64_t k, const WinCtx& c, int& slot, int& r0, int& c0) {
+  uint64_t m = (1ull << c.pb) - 1;
   c0 = (int)(k & m);
-  r0 = (int)((k >> pb) & m);
-  slot = (int)(k >> (2 * pb));
+  r0 = (int)((k >> c.pb) & m);
+  slot = (int)(k >> (2 * c.pb + c.lr));
 }
 
 // A window is "slow" when some pixel is masked by the signed diagonal rule or by a NaN/zero expected value:
@@ -505,11 +586,11 @@ __device__ __forceinline__ bool window_is_slow(const WinCtx& c, int r0, int c0) 
   return false;
 }
 
-// work item -> (slot, window range) through the per-slot chunk table
+// work item -> (extended slot, window range) through the per-extended-slot chunk table
 struct ChunkTable {
   const int32_t* slot_start;   // [n_slots+1]
-  const int32_t* chunk_start;  // [n_slots+1] exclusive scan of chunks per slot
-  int n_slots;
+  const int32_t* chunk_start;  // [n_slots+1] exclusive scan of chunks per extended slot
+  int n_slots;                 // number of EXTENDED slots (accumulator slots << lr)
   int ch;  // windows per chunk
 };
 
@@ -536,8 +617,9 @@ __device__ __forceinline__ void locate_chunk(const ChunkTable& t, int chunk, int
 struct CountParams {
   WinCtx ctx;
   const uint64_t* keys;
-  const int32_t* slot_start;  // [n_slots+1]
-  int n_slots;
+  const int32_t* slot_start;  // [n_eslots+1]
+  int n_slots;                // accumulator slots
+  int n_eslots;               // extended slots = n_slots << lr
   const int32_t* badpre;     // [nb+1] exclusive prefix count of masked bins; null for raw counts
   const int32_t* badlist;    // sorted masked bins
   int* counts;               // [copies][n_slots][cstride]
@@ -548,14 +630,14 @@ struct CountParams {
 __device__ __forceinline__ int64_t count_stride(int W) { return (int64_t)W * W + 2 * W + 2; }
 
 __global__ void __launch_bounds__(256) k_window_counts(const CountParams p) {
-  const int n = __ldg(&p.slot_start[p.n_slots]);
+  const int n = __ldg(&p.slot_start[p.n_eslots]);
   const int W = p.ctx.W;
   const int64_t cs = count_stride(W);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   bool slow = false;
   if (i < n) {
     int slot, r0, c0;
-    decode_key(__ldg(&p.keys[i]), p.ctx.pb, slot, r0, c0);
+    decode_key(__ldg(&p.keys[i]), p.ctx, slot, r0, c0);
     slow = window_is_slow(p.ctx, r0, c0);
     int* base = p.counts + ((int64_t)(blockIdx.x % p.copies) * p.n_slots + slot) * cs;
     if (slow) {
@@ -577,7 +659,7 @@ __global__ void __launch_bounds__(256) k_window_counts(const CountParams p) {
 }
 
 // acc += private copies; n comes from the slot boundaries, n_fast = n - n_slow
-__global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int n_slots, int W,
+__global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int n_slots, int W, int lr,
                                 const int32_t* __restrict__ slot_start, double* __restrict__ acc) {
   const AccLayout L(W);
   const int64_t cs = count_stride(W);
@@ -594,7 +676,7 @@ __global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int 
     } else if (j < L.w2 + 2 * W) {
       if (sum) atomicAdd(a + L.off_cb + (j - L.w2 - W), (double)sum);
     } else if (j == L.w2 + 2 * W) {
-      const int nwin = slot_start[s + 1] - slot_start[s];
+      const int nwin = slot_start[(s + 1) << lr] - slot_start[s << lr];  // over the slot's extended slots
       if (nwin) {
         atomicAdd(a + L.off_n, (double)nwin);
         atomicAdd(a + L.off_nfast, (double)(nwin - sum));
@@ -610,15 +692,15 @@ __global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int 
 struct VecParams {
   WinCtx ctx;
   const uint64_t* keys;
-  const int32_t* slot_start;  // [n_slots+1]
-  int n_slots;
+  const int32_t* slot_start;  // [n_eslots+1]
+  int n_eslots;
   const double* expected;    // for EXPCTRL
   const double* coverage;    // for COVERAGE
   double* acc;
 };
 
 __global__ void k_vector(const VecParams p) {
-  const int n = __ldg(&p.slot_start[p.n_slots]);
+  const int n = __ldg(&p.slot_start[p.n_eslots]);
   const int W = p.ctx.W;
   const AccLayout L(W);
   const int t = threadIdx.x;
@@ -651,7 +733,7 @@ __global__ void k_vector(const VecParams p) {
         ev[u] = 0.0;
         if (w + u < end) {
           int r0, c0;
-          decode_key(__ldg(&p.keys[w + u]), p.ctx.pb, slot[u], r0, c0);
+          decode_key(__ldg(&p.keys[w + u]), p.ctx, slot[u], r0, c0);
           if (cov && t < W) {
             ca[u] = __ldg(&p.coverage[r0 + t]);
             cbv[u] = __ldg(&p.coverage[c0 + t]);
@@ -685,12 +767,13 @@ __global__ void k_vector(const VecParams p) {
 
 // ------------------------------------------------------------------------------------------ main kernel
 struct MainParams {
-  int W, nb, lb;
+  int W, ns, lb;
   const Pix* pix;
   const int32_t* bucket;
   const int2* win;  // sorted (r0, c0)
-  ChunkTable chunks;
-  int Wb;       // tile rows per band (<= row-groups per CTA)
+  ChunkTable chunks;  // over extended slots
+  int Gb;        // lane groups (= strips of a window) per band
+  int n_groups;  // strips a window can touch: ceil((W + R - 1) / R)
   int n_bands;
   double* acc;
 };
@@ -702,45 +785,59 @@ __device__ __forceinline__ double lds_f64(unsigned a) {
 }
 __device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 
-// S lanes share one tile row; every row-group owns exactly one row of the band, so the shared-memory
-// read-modify-write needs no atomics and -- because a row-group also flushes and clears its own row -- the
-// kernel has no CTA-wide barrier at all: warps drift freely through the CTA's (static, round-robin) chunk list.
-// WU windows advance in lockstep per row-group (two register sets, ping-pong), so WU independent 16-byte loads
-// are in flight per lane while the previous S pixels of every window are added to the tile.
-template <int S, int WU, int MINB, int PF = 0>
-__global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p) {
+// A lane group (S lanes) owns R consecutive rows of the shared-memory tile: group G of a window works on matrix
+// strip (r0 / R) + G and adds pixel (q, col) to tile row G * R + q.  Tile row t holds window row di = t - (r0 mod R);
+// r0 mod R is constant inside an extended slot, so groups never write another group's rows, the read-modify-write
+// `tile[t][col - c0] += val` needs no atomics, and -- because a group also flushes (`red.global.add.f64`) and
+// clears its own rows when the extended slot changes -- the kernel has no CTA-wide barrier at all: warps drift
+// freely through the CTA's (static, round-robin) chunk list.  Tile rows whose di falls outside [0, W) (the part of
+// the first / last strip above / below the window) collect pixels that are simply never flushed.
+// WU windows advance in lockstep per group (two register sets, ping-pong), so WU independent 16-byte loads are in
+// flight per lane while the previous S pixels of every window are added to the tile.  A group's load covers
+// S * 16 contiguous, aligned bytes: with S >= 8 every warp-wide load touches 4 full 128-byte lines.
+template <int R, int S, int WU, int PF>
+__global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int LR = (R == 1) ? 0 : (R == 2) ? 1 : (R == 4) ? 2 : 3;
   const int W = p.W;
-  const int Wb = p.Wb;
   const AccLayout L(W);
   const int lane = threadIdx.x & 31;
   const int sub = lane / S;
   const int ls = lane % S;
-  const int g = (threadIdx.x >> 5) * (32 / S) + sub;  // row-group id == tile row owned
+  const int g = (threadIdx.x >> 5) * (32 / S) + sub;  // group id inside the band
   const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
-  const int nb = p.nb;
-  if (g >= Wb) return;  // no barriers below: idle row-groups may leave
+  const int ns = p.ns;
+  if (g >= p.Gb) return;  // no barriers below: idle groups may leave
 
-  unsigned trow = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(g * W) * 8u;  // my tile row
+  unsigned trow = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(g * R * W) * 8u;  // my R tile rows
   asm volatile("mov.u32 %0, %0;" : "+r"(trow));  // keep the address in a register (no rematerialisation)
-  for (int dj = ls; dj < W; dj += S) sts_f64(trow + dj * 8, 0.0);
+  for (int i = ls; i < R * W; i += S) sts_f64(trow + i * 8, 0.0);
   __syncwarp(gmask);
-  int cur_slot = -1, cur_band = 0;
+  int cur_slot = -1, cur_band = 0;  // extended slot
   const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
   const int total_items = total_chunks * p.n_bands;
 
-  auto flush_row = [&]() {
-    // this row-group's tile row -> global accumulator (red.global.add.f64), then clear it
+  auto flush_rows = [&]() {
+    // this group's tile rows -> global accumulator (red.global.add.f64), then clear them
     __syncwarp(gmask);
-    const int di = cur_band * Wb + g;
-    if (di < W) {
-      double* a = p.acc + (int64_t)cur_slot * L.stride + (int64_t)di * W;
-      for (int dj = ls; dj < W; dj += S) {
-        const double v = lds_f64(trow + dj * 8);
-        if (v != 0.0) {
-          atomicAdd(a + dj, v);
-          sts_f64(trow + dj * 8, 0.0);
+    const int m = cur_slot & (R - 1);
+    const int t0 = (cur_band * p.Gb + g) * R;
+    double* abase = p.acc + (int64_t)(cur_slot >> LR) * L.stride;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const int di = t0 + q - m;
+      const unsigned row = trow + (unsigned)(q * W) * 8u;
+      if ((unsigned)di < (unsigned)W) {
+        double* a = abase + (int64_t)di * W;
+        for (int dj = ls; dj < W; dj += S) {
+          const double v = lds_f64(row + dj * 8);
+          if (v != 0.0) {
+            atomicAdd(a + dj, v);
+            sts_f64(row + dj * 8, 0.0);
+          }
         }
+      } else {
+        for (int dj = ls; dj < W; dj += S) sts_f64(row + dj * 8, 0.0);
       }
     }
     __syncwarp(gmask);
@@ -751,26 +848,28 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
     int slot, w_lo, w_hi;
     locate_chunk(p.chunks, item - band * total_chunks, slot, w_lo, w_hi);
     if (slot != cur_slot || band != cur_band) {
-      if (cur_slot >= 0) flush_row();
+      if (cur_slot >= 0) flush_rows();
       cur_slot = slot;
       cur_band = band;
     }
-    const int di = band * Wb + g;
-    if (di >= W) continue;
+    const int G = band * p.Gb + g;  // my strip of every window of this chunk
+    if (G >= p.n_groups || G * R - (slot & (R - 1)) >= W) continue;  // strip entirely below the window
 
     for (int w = w_lo; w < w_hi; w += WU) {
       int idx[WU], c0s[WU];
       int djA[WU], djB[WU];
+      int qA[R > 1 ? WU : 1], qB[R > 1 ? WU : 1];
       double vA[WU], vB[WU];
-      // stage A: window records -> row pointers (WU independent chains)
+      // stage A: window records -> strip pointers (WU independent chains)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
         idx[u] = -1;
         c0s[u] = 0;
         vB[u] = 0.0;
+        if (R > 1) qA[u] = qB[u] = 0;
         if (w + u < w_hi) {
           const int2 rc = __ldg(&p.win[w + u]);
-          idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * nb + rc.x + di]) + ls;
+          idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * ns + (rc.x >> LR) + G]) + ls;
           c0s[u] = rc.y;
         }
       }
@@ -782,12 +881,13 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
         if (idx[u] >= 0) {
           const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
           djA[u] = raw.x - c0s[u];
+          if (R > 1) qA[u] = raw.y * W;
           vA[u] = __hiloint2double(raw.w, raw.z);
         }
       }
-      // stage C: the WU runs advance in lockstep, S pixels per run per half-step.  Rows end with a full group of
+      // stage C: the WU runs advance in lockstep, S pixels per run per half-step.  Strips end with a full group of
       // sentinel pixels (col = INT_MAX), so "dj >= W" is the only termination test.
-#define PUP_HALF_STEP(CD, CV, ND, NV)                                                        \
+#define PUP_HALF_STEP(CD, CQ, CV, ND, NQ, NV)                                                \
   {                                                                                          \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
       ND[u] = 0x7fffffff;                                                                    \
@@ -795,6 +895,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
       if (CD[u] < W) {                                                                       \
         const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));               \
         ND[u] = raw.x - c0s[u];                                                              \
+        if (R > 1) NQ[u] = raw.y * W;                                                        \
         NV[u] = __hiloint2double(raw.w, raw.z);                                              \
         if (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pix + idx[u] + S));     \
         if (PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pix + idx[u] + 2 * S)); \
@@ -802,7 +903,7 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
     }                                                                                        \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
       if ((unsigned)CD[u] < (unsigned)W) {                                                   \
-        const unsigned a = trow + (unsigned)CD[u] * 8u;                                      \
+        const unsigned a = trow + (unsigned)(CD[u] + (R > 1 ? CQ[u] : 0)) * 8u;              \
         sts_f64(a, lds_f64(a) + CV[u]);                                                      \
       }                                                                                      \
     }                                                                                        \
@@ -810,24 +911,24 @@ __global__ void __launch_bounds__(NT_MAX, MINB) k_pileup_main(const MainParams p
       // Lanes leave the loop individually once their WU runs are exhausted and wait at the __syncwarp below; the
       // lanes still inside execute the same predicated instruction stream, so the read-modify-writes of one tile
       // row are ordered by the program order of a converged SIMT group (racecheck reports them as intra-warp
-      // hazards "without barrier"; a quad-voted exit was measured 6 % slower and changes nothing about ordering).
+      // hazards "without barrier"; a group-voted exit was measured 6 % slower and changes nothing about ordering).
       for (;;) {
         int mn = djA[0];
 #pragma unroll
         for (int u = 1; u < WU; ++u) mn = min(mn, djA[u]);
         if (mn >= W) break;
-        PUP_HALF_STEP(djA, vA, djB, vB)
+        PUP_HALF_STEP(djA, qA, vA, djB, qB, vB)
         mn = djB[0];
 #pragma unroll
         for (int u = 1; u < WU; ++u) mn = min(mn, djB[u]);
         if (mn >= W) break;
-        PUP_HALF_STEP(djB, vB, djA, vA)
+        PUP_HALF_STEP(djB, qB, vB, djA, qA, vA)
       }
 #undef PUP_HALF_STEP
       __syncwarp(gmask);
     }
   }
-  if (cur_slot >= 0) flush_row();
+  if (cur_slot >= 0) flush_rows();
 }
 
 // ------------------------------------------------------------------------------------------ dense-num kernel
@@ -859,7 +960,7 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
   int cur_slot = -1;
   const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
   auto flush = [&]() {
-    double* a = p.acc + (int64_t)cur_slot * L.stride + L.off_num;
+    double* a = p.acc + (int64_t)cur_slot * L.stride + L.off_num;  // cur_slot: accumulator slot
     for (int i = threadIdx.x; i < w2; i += blockDim.x) {
       int c = numT[i];
       if (c != 0) {
@@ -877,7 +978,7 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
       } else {
         int slot, lo, hi;
         locate_chunk(p.chunks, item, slot, lo, hi);
-        s_slot = slot;
+        s_slot = slot >> p.ctx.lr;  // extended slot -> accumulator slot
         s_lo = lo;
         s_hi = hi;
       }
@@ -894,7 +995,7 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
     }
     for (int w = s_lo; w < s_hi; ++w) {
       int kslot, r0, c0;
-      decode_key(__ldg(&p.keys[w]), p.ctx.pb, kslot, r0, c0);
+      decode_key(__ldg(&p.keys[w]), p.ctx, kslot, r0, c0);
       if (!window_is_slow(p.ctx, r0, c0)) continue;
       for (int cell = threadIdx.x; cell < w2; cell += blockDim.x) {
         const int di = cell / W, dj = cell - di * W;
@@ -917,10 +1018,10 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
 // One warp per window; every lane looks its pixel up by binary search in the (unnormalised-NaN-aware) row.
 struct StripeParams {
   const Pix* pix;
-  const int32_t* indptr;
+  const int32_t* prow;      // strip starts
   const uint8_t* bad;       // null for raw
   const double* expected;   // null unless the region was prepared with PUP_F_OOE
-  int nb, W, ignore_diags;
+  int nb, W, ignore_diags, lr;
   unsigned flags;
 };
 
@@ -929,15 +1030,21 @@ __device__ __forceinline__ double snippet_pixel(const StripeParams& p, int r, in
   if (p.bad != nullptr && (p.bad[r] || p.bad[c])) return nan;
   const int d = c - r;
   if (!(p.flags & PUP_F_NODIAG) && d < p.ignore_diags) return nan;
-  int lo = p.indptr[r], hi = p.indptr[r + 1];
+  const int s = r >> p.lr, q = r & ((1 << p.lr) - 1);
+  int lo = p.prow[s], hi = p.prow[s + 1];  // (col, q)-sorted, closed by sentinels
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (__ldg(&p.pix[mid].col) < c)
+    const int2 k = __ldg(reinterpret_cast<const int2*>(p.pix + mid));
+    if (k.x < c || (k.x == c && k.y < q))
       lo = mid + 1;
     else
       hi = mid;
   }
-  const bool stored = lo < p.indptr[r + 1] && p.pix[lo].col == c;
+  bool stored = false;
+  if (lo < p.prow[s + 1]) {
+    const int2 k = __ldg(reinterpret_cast<const int2*>(p.pix + lo));
+    stored = k.x == c && k.y == q;
+  }
   const double v = stored ? p.pix[lo].val : 0.0;
   if ((p.flags & PUP_F_OOE) && p.expected != nullptr) {
     const double e = p.expected[d < 0 ? -d : d];
@@ -964,19 +1071,22 @@ __global__ void k_stripes(const StripeParams p, const int32_t* __restrict__ r0, 
 
 // ------------------------------------------------------------------------------------------ byte counter
 // Exact algorithmic pixel count of a window list (measurement helper, not on the timed path).
-__global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restrict__ indptr,
+__global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restrict__ prow,
                             const int32_t* __restrict__ r0, const int32_t* __restrict__ c0, int64_t n, int nb, int W,
-                            unsigned long long* out_nnz, unsigned long long* out_valid) {
+                            int lr, unsigned long long* out_nnz, unsigned long long* out_valid) {
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int R = 1 << lr;
   unsigned long long local = 0, valid = 0;
   for (int64_t i = warp; i < n; i += nwarps) {
     int r = r0[i], c = c0[i];
     if (r < 0 || c < 0 || r + W > nb || c + W > nb) continue;
     if (lane == 0) valid += 1;
-    for (int di = lane; di < W; di += 32) {
-      int lo = indptr[r + di], hi = indptr[r + di + 1];
+    const int ng = ((r & (R - 1)) + W + R - 1) >> lr;  // strips the window touches
+    for (int G = lane; G < ng; G += 32) {
+      const int s = (r >> lr) + G;
+      const int lo = prow[s], hi = prow[s + 1];
       auto lower = [&](int target) {
         int a = lo, b = hi;
         while (a < b) {
@@ -988,7 +1098,15 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
         }
         return a;
       };
-      local += (unsigned long long)(lower(c + W) - lower(c));
+      const int a = lower(c), b = lower(c + W);
+      if ((s << lr) >= r && (s << lr) + R <= r + W) {
+        local += (unsigned long long)(b - a);
+      } else {  // first / last strip: only the rows inside the window count
+        for (int k = a; k < b; ++k) {
+          const int row = (s << lr) + __ldg(&pix[k].q);
+          local += (row >= r && row < r + W) ? 1 : 0;
+        }
+      }
     }
   }
   for (int o = 16; o; o >>= 1) {
@@ -1002,41 +1120,39 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
 }
 
 // occ != nullptr: only query the occupancy; else launch
-cudaError_t launch_main(int S, int wu, int minb, const MainParams& p, int grid, int threads, size_t smem,
-                        cudaStream_t st, int* occ) {
-#define PUP_LAUNCH(SV, WV, MB)                                                                            \
-  do {                                                                                                    \
-    auto kern = k_pileup_main<SV, WV, MB>;                                                                \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return e;                                                                       \
-    if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);              \
-    kern<<<grid, threads, smem, st>>>(p);                                                                 \
-    return cudaGetLastError();                                                                            \
-  } while (0)
-  (void)minb;
-  if (S == 8) PUP_LAUNCH(8, 4, 2);
-  if (wu == 2) PUP_LAUNCH(4, 2, 3);
-  {
-    const int pf = env_int("PUP_PREFETCH", 2);
-    if (pf == 1) {
-      auto kern = k_pileup_main<4, 4, 2, 1>;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
-      kern<<<grid, threads, smem, st>>>(p);
-      return cudaGetLastError();
-    }
-    if (pf == 2) {
-      auto kern = k_pileup_main<4, 4, 2, 2>;
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
-      kern<<<grid, threads, smem, st>>>(p);
-      return cudaGetLastError();
-    }
-  }
-  PUP_LAUNCH(4, 4, 2);
-#undef PUP_LAUNCH
+template <int R, int S>
+cudaError_t launch_main_rs(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = k_pileup_main<R, S, 4, 2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
+  kern<<<grid, threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_main(int R, int S, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
+                        int* occ) {
+  if (R == 1 && S == 4) return launch_main_rs<1, 4>(p, grid, threads, smem, st, occ);
+  if (R == 1 && S == 8) return launch_main_rs<1, 8>(p, grid, threads, smem, st, occ);
+  if (R == 2 && S == 8) return launch_main_rs<2, 8>(p, grid, threads, smem, st, occ);
+  if (R == 2 && S == 16) return launch_main_rs<2, 16>(p, grid, threads, smem, st, occ);
+  if (R == 4 && S == 8) return launch_main_rs<4, 8>(p, grid, threads, smem, st, occ);
+  if (R == 4 && S == 16) return launch_main_rs<4, 16>(p, grid, threads, smem, st, occ);
+  if (R == 8 && S == 16) return launch_main_rs<8, 16>(p, grid, threads, smem, st, occ);
+  if (R == 8 && S == 32) return launch_main_rs<8, 32>(p, grid, threads, smem, st, occ);
+  return cudaErrorInvalidValue;
+}
+
+// strip geometry of a new region: R rows per strip, S lanes per strip run (PUP_STRIP / PUP_LANES override)
+void choose_strip(int* R_out, int* S_out) {
+  int R = env_int("PUP_STRIP", 2);
+  if (R != 1 && R != 2 && R != 4 && R != 8) R = 2;
+  int S = env_int("PUP_LANES", R == 1 ? 4 : R == 2 ? 8 : R == 4 ? 16 : 32);
+  const bool ok = (R == 1 && (S == 4 || S == 8)) || (R == 2 && (S == 8 || S == 16)) ||
+                  (R == 4 && (S == 8 || S == 16)) || (R == 8 && (S == 16 || S == 32));
+  if (!ok) S = R == 1 ? 4 : R == 2 ? 8 : R == 4 ? 16 : 32;
+  *R_out = R;
+  *S_out = S;
 }
 
 }  // namespace
@@ -1106,51 +1222,58 @@ int64_t pup_region_device_bytes(const pup_region_t* r) { return r ? r->bytes : 0
 
 namespace {
 
-int choose_bucket_bits(int32_t nb, int64_t nnz, int* nbk_out) {
-  // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (row, bucket); no table for very sparse rows
-  double avg = (double)nnz / nb;
+int choose_bucket_bits(int32_t nb, int32_t ns, int R, int64_t nnz, int* nbk_out) {
+  // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (strip, bucket); no table for very sparse rows
+  double avg = (double)nnz / nb;  // pixels per row; a strip holds R times as many per column
   int target = env_int("PUP_BUCKET_TARGET", 4);
   if (avg <= 24.0) {
     *nbk_out = 1;
     return 31;
   }
-  int lb = (int)floor(log2((double)target * nb / avg));
-  if (lb < 3) lb = 3;
-  while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb * 4 > (int64_t)4 * nnz + (64 << 20) ||  // <= 25% of pixels
-         ((int64_t)((nb + (1 << lb) - 1) >> lb)) * nb >= (1ll << 31))                           // 32-bit index
+  int lb = (int)floor(log2((double)target * nb / (avg * R)));
+  if (lb < 2) lb = 2;
+  while (((int64_t)((nb + (1 << lb) - 1) >> lb)) * ns * 4 > (int64_t)4 * nnz + (64 << 20) ||  // <= 25% of pixels
+         ((int64_t)((nb + (1 << lb) - 1) >> lb)) * ns >= (1ll << 31))                           // 32-bit index
     ++lb;
   *nbk_out = (nb + (1 << lb) - 1) >> lb;
   return lb;
 }
 
-// Everything after the symmetric CSR (indptr in r->indptr, DEVICE col/count) is known: normalise pixels, build the
-// bucket table and the masks.  `weight` may be host or device.
+// Everything after the symmetric CSR (indptr in r->indptr, DEVICE col/count) is known: normalise pixels into the
+// strip layout, build the bucket table and the masks.  `weight` may be host or device.
 int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const double* weight, Scratch& tmp) {
   // `weight` is DEVICE memory here (staged by the caller)
   cudaStream_t st = r->stream;
   const int32_t nb = r->nb;
   const int64_t nnz = r->nnz;
-  r->lb = choose_bucket_bits(nb, nnz, &r->nbk);
-  size_t n_ent = (size_t)nnz + (size_t)(2 * PIX_GROUP) * nb + PIX_GROUP;  // rows padded with sentinel groups
+  choose_strip(&r->R, &r->S);
+  r->lr = ilog2_ceil(r->R);
+  r->ns = (nb + r->R - 1) >> r->lr;
+  const int32_t ns = r->ns;
+  const int S = r->S;
+  r->lb = choose_bucket_bits(nb, ns, r->R, nnz, &r->nbk);
+  // strips padded with sentinel groups (+ slack for the main kernel's L2 prefetch two groups ahead)
+  size_t n_ent = (size_t)nnz + (size_t)(2 * S) * ns + 4 * S;
+  if (n_ent >= (1ull << 31)) return fail(PUP_E_ARG, "region create: padded pixel table exceeds 2^31 entries");
   CK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
-  CK(cudaMallocAsync((void**)&r->prow, (size_t)(nb + 1) * 4, st));
-  CK(cudaMallocAsync((void**)&r->rowend, (size_t)nb * 4, st));
+  CK(cudaMallocAsync((void**)&r->prow, (size_t)(ns + 1) * 4, st));
   {
     int32_t* plen;
-    CK(tmp.alloc((void**)&plen, (size_t)(nb + 1) * 4));
-    k_padded_len<<<(nb + 1 + 255) / 256, 256, 0, st>>>(r->indptr, plen, nb);
+    CK(tmp.alloc((void**)&plen, (size_t)(ns + 1) * 4));
+    k_padded_len<<<(ns + 1 + 255) / 256, 256, 0, st>>>(r->indptr, plen, nb, ns, r->lr, S);
     LAUNCH_CHECK("k_padded_len");
     size_t tb = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, plen, r->prow, nb + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, plen, r->prow, ns + 1, st));
     void* t;
     CK(tmp.alloc(&t, tb));
-    CK(cub::DeviceScan::ExclusiveSum(t, tb, plen, r->prow, nb + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, plen, r->prow, ns + 1, st));
     ++g_launches;
   }
-  CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * nb * 4, st));
+  CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * ns * 4, st));
   CK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
   CK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
-  r->bytes += (int64_t)(n_ent * sizeof(Pix) + (size_t)(nb + 1) * 12 + (size_t)r->nbk * nb * 4 + (size_t)nb);
+  r->bytes += (int64_t)(n_ent * sizeof(Pix) + (size_t)(ns + 1) * 4 + (size_t)(nb + 1) * 8 + (size_t)r->nbk * ns * 4 +
+                        (size_t)nb);
   const double* dw = weight;
   if (weight) {
     CK(cudaMallocAsync((void**)&r->bad, (size_t)nb, st));
@@ -1159,15 +1282,14 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
     r->bytes += (int64_t)nb * 9 + 4;
   }
   {
-    int grid = std::min((nb + 7) / 8, 148 * 16);
-    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, r->prow, dcol, dcnt, dw, r->expected, r->pix, r->rowend, nb,
+    int grid = std::min((ns + 7) / 8, 148 * 16);
+    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, r->prow, dcol, dcnt, dw, r->expected, r->pix, nb, ns, r->lr,
                                            r->ignore_diags, r->flags);
     LAUNCH_CHECK("k_prepare_pixels");
   }
   {
-    int64_t total = (int64_t)nb * r->nbk;
-    int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 64);
-    k_build_buckets<<<grid, 256, 0, st>>>(dcol, r->indptr, r->prow, r->rowend, r->bucket, nb, r->nbk, r->lb);
+    int grid = std::min((ns + 7) / 8, 148 * 16);
+    k_build_buckets<<<grid, 256, 0, st>>>(r->pix, r->prow, r->bucket, ns, r->nbk, r->lb, S);
     LAUNCH_CHECK("k_build_buckets");
   }
   {
@@ -1203,15 +1325,34 @@ int new_region(int device, int32_t nb, const double* expected, const double* cov
   r->flags = flags;
   *out = r;
   CK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
-  if (expected) {
-    CK(cudaMallocAsync((void**)&r->expected, (size_t)nb * 8, st));
-    CK(cudaMemcpyAsync(r->expected, expected, (size_t)nb * 8, cudaMemcpyDefault, st));
+  // host vectors go through the internal copy stream like the matrix arrays (FIFO with them), not through the
+  // caller's stream, where a small copy could wait behind uploads that other calls queued on the copy engine
+  auto put = [&](double** dst, const double* src) -> int {
+    CK(cudaMallocAsync((void**)dst, (size_t)nb * 8, st));
     r->bytes += (int64_t)nb * 8;
+    cudaStream_t cs = is_device_ptr(src) ? st : copy_stream(device);
+    if (!cs || cs == st) {
+      CK(cudaMemcpyAsync(*dst, src, (size_t)nb * 8, cudaMemcpyDefault, st));
+      return PUP_OK;
+    }
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ev, st);  // the allocation is ordered on st
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, src, (size_t)nb * 8, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return fail(PUP_E_CUDA, "region create: vector upload", e);
+    return PUP_OK;
+  };
+  if (expected) {
+    int rc = put(&r->expected, expected);
+    if (rc != PUP_OK) return rc;
   }
   if (coverage) {
-    CK(cudaMallocAsync((void**)&r->coverage, (size_t)nb * 8, st));
-    CK(cudaMemcpyAsync(r->coverage, coverage, (size_t)nb * 8, cudaMemcpyDefault, st));
-    r->bytes += (int64_t)nb * 8;
+    int rc = put(&r->coverage, coverage);
+    if (rc != PUP_OK) return rc;
   }
   return PUP_OK;
 }
@@ -1361,8 +1502,8 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
     CK(tmp.alloc((void**)&val_a, nu * 4));
     CK(tmp.alloc((void**)&val_b, nu * 4));
     CK(tmp.alloc((void**)&row_of, nu * 4));
-    CK(cudaMemsetAsync(lo_cnt, 0, (size_t)(nb + 1) * 4, st));
-    CK(cudaMemsetAsync(up_cnt, 0, (size_t)(nb + 1) * 4, st));
+    CK(zero_async(lo_cnt, (size_t)(nb + 1) * 4, st));
+    CK(zero_async(up_cnt, (size_t)(nb + 1) * 4, st));
     const int wgrid = std::min((nb + 7) / 8, 148 * 16);
     k_upper_counts<<<wgrid, 256, 0, st>>>(d_ip, d_col, nb, up_cnt, lo_cnt, key_a, val_a);
     LAUNCH_CHECK("k_upper_counts");
@@ -1412,12 +1553,34 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
   return PUP_OK;
 }
 
+int pup_upload(int device, void* dst, const void* src, int64_t bytes, void* stream) {
+  if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(PUP_E_ARG, "pup_upload: bad arguments");
+  if (bytes == 0) return PUP_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_upload: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t cs = copy_stream(device);
+  if (!cs) cs = st;
+  cudaEvent_t ev;
+  CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  // the upload stream never waits for the caller's stream (that would hold back every upload queued behind this
+  // one): dst must not be in use by work that is still pending when this is called
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess && cs != st) {
+    e = cudaEventRecord(ev, cs);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+  }
+  cudaEventDestroy(ev);
+  if (e != cudaSuccess) return fail(PUP_E_CUDA, "pup_upload", e);
+  return PUP_OK;
+}
+
 int pup_region_destroy(pup_region_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
-  void* ptrs[] = {r->pix,      r->indptr, r->prow,   r->rowend,  r->bucket,   r->expected, r->coverage,
-                  r->bad,      r->ebad,   r->ebadpre, r->badpre, r->badlist};
+  void* ptrs[] = {r->pix, r->indptr, r->prow,    r->bucket, r->expected, r->coverage,
+                  r->bad, r->ebad,   r->ebadpre, r->badpre, r->badlist};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
   delete r;
@@ -1443,8 +1606,11 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   if ((flags & PUP_F_COVERAGE) && !m->coverage)
     return fail(PUP_E_ARG, "pup_accumulate: coverage requested but the region has none");
   const int pb = ilog2_ceil((int64_t)m->nb + 1);
-  const int sb = ilog2_ceil((int64_t)n_slots + 1);
-  if (2 * pb + sb > 62) return fail(PUP_E_ARG, "pup_accumulate: too many slots for this region size");
+  const int lr = m->lr;
+  const int n_eslots = n_slots << lr;  // extended slots: (slot, r0 mod R)
+  const int sb = ilog2_ceil((int64_t)n_eslots + 1);
+  if (2 * pb + sb > 62 || (int64_t)n_slots << lr >= (1ll << 30))
+    return fail(PUP_E_ARG, "pup_accumulate: too many slots for this region size");
   DeviceGuard guard(m->device);
   if (!guard.ok) return fail(PUP_E_NODEV, "pup_accumulate: cudaSetDevice failed");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1477,7 +1643,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   if (host_acc && async) return fail(PUP_E_ARG, "pup_accumulate: PUP_F_ASYNC needs a device accumulator");
   if (host_acc) {
     CK(tmp.alloc((void**)&d_acc, (size_t)acc_len * 8));
-    CK(cudaMemsetAsync(d_acc, 0, (size_t)acc_len * 8, st));
+    CK(zero_async(d_acc, (size_t)acc_len * 8, st));
   }
 
   int n_sm = 148;
@@ -1494,7 +1660,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
     CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
     k_window_keys<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(d_r0, d_c0, d_slot, keys_a, n_win, m->nb, W,
-                                                                    n_slots, pb);
+                                                                    n_slots, pb, lr);
     LAUNCH_CHECK("k_window_keys");
     cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
     size_t tb = 0;
@@ -1511,22 +1677,23 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     k_decode_windows<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(keys, win, n_win, pb);
     LAUNCH_CHECK("k_decode_windows");
 
-    CK(tmp.alloc((void**)&slot_start, (size_t)(n_slots + 1) * 4));
-    CK(tmp.alloc((void**)&nchunks, (size_t)(n_slots + 1) * 4));
-    CK(tmp.alloc((void**)&chunk_start, (size_t)(n_slots + 1) * 4));
+    CK(tmp.alloc((void**)&slot_start, (size_t)(n_eslots + 1) * 4));
+    CK(tmp.alloc((void**)&nchunks, (size_t)(n_eslots + 1) * 4));
+    CK(tmp.alloc((void**)&chunk_start, (size_t)(n_eslots + 1) * 4));
     CK(tmp.alloc((void**)&counters, 16));
-    CK(cudaMemsetAsync(counters, 0, 16, st));
-    k_slot_bounds<<<(n_slots + 1 + 127) / 128, 128, 0, st>>>(keys, (int)n_win, n_slots, pb, ch, slot_start, nchunks);
+    CK(zero_async(counters, 16, st));
+    k_slot_bounds<<<(n_eslots + 1 + 127) / 128, 128, 0, st>>>(keys, (int)n_win, n_eslots, pb, ch, slot_start,
+                                                               nchunks);
     LAUNCH_CHECK("k_slot_bounds");
     size_t tb2 = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, nchunks, chunk_start, n_slots + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb2, nchunks, chunk_start, n_eslots + 1, st));
     void* t2;
     CK(tmp.alloc(&t2, tb2));
-    CK(cub::DeviceScan::ExclusiveSum(t2, tb2, nchunks, chunk_start, n_slots + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(t2, tb2, nchunks, chunk_start, n_eslots + 1, st));
     ++g_launches;
   }
-  WinCtx ctx{m->nb, W, pb, m->ignore_diags, all_flags, m->ebadpre};
-  ChunkTable chunks{slot_start, chunk_start, n_slots, ch};
+  WinCtx ctx{m->nb, W, pb, lr, m->ignore_diags, all_flags, m->ebadpre};
+  ChunkTable chunks{slot_start, chunk_start, n_eslots, ch};
 
   // 2. per-window counts (n, n_fast, masked rows / columns) and, on request, the O(W) fp64 vectors
   {
@@ -1536,15 +1703,15 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     const int copies = (int)std::max<int64_t>(1, std::min<int64_t>(64, (64ll << 20) / (one * 4)));
     int* counts;
     CK(tmp.alloc((void**)&counts, (size_t)(one * copies) * 4));
-    CK(cudaMemsetAsync(counts, 0, (size_t)(one * copies) * 4, st));
-    CountParams cp{ctx, keys, slot_start, n_slots, m->badpre, m->badlist, counts, copies, counters + 2};
+    CK(zero_async(counts, (size_t)(one * copies) * 4, st));
+    CountParams cp{ctx, keys, slot_start, n_slots, n_eslots, m->badpre, m->badlist, counts, copies, counters + 2};
     k_window_counts<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(cp);
     LAUNCH_CHECK("k_window_counts");
     int rgrid = (int)std::min<int64_t>((one + 255) / 256, (int64_t)n_sm * 8);
-    k_counts_reduce<<<rgrid, 256, 0, st>>>(counts, copies, n_slots, W, slot_start, d_acc);
+    k_counts_reduce<<<rgrid, 256, 0, st>>>(counts, copies, n_slots, W, lr, slot_start, d_acc);
     LAUNCH_CHECK("k_counts_reduce");
     if (flags & (PUP_F_EXPCTRL | PUP_F_COVERAGE)) {
-      VecParams vp{ctx, keys, slot_start, n_slots, m->expected, m->coverage, d_acc};
+      VecParams vp{ctx, keys, slot_start, n_eslots, m->expected, m->coverage, d_acc};
       const int need = ((flags & PUP_F_EXPCTRL) ? 2 * W - 1 : W);
       const int vthreads = std::min(VT, ((need + 31) / 32) * 32);
       int grid = (int)std::min<int64_t>((n_win + VCH - 1) / VCH, (int64_t)n_sm * 16);
@@ -1556,25 +1723,24 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   // 3. the pile-up itself
   {
     SpanGuard span(2, st);
-    int S = env_int("PUP_GROUP", 4);
-    if (S != 8) S = 4;
-    // band height: one tile row per row-group, fp64 tile within PUP_TILE_KB
+    const int R = m->R, S = m->S;
+    // one lane group per strip of the window; a band = the groups whose R x W fp64 tile rows fit PUP_TILE_KB
+    const int n_groups = (W + 2 * R - 2) / R;  // ceil((W + R - 1) / R): a window touches at most that many strips
     const int tile_kb = env_int("PUP_TILE_KB", 72);
-    int Wb = (int)std::min<int64_t>(W, ((int64_t)tile_kb * 1024) / (8ll * W));
-    Wb = std::min(Wb, NT_MAX / S);
-    if (Wb < 1) Wb = 1;
-    const int n_bands = (W + Wb - 1) / Wb;
-    Wb = (W + n_bands - 1) / n_bands;  // balance the bands
-    const int threads = std::min(NT_MAX, ((Wb * S + 31) / 32) * 32);
-    const size_t smem = (size_t)Wb * W * 8;
-    MainParams mp{W, m->nb, m->lb, m->pix, m->bucket, win, chunks, Wb, n_bands, d_acc};
+    int Gb = (int)std::min<int64_t>(n_groups, ((int64_t)tile_kb * 1024) / (8ll * W * R));
+    const int nt_max = (S == 32) ? NT_MAX : NT_MAX - 32;  // the kernel's launch bound
+    Gb = std::min(Gb, nt_max / S);
+    if (Gb < 1) Gb = 1;
+    const int n_bands = (n_groups + Gb - 1) / Gb;
+    Gb = (n_groups + n_bands - 1) / n_bands;  // balance the bands
+    const int threads = std::min(nt_max, ((Gb * S + 31) / 32) * 32);
+    const size_t smem = (size_t)Gb * R * W * 8;
+    MainParams mp{W, m->ns, m->lb, m->pix, m->bucket, win, chunks, Gb, n_groups, n_bands, d_acc};
     int occ = 1;
-    const int minb = env_int("PUP_MINBLOCKS", 2);
-    const int wu = env_int("PUP_INFLIGHT", 4);
-    cudaError_t e = launch_main(S, wu, minb, mp, 0, threads, smem, st, &occ);
+    cudaError_t e = launch_main(R, S, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);
     if (occ < 1) return fail(PUP_E_CUDA, "main kernel does not fit on an SM");
-    e = launch_main(S, wu, minb, mp, n_sm * occ, threads, smem, st, nullptr);
+    e = launch_main(R, S, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
   }
@@ -1602,7 +1768,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   }
   if (n_valid_out) {
     int32_t nv = 0;
-    CK(cudaMemcpyAsync(&nv, slot_start + n_slots, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&nv, slot_start + n_eslots, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     *n_valid_out = nv;
   } else if (host_inputs && !host_acc && !async) {
@@ -1692,7 +1858,7 @@ int pup_stripes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const i
   if (host_h) CK(tmp.alloc((void**)&d_h, bytes));
   if (host_v) CK(tmp.alloc((void**)&d_v, bytes));
   StripeParams sp{m->pix, m->prow, m->bad, (m->flags & PUP_F_OOE) ? m->expected : nullptr, m->nb, W,
-                  m->ignore_diags, m->flags};
+                  m->ignore_diags, m->lr, m->flags};
   k_stripes<<<(unsigned)((n_win * 32 + 255) / 256), 256, 0, st>>>(sp, d_r0, d_c0, n_win, d_h, d_v);
   LAUNCH_CHECK("k_stripes");
   if (host_h) CK(cudaMemcpyAsync(horizontal, d_h, bytes, cudaMemcpyDeviceToHost, st));
@@ -1723,9 +1889,9 @@ int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r
   }
   unsigned long long* d_out;
   CK(tmp.alloc((void**)&d_out, 16));
-  CK(cudaMemsetAsync(d_out, 0, 16, st));
+  CK(zero_async(d_out, 16, st));
   if (n_win > 0) {
-    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->pix, m->prow, d_r0, d_c0, n_win, m->nb, W, d_out, d_out + 1);
+    k_count_nnz<<<148 * 8, 256, 0, st>>>(m->pix, m->prow, d_r0, d_c0, n_win, m->nb, W, m->lr, d_out, d_out + 1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_count_nnz", e);
   }

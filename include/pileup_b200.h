@@ -98,6 +98,15 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
                             const double* expected, const double* coverage, int ignore_diags, unsigned flags,
                             void* stream, pup_region_t** out);
 int pup_region_destroy(pup_region_t* region);
+/*
+ * Asynchronous host->device copy of a caller buffer (e.g. the window arrays of the region just created) through the
+ * library's internal upload stream, the same FIFO the matrices of pup_region_create* travel on: the copy is served
+ * in call order between the matrix uploads, and `stream` waits for it.  (A copy issued on any other stream can wait
+ * on the copy engine until every queued matrix upload has been served.)  dst is DEVICE memory the caller owns and that no
+ * pending work still uses (the upload stream does not wait for `stream`), src HOST memory (pinned for a truly
+ * asynchronous copy) that must stay valid until `stream` has passed this call.
+ */
+int pup_upload(int device, void* dst, const void* src, int64_t bytes, void* stream);
 /* bytes of HBM held by the region, and the algorithmic bytes of its pixels (8 per stored pixel) */
 int64_t pup_region_device_bytes(const pup_region_t* region);
 

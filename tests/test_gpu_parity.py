@@ -130,6 +130,39 @@ def test_kernel_vs_oracle_random(mode, nb, W, dens, nwin, n_slots, memory):
         np.testing.assert_allclose(out["cov_end"], ref["cov_end"], rtol=RTOL)
 
 
+@pytest.mark.parametrize("strip,lanes", [(1, 4), (1, 8), (2, 8), (2, 16), (4, 8), (4, 16), (8, 16), (8, 32)])
+@pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(701, 83, 200, 400, 3), (333, 21, 40, 700, 5), (900, 203, 400, 50, 2)])
+def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots):
+    """Every strip height R / lane count S the main kernel is instantiated for gives the oracle's accumulators
+    (the default is R = 2, S = 8; the geometry is fixed when the region is created)."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    monkeypatch.setenv("PUP_STRIP", str(strip))
+    monkeypatch.setenv("PUP_LANES", str(lanes))
+    ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb + W, nan_frac=0.05, with_expected=True)
+    r0, c0, sl = random_windows(nb, W, nwin, n_slots, seed=3 * nb + W)
+    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+    acc = np.zeros(n_slots * nat.acc_stride(W))
+    nv = nat.accumulate_region(0, nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, nat.PUP_F_OOE, acc)
+    _check_against_oracle(nv, nat.acc_export(acc, W, n_slots), ref)
+    # the per-window stripes read the same strip layout
+    reg = nat.Region(0, nb, ip, col, cnt, w, e, None, ignore_diags=2, flags=nat.PUP_F_OOE)
+    hor, ver = reg.stripes(r0[:40], c0[:40], W)
+    b, z = reg.algorithmic_bytes(r0, c0, W)
+    reg.close()
+    from scipy import sparse
+
+    from emulator import EmuRegion
+
+    mat = sparse.csr_matrix((cnt, col, ip), shape=(nb, nb))
+    inb = (r0 >= 0) & (c0 >= 0) & (r0 + W <= nb) & (c0 + W <= nb)
+    assert z == sum(mat[a : a + W, c : c + W].nnz for a, c in zip(r0[inb], c0[inb]))
+    ehor, ever = EmuRegion(0, nb, ip, col, cnt, w, e, None, ignore_diags=2, flags=nat.PUP_F_OOE).stripes(r0[:40], c0[:40], W)
+    np.testing.assert_allclose(hor, ehor, rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(ver, ever, rtol=RTOL, equal_nan=True)
+
+
 @pytest.mark.parametrize("nb,W,dens", [(300, 21, 30), (900, 83, 300), (64, 5, 2), (2000, 11, 1)])
 def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens):
     """pup_region_create_upper (cooler's stored upper triangle, incl. pixels that leave the region) gives the same
