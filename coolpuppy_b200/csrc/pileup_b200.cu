@@ -236,7 +236,6 @@ struct pup_region {
   int ignore_diags;
   unsigned flags;     // PUP_F_OOE | PUP_F_NODIAG folded into the pixel values
   Pix* pix;           // strip-major pixels: (col, q, normalised value), sorted by (col, q) inside a strip
-  int32_t* indptr;    // [nb+1] CSR row pointers of the symmetric matrix (input order, unpadded)
   int32_t* prow;      // [ns+1] strip starts inside pix[]: multiples of S pixels, >= S sentinel pixels close a strip
   int32_t* bucket;    // [nbk][ns] first entry (rounded down to S) of strip s with col >= b << lb
   double* expected;   // [nb] or null
@@ -254,15 +253,17 @@ namespace {
 
 // ------------------------------------------------------------------------------------------ prep kernels
 // padded strip length (multiple of S pixels) -> scanned into prow[]
-__global__ void k_padded_len(const int32_t* __restrict__ indptr, int32_t* __restrict__ plen, int nb, int ns, int lr,
-                             int S) {
+__global__ void k_padded_len(const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
+                             int32_t* __restrict__ plen, int nb, int ns, int lr, int S) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   // at least one complete group of S sentinel pixels follows the last stored pixel of every strip, so a lane that
   // steps past the end of its strip always reads a sentinel (col = INT_MAX) and the pile-up loop needs no
   // end-of-strip test
   if (s < ns) {
     const int r_lo = s << lr, r_hi = min(nb, r_lo + (1 << lr));
-    plen[s] = ((indptr[r_hi] - indptr[r_lo] + S - 1) / S + 1) * S;
+    int len = 0;
+    for (int r = r_lo; r < r_hi; ++r) len += re[r] - rs[r];
+    plen[s] = ((len + S - 1) / S + 1) * S;
   }
   if (s == ns) plen[s] = 0;
 }
@@ -316,7 +317,10 @@ __device__ __forceinline__ int lower_bound_hint(const int32_t* __restrict__ col,
 // in (col, row) order -- the position of a pixel is its index in its own row plus, for every other row of the
 // strip, the number of that row's pixels that sort before it.  The strip is closed with sentinel pixels
 // (col = INT_MAX, sorted last) up to the next multiple of S.
-__global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32_t* __restrict__ prow,
+// Row r of the source matrix is col/cnt[rs[r] .. re[r]) (a CSR with rs = indptr, re = indptr + 1, or the in-region
+// prefix of the rows of an uploaded upper triangle).
+__global__ void k_prepare_pixels(const int32_t* __restrict__ rs, const int32_t* __restrict__ re,
+                                 const int32_t* __restrict__ prow,
                                  const int32_t* __restrict__ col, const int32_t* __restrict__ cnt,
                                  const double* __restrict__ weight, const double* __restrict__ expected,
                                  Pix* __restrict__ pix, int nb, int ns, int lr, int ignore_diags, unsigned flags) {
@@ -328,9 +332,10 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
   for (int64_t s = warp; s < ns; s += nwarps) {
     const int r_lo = (int)s << lr, r_hi = min(nb, r_lo + (1 << lr));
     const int dst = prow[s], dend = prow[s + 1];
-    const int len = indptr[r_hi] - indptr[r_lo];
+    int len = 0;
+    for (int r = r_lo; r < r_hi; ++r) len += re[r] - rs[r];
     for (int r = r_lo; r < r_hi; ++r) {
-      const int lo = indptr[r], hi = indptr[r + 1];
+      const int lo = rs[r], hi = re[r];
       double wr = 1.0;
       if (weight != nullptr) wr = weight[r];
       for (int i = lo + lane; i < hi; i += 32) {
@@ -344,7 +349,7 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
         int rank = i - lo;
         for (int r2 = r_lo; r2 < r_hi; ++r2) {
           if (r2 == r) continue;
-          const int lo2 = indptr[r2], hi2 = indptr[r2 + 1];
+          const int lo2 = rs[r2], hi2 = re[r2];
           rank += lower_bound_hint(col, lo2, hi2, lo2 + (i - lo), c + (r2 < r ? 1 : 0)) - lo2;
         }
         Pix p;
@@ -362,6 +367,30 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ indptr, const int32
       pix[k] = p;
     }
   }
+}
+
+// Stored part of every source row: rs[r] = first entry with column >= r + min_d (pixels below that are masked by the
+// signed diagonal rule, coolpup.py:1141-1149, and never contribute), re[r] = first entry with column >= nb (pixels
+// of an uploaded upper triangle that leave the region).
+__global__ void k_row_trim(const int32_t* __restrict__ indptr, const int32_t* __restrict__ col, int nb, int min_d,
+                           int32_t* __restrict__ rs, int32_t* __restrict__ re) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nb) return;
+  const int lo0 = indptr[r], hi0 = indptr[r + 1];
+  auto lower = [&](int target) {
+    int lo = lo0, hi = hi0;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(&col[mid]) < target)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    return lo;
+  };
+  const int e = lower(nb);
+  re[r] = e;
+  rs[r] = min(lower(r + min_d), e);
 }
 
 // ---- symmetric fill on the device (cooler stores the upper triangle only; coolpup.py:1053-1057 relies on
@@ -1239,9 +1268,10 @@ int choose_bucket_bits(int32_t nb, int32_t ns, int R, int64_t nnz, int* nbk_out)
   return lb;
 }
 
-// Everything after the symmetric CSR (indptr in r->indptr, DEVICE col/count) is known: normalise pixels into the
-// strip layout, build the bucket table and the masks.  `weight` may be host or device.
-int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const double* weight, Scratch& tmp) {
+// The source matrix is on the device (row r = dcol/dcnt[rs[r] .. re[r]), r->nnz bounds the pixel count): normalise
+// the pixels into the strip layout, build the bucket table and the masks.
+int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int32_t* dcol, const int32_t* dcnt,
+                  const double* weight, int64_t nnz_estimate, Scratch& tmp) {
   // `weight` is DEVICE memory here (staged by the caller)
   cudaStream_t st = r->stream;
   const int32_t nb = r->nb;
@@ -1251,7 +1281,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   r->ns = (nb + r->R - 1) >> r->lr;
   const int32_t ns = r->ns;
   const int S = r->S;
-  r->lb = choose_bucket_bits(nb, ns, r->R, nnz, &r->nbk);
+  r->lb = choose_bucket_bits(nb, ns, r->R, std::max<int64_t>(nnz_estimate, 1), &r->nbk);
   // strips padded with sentinel groups (+ slack for the main kernel's L2 prefetch two groups ahead)
   size_t n_ent = (size_t)nnz + (size_t)(2 * S) * ns + 4 * S;
   if (n_ent >= (1ull << 31)) return fail(PUP_E_ARG, "region create: padded pixel table exceeds 2^31 entries");
@@ -1260,7 +1290,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   {
     int32_t* plen;
     CK(tmp.alloc((void**)&plen, (size_t)(ns + 1) * 4));
-    k_padded_len<<<(ns + 1 + 255) / 256, 256, 0, st>>>(r->indptr, plen, nb, ns, r->lr, S);
+    k_padded_len<<<(ns + 1 + 255) / 256, 256, 0, st>>>(rs, re, plen, nb, ns, r->lr, S);
     LAUNCH_CHECK("k_padded_len");
     size_t tb = 0;
     CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, plen, r->prow, ns + 1, st));
@@ -1272,7 +1302,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * ns * 4, st));
   CK(cudaMallocAsync((void**)&r->ebad, (size_t)nb, st));
   CK(cudaMallocAsync((void**)&r->ebadpre, (size_t)(nb + 1) * 4, st));
-  r->bytes += (int64_t)(n_ent * sizeof(Pix) + (size_t)(ns + 1) * 4 + (size_t)(nb + 1) * 8 + (size_t)r->nbk * ns * 4 +
+  r->bytes += (int64_t)(n_ent * sizeof(Pix) + (size_t)(ns + 1) * 4 + (size_t)(nb + 1) * 4 + (size_t)r->nbk * ns * 4 +
                         (size_t)nb);
   const double* dw = weight;
   if (weight) {
@@ -1283,7 +1313,7 @@ int finish_region(pup_region* r, const int32_t* dcol, const int32_t* dcnt, const
   }
   {
     int grid = std::min((ns + 7) / 8, 148 * 16);
-    k_prepare_pixels<<<grid, 256, 0, st>>>(r->indptr, r->prow, dcol, dcnt, dw, r->expected, r->pix, nb, ns, r->lr,
+    k_prepare_pixels<<<grid, 256, 0, st>>>(rs, re, r->prow, dcol, dcnt, dw, r->expected, r->pix, nb, ns, r->lr,
                                            r->ignore_diags, r->flags);
     LAUNCH_CHECK("k_prepare_pixels");
   }
@@ -1324,7 +1354,6 @@ int new_region(int device, int32_t nb, const double* expected, const double* cov
   r->ignore_diags = ignore_diags;
   r->flags = flags;
   *out = r;
-  CK(cudaMallocAsync((void**)&r->indptr, (size_t)(nb + 1) * 4, st));
   // host vectors go through the internal copy stream like the matrix arrays (FIFO with them), not through the
   // caller's stream, where a small copy could wait behind uploads that other calls queued on the copy engine
   auto put = [&](double** dst, const double* src) -> int {
@@ -1356,6 +1385,10 @@ int new_region(int device, int32_t nb, const double* expected, const double* cov
   }
   return PUP_OK;
 }
+
+// With the signed diagonal mask every pixel with col - row < ignore_diags is NaN in the reference's snippets: for
+// ignore_diags >= 0 that is the whole lower triangle, which is then neither mirrored nor stored.
+bool lower_triangle_masked(unsigned flags, int ignore_diags) { return !(flags & PUP_F_NODIAG) && ignore_diags >= 0; }
 
 int check_region_args(const char* who, int device, int32_t nb, int64_t nnz, const void* indptr, const void* col,
                       const void* count, const double* expected, unsigned flags) {
@@ -1440,11 +1473,25 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
     if (rc == PUP_OK) rc = up.stage(weight, (size_t)nb * 8, &dw);
     if (rc == PUP_OK) rc = up.join();
     if (rc == PUP_OK) {
-      cudaError_t e = cudaMemcpyAsync(r->indptr, dip, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) rc = fail(PUP_E_CUDA, "pup_region_create: indptr copy", e);
+      const int32_t *rs = (const int32_t*)dip, *re = (const int32_t*)dip + 1;
+      int64_t nnz_est = nnz;
+      if (lower_triangle_masked(flags, ignore_diags) && nnz > 0) {
+        int32_t *trs, *tre;
+        cudaError_t e = tmp.alloc((void**)&trs, (size_t)nb * 4);
+        if (e == cudaSuccess) e = tmp.alloc((void**)&tre, (size_t)nb * 4);
+        if (e != cudaSuccess) {
+          rc = fail(PUP_E_OOM, "pup_region_create: scratch", e);
+        } else {
+          k_row_trim<<<(nb + 255) / 256, 256, 0, st>>>((const int32_t*)dip, (const int32_t*)dcol, nb, ignore_diags, trs,
+                                                        tre);
+          ++g_launches;
+          rs = trs;
+          re = tre;  // bucket sizing keeps using the symmetric count: the density per column is unchanged
+        }
+      }
+      if (rc == PUP_OK)
+        rc = finish_region(r, rs, re, (const int32_t*)dcol, (const int32_t*)dcnt, (const double*)dw, nnz_est, tmp);
     }
-    if (rc == PUP_OK)
-      rc = finish_region(r, (const int32_t*)dcol, (const int32_t*)dcnt, (const double*)dw, tmp);
     cudaError_t e = cudaSuccess;
     const bool host_in = !is_device_ptr(indptr) || (nnz > 0 && (!is_device_ptr(col) || !is_device_ptr(count))) ||
                          (weight && !is_device_ptr(weight)) || (expected && !is_device_ptr(expected)) ||
@@ -1491,8 +1538,19 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
     if ((rc2 = up.stage(weight, weight ? (size_t)nb * 8 : 0, &v_w)) != PUP_OK) return rc2;
     if ((rc2 = up.join()) != PUP_OK) return rc2;
     const int32_t *d_ip = (const int32_t*)v_ip, *d_col = (const int32_t*)v_col, *d_cnt = (const int32_t*)v_cnt;
+    if (lower_triangle_masked(flags, ignore_diags)) {
+      // nothing below the diagonal survives the mask: the uploaded upper triangle is all the pile-up needs
+      int32_t *rs, *re;
+      CK(tmp.alloc((void**)&rs, (size_t)nb * 4));
+      CK(tmp.alloc((void**)&re, (size_t)nb * 4));
+      k_row_trim<<<(nb + 255) / 256, 256, 0, st>>>(d_ip, d_col, nb, ignore_diags, rs, re);
+      LAUNCH_CHECK("k_row_trim");
+      r->nnz = nnz_upper;
+      return finish_region(r, rs, re, d_col, d_cnt, (const double*)v_w, 2 * nnz_upper, tmp);
+    }
     const size_t nu = (size_t)(nnz_upper > 0 ? nnz_upper : 1);
-    int32_t *up_cnt, *lo_cnt, *lo_start, *tot_cnt, *key_a, *key_b, *val_a, *val_b, *row_of;
+    int32_t *up_cnt, *lo_cnt, *lo_start, *tot_cnt, *key_a, *key_b, *val_a, *val_b, *row_of, *sym_indptr;
+    CK(tmp.alloc((void**)&sym_indptr, (size_t)(nb + 1) * 4));
     CK(tmp.alloc((void**)&up_cnt, (size_t)(nb + 1) * 4));
     CK(tmp.alloc((void**)&lo_cnt, (size_t)(nb + 1) * 4));
     CK(tmp.alloc((void**)&lo_start, (size_t)(nb + 1) * 4));
@@ -1514,11 +1572,11 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
     size_t tb = 0, tb2 = 0;
     cub::DoubleBuffer<int32_t> dk(key_a, key_b), dv(val_a, val_b);
     const int bits = ilog2_ceil((int64_t)nb + 1);
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, tot_cnt, r->indptr, nb + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, tot_cnt, sym_indptr, nb + 1, st));
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tb2, dk, dv, (int)nnz_upper, 0, bits, st));
     void* t;
     CK(tmp.alloc(&t, std::max(tb, tb2)));
-    CK(cub::DeviceScan::ExclusiveSum(t, tb, tot_cnt, r->indptr, nb + 1, st));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, tot_cnt, sym_indptr, nb + 1, st));
     CK(cub::DeviceScan::ExclusiveSum(t, tb, lo_cnt, lo_start, nb + 1, st));
     if (nnz_upper > 0) CK(cub::DeviceRadixSort::SortPairs(t, tb2, dk, dv, (int)nnz_upper, 0, bits, st));
     g_launches += 2 + (bits + 7) / 8;
@@ -1528,14 +1586,14 @@ int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int
     int32_t *col_s, *cnt_s;
     CK(tmp.alloc((void**)&col_s, (size_t)std::max<int64_t>(r->nnz, 1) * 4));
     CK(tmp.alloc((void**)&cnt_s, (size_t)std::max<int64_t>(r->nnz, 1) * 4));
-    k_place_upper<<<wgrid, 256, 0, st>>>(d_ip, d_col, d_cnt, r->indptr, lo_cnt, nb, col_s, cnt_s);
+    k_place_upper<<<wgrid, 256, 0, st>>>(d_ip, d_col, d_cnt, sym_indptr, lo_cnt, nb, col_s, cnt_s);
     LAUNCH_CHECK("k_place_upper");
     if (nnz_upper > 0) {
       k_place_lower<<<(unsigned)((nnz_upper + 255) / 256), 256, 0, st>>>(dk.Current(), dv.Current(), row_of, d_cnt,
-                                                                          r->indptr, lo_start, nb, col_s, cnt_s);
+                                                                          sym_indptr, lo_start, nb, col_s, cnt_s);
       LAUNCH_CHECK("k_place_lower");
     }
-    return finish_region(r, col_s, cnt_s, (const double*)v_w, tmp);
+    return finish_region(r, sym_indptr, sym_indptr + 1, col_s, cnt_s, (const double*)v_w, r->nnz, tmp);
   };
   if (rc == PUP_OK) rc = body();
   const bool host_in = !is_device_ptr(indptr_upper) || (nnz_upper > 0 && (!is_device_ptr(col_upper) || !is_device_ptr(count_upper))) ||
@@ -1579,8 +1637,8 @@ int pup_region_destroy(pup_region_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
-  void* ptrs[] = {r->pix, r->indptr, r->prow,    r->bucket, r->expected, r->coverage,
-                  r->bad, r->ebad,   r->ebadpre, r->badpre, r->badlist};
+  void* ptrs[] = {r->pix, r->prow, r->bucket,  r->expected, r->coverage, r->bad,
+                  r->ebad, r->ebadpre, r->badpre, r->badlist};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
   delete r;

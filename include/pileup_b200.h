@@ -90,8 +90,11 @@ int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr
  * Same, from the UPPER triangle as cooler stores it (replaces the symmetric fill that cooler's
  * matrix(...).fetch() performs on the CPU, coolpup.py:1053-1057): row r of the region holds its stored pixels with
  * region-relative columns >= r, sorted; columns >= nb (pixels that leave the region: trans, or beyond a view arm)
- * are dropped.  The lower triangle is mirrored in on the device (stable radix sort by column), which halves the
- * host->device traffic; device arrays are sized for the 2 * nnz_upper bound so no size is read back.
+ * are dropped.  With the signed diagonal mask and ignore_diags >= 0 (every cis pile-up of the reference) all pixels
+ * below the diagonal are masked, so nothing is mirrored: the upload is indexed as it is, half the device work and
+ * memory.  Otherwise (ignore_diags < 0 or PUP_F_NODIAG) the lower triangle is mirrored in on the device (stable
+ * radix sort by column); device arrays are sized for the 2 * nnz_upper bound so no size is read back.
+ * Both entry points drop the pixels the mask removes (col - row < ignore_diags) instead of storing zeros.
  */
 int pup_region_create_upper(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper,
                             const int32_t* col_upper, const int32_t* count_upper, const double* weight,

@@ -157,7 +157,13 @@ def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots)
 
     mat = sparse.csr_matrix((cnt, col, ip), shape=(nb, nb))
     inb = (r0 >= 0) & (c0 >= 0) & (r0 + W <= nb) & (c0 + W <= nb)
-    assert z == sum(mat[a : a + W, c : c + W].nnz for a, c in zip(r0[inb], c0[inb]))
+    # algorithmic pixels = stored pixels inside the window that the signed diagonal mask keeps (col - row >= 2);
+    # masked pixels are not stored on the device at all
+    def kept(a, c):
+        blk = mat[a : a + W, c : c + W].tocoo()
+        return int(((blk.col + c) - (blk.row + a) >= 2).sum())
+
+    assert z == sum(kept(a, c) for a, c in zip(r0[inb], c0[inb]))
     ehor, ever = EmuRegion(0, nb, ip, col, cnt, w, e, None, ignore_diags=2, flags=nat.PUP_F_OOE).stripes(r0[:40], c0[:40], W)
     np.testing.assert_allclose(hor, ehor, rtol=RTOL, equal_nan=True)
     np.testing.assert_allclose(ver, ever, rtol=RTOL, equal_nan=True)
