@@ -190,6 +190,7 @@ int ilog2_ceil(int64_t v) {
 }
 
 constexpr int NT_MAX = 384;  // max threads per CTA of the main kernel (12 warps)
+constexpr int SENT_PAD = 4;  // groups of S sentinel pixels at the start of pix[]
 constexpr int VT = 512;      // max threads per CTA of the vector kernel
 constexpr int VCH = 256;     // windows per CTA step of the vector kernel
 constexpr int VU = 4;        // windows in flight per thread of the vector kernel
@@ -329,6 +330,15 @@ __global__ void k_prepare_pixels(const int32_t* __restrict__ rs, const int32_t* 
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool ooe = (flags & PUP_F_OOE) && expected != nullptr;
   const bool nodiag = flags & PUP_F_NODIAG;
+  if (warp == 0) {  // the sentinel block in front of the first strip
+    for (int k = lane; k < prow[0]; k += 32) {
+      Pix p;
+      p.col = 0x7fffffff;
+      p.q = 0;
+      p.val = 0.0;
+      pix[k] = p;
+    }
+  }
   for (int64_t s = warp; s < ns; s += nwarps) {
     const int r_lo = (int)s << lr, r_hi = min(nb, r_lo + (1 << lr));
     const int dst = prow[s], dend = prow[s + 1];
@@ -885,17 +895,17 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
     if (G >= p.n_groups || G * R - (slot & (R - 1)) >= W) continue;  // strip entirely below the window
 
     for (int w = w_lo; w < w_hi; w += WU) {
+      // Two register sets (A, B) of raw pixel records {col, q, val} per window in flight.  Every half-step loads
+      // the next record of every run unconditionally: a lane whose current pixel already lies right of the window
+      // reads a sentinel (col = INT_MAX) from the block at the start of pix[] instead, which ends its run -- no
+      // predicated loads, no register copies.
       int idx[WU], c0s[WU];
-      int djA[WU], djB[WU];
-      int qA[R > 1 ? WU : 1], qB[R > 1 ? WU : 1];
-      double vA[WU], vB[WU];
+      int4 A[WU], B[WU];
       // stage A: window records -> strip pointers (WU independent chains)
 #pragma unroll
       for (int u = 0; u < WU; ++u) {
-        idx[u] = -1;
+        idx[u] = ls;  // a sentinel
         c0s[u] = 0;
-        vB[u] = 0.0;
-        if (R > 1) qA[u] = qB[u] = 0;
         if (w + u < w_hi) {
           const int2 rc = __ldg(&p.win[w + u]);
           idx[u] = __ldg(&p.bucket[(rc.y >> p.lb) * ns + (rc.x >> LR) + G]) + ls;
@@ -904,54 +914,36 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
       }
       // stage B: first pixel of every window's run
 #pragma unroll
-      for (int u = 0; u < WU; ++u) {
-        djA[u] = 0x7fffffff;
-        vA[u] = 0.0;
-        if (idx[u] >= 0) {
-          const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
-          djA[u] = raw.x - c0s[u];
-          if (R > 1) qA[u] = raw.y * W;
-          vA[u] = __hiloint2double(raw.w, raw.z);
-        }
-      }
+      for (int u = 0; u < WU; ++u) A[u] = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));
       // stage C: the WU runs advance in lockstep, S pixels per run per half-step.  Strips end with a full group of
-      // sentinel pixels (col = INT_MAX), so "dj >= W" is the only termination test.
-#define PUP_HALF_STEP(CD, CQ, CV, ND, NQ, NV)                                                \
-  {                                                                                          \
-    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
-      ND[u] = 0x7fffffff;                                                                    \
-      idx[u] += S;                                                                           \
-      if (CD[u] < W) {                                                                       \
-        const int4 raw = __ldg(reinterpret_cast<const int4*>(p.pix + idx[u]));               \
-        ND[u] = raw.x - c0s[u];                                                              \
-        if (R > 1) NQ[u] = raw.y * W;                                                        \
-        NV[u] = __hiloint2double(raw.w, raw.z);                                              \
-        if (PF == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.pix + idx[u] + S));     \
-        if (PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pix + idx[u] + 2 * S)); \
-      }                                                                                      \
-    }                                                                                        \
-    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                         \
-      if ((unsigned)CD[u] < (unsigned)W) {                                                   \
-        const unsigned a = trow + (unsigned)(CD[u] + (R > 1 ? CQ[u] : 0)) * 8u;              \
-        sts_f64(a, lds_f64(a) + CV[u]);                                                      \
-      }                                                                                      \
-    }                                                                                        \
+      // sentinel pixels, so "dj >= W" is the only termination test.
+#define PUP_HALF_STEP(C, N)                                                                      \
+  {                                                                                              \
+    int dj[WU];                                                                                  \
+    _Pragma("unroll") for (int u = 0; u < WU; ++u) dj[u] = C[u].x - c0s[u];                      \
+    int mn = dj[0];                                                                              \
+    _Pragma("unroll") for (int u = 1; u < WU; ++u) mn = min(mn, dj[u]);                          \
+    if (mn >= W) break;                                                                          \
+    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                             \
+      idx[u] = (dj[u] < W) ? idx[u] + S : ls;                                                    \
+      const Pix* src = p.pix + idx[u];                                                           \
+      N[u] = __ldg(reinterpret_cast<const int4*>(src));                                          \
+      if (PF == 2 && dj[u] < W) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * S));     \
+    }                                                                                            \
+    _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                             \
+      if ((unsigned)dj[u] < (unsigned)W) {                                                       \
+        const unsigned a = trow + (unsigned)(dj[u] + (R > 1 ? C[u].y * W : 0)) * 8u;             \
+        sts_f64(a, lds_f64(a) + __hiloint2double(C[u].w, C[u].z));                               \
+      }                                                                                          \
+    }                                                                                            \
   }
       // Lanes leave the loop individually once their WU runs are exhausted and wait at the __syncwarp below; the
       // lanes still inside execute the same predicated instruction stream, so the read-modify-writes of one tile
       // row are ordered by the program order of a converged SIMT group (racecheck reports them as intra-warp
       // hazards "without barrier"; a group-voted exit was measured 6 % slower and changes nothing about ordering).
       for (;;) {
-        int mn = djA[0];
-#pragma unroll
-        for (int u = 1; u < WU; ++u) mn = min(mn, djA[u]);
-        if (mn >= W) break;
-        PUP_HALF_STEP(djA, qA, vA, djB, qB, vB)
-        mn = djB[0];
-#pragma unroll
-        for (int u = 1; u < WU; ++u) mn = min(mn, djB[u]);
-        if (mn >= W) break;
-        PUP_HALF_STEP(djB, qB, vB, djA, qA, vA)
+        PUP_HALF_STEP(A, B)
+        PUP_HALF_STEP(B, A)
       }
 #undef PUP_HALF_STEP
       __syncwarp(gmask);
@@ -1149,14 +1141,21 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
 }
 
 // occ != nullptr: only query the occupancy; else launch
-template <int R, int S>
-cudaError_t launch_main_rs(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = k_pileup_main<R, S, 4, 2>;
+template <int R, int S, int PF>
+cudaError_t launch_main_rsp(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = k_pileup_main<R, S, 4, PF>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
   kern<<<grid, threads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int R, int S>
+cudaError_t launch_main_rs(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
+  const int pf = env_int("PUP_PREFETCH", 2);
+  if (R == 2 && S == 8 && pf == 0) return launch_main_rsp<R, S, 0>(p, grid, threads, smem, st, occ);
+  return launch_main_rsp<R, S, 2>(p, grid, threads, smem, st, occ);
 }
 
 cudaError_t launch_main(int R, int S, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
@@ -1283,7 +1282,7 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
   const int S = r->S;
   r->lb = choose_bucket_bits(nb, ns, r->R, std::max<int64_t>(nnz_estimate, 1), &r->nbk);
   // strips padded with sentinel groups (+ slack for the main kernel's L2 prefetch two groups ahead)
-  size_t n_ent = (size_t)nnz + (size_t)(2 * S) * ns + 4 * S;
+  size_t n_ent = (size_t)nnz + (size_t)(2 * S) * ns + 4 * S + SENT_PAD * S;
   if (n_ent >= (1ull << 31)) return fail(PUP_E_ARG, "region create: padded pixel table exceeds 2^31 entries");
   CK(cudaMallocAsync((void**)&r->pix, n_ent * sizeof(Pix), st));
   CK(cudaMallocAsync((void**)&r->prow, (size_t)(ns + 1) * 4, st));
@@ -1293,10 +1292,12 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
     k_padded_len<<<(ns + 1 + 255) / 256, 256, 0, st>>>(rs, re, plen, nb, ns, r->lr, S);
     LAUNCH_CHECK("k_padded_len");
     size_t tb = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, plen, r->prow, ns + 1, st));
+    // pix[0 .. SENT_PAD * S) is a block of sentinel pixels (the main kernel reads it instead of predicating a load
+    // off); the strips follow
+    CK(cub::DeviceScan::ExclusiveScan(nullptr, tb, plen, r->prow, cub::Sum(), SENT_PAD * S, ns + 1, st));
     void* t;
     CK(tmp.alloc(&t, tb));
-    CK(cub::DeviceScan::ExclusiveSum(t, tb, plen, r->prow, ns + 1, st));
+    CK(cub::DeviceScan::ExclusiveScan(t, tb, plen, r->prow, cub::Sum(), SENT_PAD * S, ns + 1, st));
     ++g_launches;
   }
   CK(cudaMallocAsync((void**)&r->bucket, (size_t)r->nbk * ns * 4, st));

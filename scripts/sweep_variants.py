@@ -58,6 +58,7 @@ def main():
         os.environ["PUP_STRIP"], os.environ["PUP_LANES"] = parts[0], parts[1]
         os.environ["PUP_BUCKET_TARGET"] = parts[2] if len(parts) > 2 else "4"
         os.environ["PUP_CHUNK"] = parts[3] if len(parts) > 3 else "64"
+        os.environ["PUP_PREFETCH"] = parts[4] if len(parts) > 4 else "2"
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         regions = {c: _native.Region(0, d["nb"], d["indptr"], d["col"], d["count"], d["weight"], None, None, ignore_diags=2,
