@@ -925,10 +925,14 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
     _Pragma("unroll") for (int u = 1; u < WU; ++u) mn = min(mn, dj[u]);                          \
     if (mn >= W) break;                                                                          \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                             \
-      idx[u] = (dj[u] < W) ? idx[u] + S : ls;                                                    \
-      const Pix* src = p.pix + idx[u];                                                           \
-      N[u] = __ldg(reinterpret_cast<const int4*>(src));                                          \
-      if (PF == 2 && dj[u] < W) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * S));     \
+      idx[u] += S;                                                                               \
+      if (dj[u] < W) {                                                                           \
+        const Pix* src = p.pix + idx[u];                                                         \
+        N[u] = __ldg(reinterpret_cast<const int4*>(src));                                        \
+        if (PF == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2 * S));                \
+      } else {                                                                                   \
+        N[u].x = 0x7fffffff;                                                                     \
+      }                                                                                          \
     }                                                                                            \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                             \
       if ((unsigned)dj[u] < (unsigned)W) {                                                       \
