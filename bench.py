@@ -275,10 +275,28 @@ def main():
         "host_window_generation_s": round(host_window_s, 3),
     }
 
-    # which chromosomes are mine
+    # which chromosomes are mine (the sharding unit of the reference: one view region per worker, coolpup.py:1502-1508)
     cost = [len(windows[c]["r0"]) * (windows[c]["nb"] / 1e4) for c in names]
     owner = lpt(cost, world if args.impl == "b200" else 1)
     mine = [c for c, o in zip(names, owner) if o == (rank if args.impl == "b200" else 0)]
+    # Resident pass, N > 1: a chromosome heavier than half a rank's share is split by WINDOWS into equal parts that go
+    # to different ranks with the matrix replicated (windows are independent, the accumulators add up);
+    # otherwise chr1 alone (13 % of the work) caps 8 ranks at 7.6x.  The e2e pass keeps whole chromosomes per rank:
+    # there the matrix upload, not the pile-up, is the cost of a unit.
+    units, ucost = [], []
+    share = sum(cost) / max(world, 1)
+    for c, k in zip(names, cost):
+        parts = 1 if world == 1 else int(min(world, max(1, np.ceil(k / (0.5 * share)))))
+        for part in range(parts):
+            units.append((c, part, parts))
+            ucost.append(k / parts)
+    uowner = lpt(ucost, world if args.impl == "b200" else 1)
+    my_units = [u for u, o in zip(units, uowner) if o == (rank if args.impl == "b200" else 0)]
+    split = sorted({c for c, _, n in units if n > 1}, key=names.index)
+    if split:
+        config["parallelism"] = (f"chromosomes sharded over {world} GPUs by LPT; {','.join(split)} split by windows into "
+                                 f"{sum(1 for c, _, n in units if n > 1)} parts (matrix replicated); one all-reduce of the "
+                                 "accumulators; e2e: whole chromosomes per GPU")
 
     if args.impl == "reference":
         return run_reference(args, names, sizes, windows, config, dev)
@@ -287,20 +305,25 @@ def main():
     stream = torch.cuda.current_stream(dev).cuda_stream
     regions, host, dwin = {}, {}, {}
     nnz_total = 0
+    unit_chroms = {c for c, _, _ in my_units}
     for ci, c in enumerate(names):
-        if c not in mine:
+        if c not in mine and c not in unit_chroms:
             continue
         t = synthetic_region(windows[c]["nb"], depth=args.depth, seed=1234 + ci, device=dev, nan_frac=0.03)
-        nnz_total += int(t["col"].shape[0])
-        regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None,
-                                    ignore_diags=2, flags=0, stream=stream)
-        if not args.no_e2e or (rank == 0 and not args.no_cpu):
+        if c in unit_chroms:
+            nnz_total += int(t["col"].shape[0])
+            regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None,
+                                        ignore_diags=2, flags=0, stream=stream)
+        if c in mine and (not args.no_e2e or (rank == 0 and not args.no_cpu)):
             host[c] = {k: t[k].cpu().pin_memory() for k in ("upper_indptr", "upper_col", "upper_count", "weight")}
             if rank == 0 and not args.no_cpu and c in CPU_SAMPLE_REGIONS:
                 host[c].update({k: t[k].cpu() for k in ("indptr", "col", "count")})
-        w = windows[c]
-        dwin[c] = tuple(torch.from_numpy(w[k]).to(dev) for k in ("r0", "c0", "slot"))
         del t
+    for c, part, parts in my_units:
+        w = windows[c]
+        n = len(w["r0"])
+        lo, hi = (n * part) // parts, (n * (part + 1)) // parts
+        dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][lo:hi])).to(dev) for k in ("r0", "c0", "slot"))
     torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()
 
@@ -312,16 +335,16 @@ def main():
     # exact algorithmic bytes of my windows (untimed)
     alg_bytes = 0
     alg_nnz = 0
-    for c in mine:
-        b, z = regions[c].algorithmic_bytes(dwin[c][0], dwin[c][1], W, flags, stream=stream)
+    for c, part, _ in my_units:
+        b, z = regions[c].algorithmic_bytes(dwin[(c, part)][0], dwin[(c, part)][1], W, flags, stream=stream)
         alg_bytes += b
         alg_nnz += z
 
     def step():
         acc.zero_()
         launches = 1
-        for c in mine:
-            r0, c0, sl = dwin[c]
+        for c, part, _ in my_units:
+            r0, c0, sl = dwin[(c, part)]
             regions[c].accumulate(r0, c0, sl, W, n_slots, flags, acc, stream=stream)
             launches += _native.lib().pup_last_launches()
         if dist is not None:
@@ -469,7 +492,7 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = int(tr["dram_bytes"] / tr["algorithmic_bytes"] * (slow_b / max(1, len(mine))))
+        traffic = int(tr["dram_bytes"] / tr["algorithmic_bytes"] * (slow_b / max(1, len(my_units))))
     except Exception:
         pass
     roofline = {
@@ -477,7 +500,7 @@ def main():
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "traffic_source": "ncu --set full capture of the chr1 launch (profiles/r1_k_pileup_main_ncu.md), scaled by "
                           "algorithmic bytes to the average launch",
-        "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1, len(mine))),
+        "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1, len(my_units))),
         "kernel_ms_per_step": slow_ms, "launches_per_step": n_main // args.steps,
         "avg_launch_ms": slow_ms / max(1, n_main // args.steps),
         "stored_pixels_in_windows_per_step": int(sum(float(s[1]) for s in allstats)),

@@ -1730,11 +1730,15 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     // valid keys use 2*pb+sb bits and have bit (2*pb+sb) clear; the invalid marker (~0) has it set,
     // so sorting bits [0, 2*pb+sb+1) orders everything and puts the invalid windows last.
     const int end_bit = 2 * pb + sb + 1;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_win, 0, end_bit, st));
+    // the order of the lowest c0 bits only matters for locality: leave up to 4 of them unsorted when that saves
+    // an 8-bit radix pass (the key still carries them for k_decode_windows)
+    int begin_bit = end_bit - 8 * ((end_bit + 7) / 8 - 1);
+    if (begin_bit > 4 || begin_bit >= pb || end_bit <= 8) begin_bit = 0;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, dbuf, (int)n_win, begin_bit, end_bit, st));
     void* t;
     CK(tmp.alloc(&t, tb));
-    CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, 0, end_bit, st));
-    g_launches += (end_bit + 7) / 8 + 1;
+    CK(cub::DeviceRadixSort::SortKeys(t, tb, dbuf, (int)n_win, begin_bit, end_bit, st));
+    g_launches += (end_bit - begin_bit + 7) / 8 + 1;
     keys = dbuf.Current();
     CK(tmp.alloc((void**)&win, (size_t)n_win * 8));
     k_decode_windows<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(keys, win, n_win, pb);

@@ -306,3 +306,63 @@ def test_linearity_and_permutation_large():
     out = nat.acc_export(acc, W, n_slots, device=0, stream=stream)
     _check_against_oracle(k, out, ref)
     reg.close()
+
+
+def test_async_upload_pipeline_matches_oracle():
+    """The end-to-end pattern of bench.py: regions created from pinned HOST upper triangles with PUP_F_ASYNC on a
+    prepare stream, window arrays through pup_upload, pile-ups with PUP_F_ASYNC on a compute stream, everything
+    adding into one device accumulator -- equals the sum of the oracle's per-region accumulators."""
+    nat = _cuda()
+    import torch
+
+    from oracle.pileup_oracle import oracle_accumulate
+
+    dev = torch.device("cuda", 0)
+    W, n_slots = 21, 3
+    stride = nat.acc_stride(W)
+    regions = []
+    ref_sum, ref_num, ref_n = 0, 0, 0
+    for k, (nb, dens) in enumerate([(900, 60), (300, 30), (1500, 120), (64, 3)]):
+        ip, col, cnt, w, e, cov = random_region(nb, dens, seed=100 + k, nan_frac=0.05, with_expected=True)
+        r0, c0, sl = random_windows(nb, W, 700, n_slots, seed=200 + k)
+        ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+        ref_sum, ref_num, ref_n = ref_sum + np.nan_to_num(ref["sum"], posinf=np.inf), ref_num + ref["num"], ref_n + ref["n"]
+        rows = np.repeat(np.arange(nb), np.diff(ip))
+        up = col >= rows
+        uip = np.zeros(nb + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows[up], minlength=nb), out=uip[1:])
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        regions.append(dict(nb=nb, uip=pin(uip.astype(np.int32)), uc=pin(col[up]), uv=pin(cnt[up]), w=pin(w), e=pin(e),
+                            win=[pin(r0), pin(c0), pin(sl)]))
+    acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
+    s_prep, s_comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dwin = [[torch.empty_like(t, device=dev) for t in r["win"]] for r in regions]
+    torch.cuda.synchronize()
+    ASYNC = nat.PUP_F_ASYNC
+
+    def upload(k):
+        r = regions[k]
+        reg = nat.Region(0, r["nb"], r["uip"], r["uc"], r["uv"], r["w"], r["e"], None, ignore_diags=2,
+                         flags=nat.PUP_F_OOE | ASYNC, stream=s_prep.cuda_stream, upper=True)
+        for d, h in zip(dwin[k], r["win"]):
+            nat.upload(0, d, h, stream=s_prep.cuda_stream)
+        return reg, s_prep.record_event()
+
+    for _ in range(2):  # twice: the second pass re-uses pool memory and the landing buffers
+        acc.zero_()
+        torch.cuda.synchronize()
+        nxt = upload(0)
+        for k in range(len(regions)):
+            reg, ready = nxt
+            nxt = upload(k + 1) if k + 1 < len(regions) else None
+            s_comp.wait_event(ready)
+            reg.accumulate(dwin[k][0], dwin[k][1], dwin[k][2], W, n_slots, ASYNC, acc, stream=s_comp.cuda_stream)
+            s_prep.wait_event(s_comp.record_event())
+            with torch.cuda.stream(s_prep):
+                reg.close()
+        torch.cuda.synchronize()
+        out = nat.acc_export(acc, W, n_slots, device=0)
+        assert np.array_equal(out["n"], ref_n) and np.array_equal(out["num"], ref_num)
+        m = np.isfinite(ref_sum)
+        assert np.array_equal(np.isinf(out["sum"]), np.isinf(ref_sum))
+        np.testing.assert_allclose(out["sum"][m], ref_sum[m], rtol=RTOL, atol=1e-300)
