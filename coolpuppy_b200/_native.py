@@ -21,7 +21,7 @@ _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200
 
 SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",
-    "pup_region_destroy", "pup_upload",
+    "pup_region_destroy", "pup_upload", "pup_expected_cis",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
 ]
@@ -50,6 +50,7 @@ def lib():
     L.pup_region_create_upper.argtypes = L.pup_region_create.argtypes
     L.pup_region_destroy.argtypes = [vp]
     L.pup_upload.argtypes = [C.c_int, vp, vp, i64, vp]
+    L.pup_expected_cis.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
     L.pup_acc_stride.argtypes = [C.c_int]
@@ -190,6 +191,18 @@ def upload(device, dst, src, stream=0):
     tensor ``dst`` through the library's upload stream (FIFO with the region matrices); ``stream`` waits for it."""
     nbytes = src.numel() * src.element_size() if hasattr(src, "numel") else src.nbytes
     check(lib().pup_upload(device, ptr(dst), ptr(src), int(nbytes), stream))
+
+
+def expected_cis_sums(device, nb, indptr_upper, col_upper, count_upper, weight=None, stream=0):
+    """``pup_expected_cis``: per-diagonal ``(count_sum f64[nb], balanced_sum f64[nb] | None, n_valid i64[nb])`` of one
+    region's upper triangle (host arrays out)."""
+    nb = int(nb)
+    cs = np.empty(nb, dtype=np.float64)
+    bs = np.empty(nb, dtype=np.float64) if weight is not None else None
+    nv = np.empty(nb, dtype=np.int64)
+    check(lib().pup_expected_cis(device, nb, int(col_upper.shape[0]), ptr(indptr_upper), ptr(col_upper), ptr(count_upper),
+                                 ptr(weight), ptr(cs), ptr(bs), ptr(nv), stream))
+    return cs, bs, nv
 
 
 def timing_enable(on=True):

@@ -1144,6 +1144,54 @@ __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------ expected by distance
+// Per-diagonal sums of a region's stored upper-triangle pixels: what `cooltools expected-cis` feeds into the
+// reference's --expected option (CLI.py:484-508; consumed at coolpup.py:861-918).  One warp per row.
+__global__ void k_diag_sums(const int32_t* __restrict__ indptr_u, const int32_t* __restrict__ col_u,
+                            const int32_t* __restrict__ cnt_u, const double* __restrict__ weight, int nb,
+                            double* __restrict__ count_sum, double* __restrict__ bal_sum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < nb; r += nwarps) {
+    const double wr = weight ? weight[r] : 1.0;
+    for (int i = indptr_u[r] + lane; i < indptr_u[r + 1]; i += 32) {
+      const int c = col_u[i];
+      if (c < (int)r || c >= nb) continue;  // pixels that leave the region
+      const double cnt = (double)cnt_u[i];
+      if (weight) {
+        const double v = wr * weight[c] * cnt;
+        if (v != v) continue;  // a masked bin: the position is not valid
+        atomicAdd(bal_sum + (c - (int)r), v);
+      }
+      atomicAdd(count_sum + (c - (int)r), cnt);
+    }
+  }
+}
+
+// n_valid[d] = number of positions (i, i + d) whose two bins are valid
+//            = (nb - d) - #masked in [0, nb-d) - #masked in [d, nb) + #(i: i and i+d both masked)
+__global__ void k_bad_pairs(const int32_t* __restrict__ badlist, int nbad, unsigned long long* __restrict__ both) {
+  const int64_t total = (int64_t)nbad * nbad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(i / nbad), b = (int)(i % nbad);
+    if (a <= b) atomicAdd(both + (badlist[b] - badlist[a]), 1ull);
+  }
+}
+
+__global__ void k_n_valid(const int32_t* __restrict__ badpre, const unsigned long long* __restrict__ both, int nb,
+                          int64_t* __restrict__ n_valid) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= nb) return;
+  int64_t v = nb - d;
+  if (badpre != nullptr) {
+    v -= badpre[nb - d];             // masked first bins
+    v -= badpre[nb] - badpre[d];     // masked second bins
+    v += (int64_t)both[d];           // counted twice
+  }
+  n_valid[d] = v;
+}
+
 // occ != nullptr: only query the occupancy; else launch
 template <int R, int S, int PF>
 cudaError_t launch_main_rsp(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
@@ -1931,6 +1979,88 @@ int pup_stripes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const i
   if (host_h) CK(cudaMemcpyAsync(horizontal, d_h, bytes, cudaMemcpyDeviceToHost, st));
   if (host_v) CK(cudaMemcpyAsync(vertical, d_v, bytes, cudaMemcpyDeviceToHost, st));
   if (host_h || host_v || !is_device_ptr(r0) || !is_device_ptr(c0)) CK(cudaStreamSynchronize(st));
+  return PUP_OK;
+}
+
+int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper, const int32_t* col_upper,
+                     const int32_t* count_upper, const double* weight, double* count_sum, double* balanced_sum,
+                     int64_t* n_valid, void* stream) {
+  if (nb <= 0 || nnz_upper < 0 || nnz_upper >= (1ll << 31) || !indptr_upper || (nnz_upper > 0 && (!col_upper || !count_upper)) ||
+      !count_sum || !n_valid)
+    return fail(PUP_E_ARG, "pup_expected_cis: bad sizes or null arrays");
+  if ((weight == nullptr) != (balanced_sum == nullptr))
+    return fail(PUP_E_ARG, "pup_expected_cis: weight and balanced_sum go together");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(PUP_E_NODEV, "pup_expected_cis: no such CUDA device");
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_expected_cis: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches = 0;
+  Scratch tmp(st);
+  Uploader up(st, device);
+  const void *v_ip, *v_col, *v_cnt, *v_w;
+  int rc;
+  if ((rc = up.stage(indptr_upper, ((size_t)nb + 1) * 4, &v_ip)) != PUP_OK) return rc;
+  if ((rc = up.stage(col_upper, (size_t)nnz_upper * 4, &v_col)) != PUP_OK) return rc;
+  if ((rc = up.stage(count_upper, (size_t)nnz_upper * 4, &v_cnt)) != PUP_OK) return rc;
+  if ((rc = up.stage(weight, weight ? (size_t)nb * 8 : 0, &v_w)) != PUP_OK) return rc;
+  if ((rc = up.join()) != PUP_OK) return rc;
+  const double* dw = (const double*)v_w;
+  double *d_cs = count_sum, *d_bs = balanced_sum;
+  int64_t* d_nv = n_valid;
+  const bool h_cs = !is_device_ptr(count_sum), h_bs = balanced_sum && !is_device_ptr(balanced_sum),
+             h_nv = !is_device_ptr(n_valid);
+  if (h_cs) CK(tmp.alloc((void**)&d_cs, (size_t)nb * 8));
+  if (h_bs) CK(tmp.alloc((void**)&d_bs, (size_t)nb * 8));
+  if (h_nv) CK(tmp.alloc((void**)&d_nv, (size_t)nb * 8));
+  CK(zero_async(d_cs, (size_t)nb * 8, st));
+  if (d_bs) CK(zero_async(d_bs, (size_t)nb * 8, st));
+  const int wgrid = std::min((nb + 7) / 8, 148 * 16);
+  k_diag_sums<<<wgrid, 256, 0, st>>>((const int32_t*)v_ip, (const int32_t*)v_col, (const int32_t*)v_cnt, dw, nb, d_cs,
+                                     d_bs);
+  LAUNCH_CHECK("k_diag_sums");
+  int32_t* badpre = nullptr;
+  unsigned long long* both = nullptr;
+  if (dw) {
+    uint8_t *bad, *ebad;
+    int32_t *ebad32, *bad32, *badlist;
+    CK(tmp.alloc((void**)&bad, (size_t)nb));
+    CK(tmp.alloc((void**)&ebad, (size_t)nb));
+    CK(tmp.alloc((void**)&ebad32, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&bad32, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&badpre, (size_t)(nb + 1) * 4));
+    CK(tmp.alloc((void**)&badlist, (size_t)nb * 4));
+    CK(tmp.alloc((void**)&both, (size_t)nb * 8));
+    CK(zero_async(both, (size_t)nb * 8, st));
+    k_masks<<<(nb + 1 + 255) / 256, 256, 0, st>>>(dw, nullptr, bad, ebad, ebad32, bad32, nb);
+    LAUNCH_CHECK("k_masks");
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, bad32, badpre, nb + 1, st));
+    void* t;
+    CK(tmp.alloc(&t, tb));
+    CK(cub::DeviceScan::ExclusiveSum(t, tb, bad32, badpre, nb + 1, st));
+    ++g_launches;
+    k_badlist<<<(nb + 255) / 256, 256, 0, st>>>(bad, badpre, badlist, nb);
+    LAUNCH_CHECK("k_badlist");
+    int32_t nbad = 0;  // the pair kernel's grid does not depend on it, only its loop bound: read it on the device
+    CK(cudaMemcpyAsync(&nbad, badpre + nb, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nbad > 0) {
+      k_bad_pairs<<<148 * 8, 256, 0, st>>>(badlist, nbad, both);
+      LAUNCH_CHECK("k_bad_pairs");
+    }
+  }
+  k_n_valid<<<(nb + 255) / 256, 256, 0, st>>>(badpre, both, nb, d_nv);
+  LAUNCH_CHECK("k_n_valid");
+  if (h_cs) CK(cudaMemcpyAsync(count_sum, d_cs, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+  if (h_bs) CK(cudaMemcpyAsync(balanced_sum, d_bs, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+  if (h_nv) CK(cudaMemcpyAsync(n_valid, d_nv, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+  const bool host_in = !is_device_ptr(indptr_upper) || (nnz_upper > 0 && (!is_device_ptr(col_upper) || !is_device_ptr(count_upper))) ||
+                       (weight && !is_device_ptr(weight));
+  if (h_cs || h_bs || h_nv || host_in) CK(cudaStreamSynchronize(st));
   return PUP_OK;
 }
 

@@ -63,3 +63,36 @@ def expected_cis(clr, view_df=None, clr_weight_name=None, ignore_diags=2):
                 tab["balanced.avg"] = bs / n_valid
         rows.append(pd.DataFrame(tab))
     return pd.concat(rows, ignore_index=True)
+
+
+def expected_cis_gpu(clr, view_df=None, clr_weight_name=None, ignore_diags=2, device=0):
+    """Same table as :func:`expected_cis`, with the per-diagonal sums computed on the GPU (``pup_expected_cis``) from
+    the cooler's upper triangle as stored (needs a reader with ``region_upper_csr``, e.g. ``coolio.Cooler``)."""
+    from . import _native
+
+    _native.require_device()
+    if view_df is None:
+        names = list(clr.chromnames)
+        view_df = pd.DataFrame(
+            {"chrom": names, "start": 0, "end": [int(clr.chromsizes[c]) for c in names], "name": names}
+        )
+    rows = []
+    for chrom, start, end, name in zip(view_df["chrom"], view_df["start"], view_df["end"], view_df["name"]):
+        lo, hi = clr.extent((chrom, start, end))
+        nb = hi - lo
+        indptr, col, cnt = clr.region_upper_csr(lo, hi)
+        w = None
+        if clr_weight_name:
+            w = np.ascontiguousarray(np.asarray(clr._bin_column(clr_weight_name), dtype=np.float64)[lo:hi])
+        cs, bs, nv = _native.expected_cis_sums(device, nb, indptr, col, cnt, w)
+        tab = {"region1": name, "region2": name, "dist": np.arange(nb), "n_valid": nv}
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cs[:ignore_diags] = np.nan
+            tab["count.sum"] = cs
+            tab["count.avg"] = cs / nv
+            if bs is not None:
+                bs[:ignore_diags] = np.nan
+                tab["balanced.sum"] = bs
+                tab["balanced.avg"] = bs / nv
+        rows.append(pd.DataFrame(tab))
+    return pd.concat(rows, ignore_index=True)

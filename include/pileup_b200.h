@@ -161,6 +161,19 @@ int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stre
 int pup_stripes(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0, int W,
                 double* horizontal, double* vertical, void* stream);
 
+/*
+ * Per-diagonal sums of one view region, the arithmetic of `cooltools expected-cis` whose table the reference takes
+ * through --expected / expected_df (CLI.py:484-508, coolpup.py:861-918), from the region's upper triangle as cooler
+ * stores it (same layout as pup_region_create_upper; columns >= nb are ignored).  Outputs, host or device, [nb] each:
+ *   count_sum[d]     sum of raw counts on diagonal d over positions whose two bins are valid
+ *   balanced_sum[d]  sum of (weight[row] * weight[col]) * count; NULL exactly when weight is NULL
+ *   n_valid[d]       number of positions (i, i + d) whose two bins are valid (all nb - d without weights)
+ * A bin is valid when its weight is not NaN.  expected = sum / n_valid; masking the first diagonals is the caller's.
+ */
+int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper, const int32_t* col_upper,
+                     const int32_t* count_upper, const double* weight, double* count_sum, double* balanced_sum,
+                     int64_t* n_valid, void* stream);
+
 /* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
  * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */
 int pup_last_launches(void);

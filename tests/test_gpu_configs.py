@@ -89,3 +89,43 @@ def test_config3_shape_controls_allpairs_pad41(genome):
         pups = cp.pileup(clr, sites, **kw)
         ref = oracle_pileup(clr, sites, **kw)
     _compare(pups, ref)
+
+
+@pytest.mark.parametrize("fixture,weight", [("CN.mm9.1000kb.cool", "weight"), ("CN.mm9.1000kb.cool", None),
+                                            ("Scc1-control.10000.cool", None)])
+def test_expected_cis_on_gpu_matches_numpy(fixture, weight):
+    """pup_expected_cis (per-diagonal sums + valid-pair counts on the device) == the numpy restatement of
+    cooltools expected-cis that the golden cases use."""
+    import os
+
+    import pandas as pd
+
+    from coolpuppy_b200 import _native
+    from coolpuppy_b200.coolio import Cooler
+    from coolpuppy_b200.expected import expected_cis, expected_cis_gpu
+
+    if _native.device_count() < 1:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    clr = Cooler(os.path.join(os.path.dirname(__file__), "fixtures", fixture))
+    names = list(clr.chromnames)[:4]
+    view = pd.DataFrame({"chrom": names, "start": 0, "end": [int(clr.chromsizes[c]) for c in names], "name": names})
+    # an arm-like sub-region too: pixels that leave the region must be ignored
+    view.loc[len(view)] = [names[0], 0, int(clr.chromsizes[names[0]]) // 2 // clr.binsize * clr.binsize, "half"]
+    a = expected_cis(clr, view_df=view, clr_weight_name=weight, ignore_diags=2)
+    b = expected_cis_gpu(clr, view_df=view, clr_weight_name=weight, ignore_diags=2)
+    assert list(a.columns) == list(b.columns) and len(a) == len(b)
+    assert np.array_equal(a["n_valid"].values, b["n_valid"].values)
+    for c in a.columns:
+        if c.endswith((".sum", ".avg")):
+            np.testing.assert_allclose(b[c].values, a[c].values, rtol=1e-10, equal_nan=True)
+
+
+def test_expected_cis_gpu_on_synthetic_genome(genome):
+    from coolpuppy_b200.expected import expected_cis, expected_cis_gpu
+
+    (clr, exp), sizes = genome
+    a = expected_cis(clr, clr_weight_name="weight", ignore_diags=2)
+    b = expected_cis_gpu(clr, clr_weight_name="weight", ignore_diags=2)
+    assert np.array_equal(a["n_valid"].values, b["n_valid"].values)
+    np.testing.assert_allclose(b["balanced.avg"].values, a["balanced.avg"].values, rtol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(b["count.sum"].values, a["count.sum"].values, rtol=1e-10, equal_nan=True)

@@ -169,17 +169,19 @@ def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots)
     np.testing.assert_allclose(ver, ever, rtol=RTOL, equal_nan=True)
 
 
+@pytest.mark.parametrize("ignore_diags", [2, 0, -4])
 @pytest.mark.parametrize("nb,W,dens", [(300, 21, 30), (900, 83, 300), (64, 5, 2), (2000, 11, 1)])
-def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens):
+def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens, ignore_diags):
     """pup_region_create_upper (cooler's stored upper triangle, incl. pixels that leave the region) gives the same
-    accumulators as the symmetric-CSR entry point and as the oracle."""
+    accumulators as the symmetric-CSR entry point and as the oracle.  ignore_diags >= 0: the diagonal mask removes
+    the lower triangle and nothing is mirrored; ignore_diags < 0: the lower triangle is mirrored in on the device."""
     nat = _cuda()
     from oracle.pileup_oracle import oracle_accumulate
 
     n_slots = 3
     ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb, nan_frac=0.05, with_expected=True)
-    r0, c0, sl = random_windows(nb, W, 600, n_slots, seed=nb + 1)
-    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+    r0, c0, sl = random_windows(nb, W, 600, n_slots, seed=nb + 1, near_diag_frac=0.5)
+    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, ignore_diags, n_slots, ooe=True)
     # build the upper triangle the way a cooler holds it: rows of a LARGER matrix, so some columns are >= nb
     rows = np.repeat(np.arange(nb), np.diff(ip))
     up = col >= rows
@@ -197,7 +199,7 @@ def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens):
     stride = nat.acc_stride(W)
     for memory in ("host", "device"):
         if memory == "host":
-            reg = nat.Region(0, nb, uip, uc, uv, w, e, None, ignore_diags=2, flags=nat.PUP_F_OOE, upper=True)
+            reg = nat.Region(0, nb, uip, uc, uv, w, e, None, ignore_diags=ignore_diags, flags=nat.PUP_F_OOE, upper=True)
             acc = np.zeros(n_slots * stride)
             nv = reg.accumulate(r0, c0, sl, W, n_slots, 0, acc, want_n_valid=True)
         else:
@@ -207,7 +209,7 @@ def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens):
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
             tens = [t(x) for x in (uip, uc, uv, w, e, r0, c0, sl)]
             stream = torch.cuda.current_stream(dev).cuda_stream
-            reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], None, ignore_diags=2,
+            reg = nat.Region(0, nb, tens[0], tens[1], tens[2], tens[3], tens[4], None, ignore_diags=ignore_diags,
                              flags=nat.PUP_F_OOE, stream=stream, upper=True)
             acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
             nv = reg.accumulate(tens[5], tens[6], tens[7], W, n_slots, 0, acc, stream=stream, want_n_valid=True)
