@@ -66,6 +66,17 @@ CASES = {
     "scc1_loops_stripes_ctrl": {**SCC1, "features": "CH12_loops_Rao.bed", "features_schema": "bedpe6",
                                 "kwargs": dict(features_format="bedpe", clr_weight_name=None, flank=50_000, nshifts=1, seed=5,
                                                maxdist=400_000, store_stripes=True)},
+    # ---- ignore_diags other than the default 2 (0: only the lower triangle is masked, the diagonal stays)
+    "toy_igd0_strand": {**TOY, "kwargs": {**TOYKW, "by_strand": True, "min_diag": 0}},
+    "toy_igd3_ooe_stripes": {**TOY, "expected": "CN.mm9.toy_expected.tsv",
+                             "kwargs": {**TOYKW, "ooe": True, "min_diag": 3, "store_stripes": True}},
+    "toy_local_igd0_raw_ctrl": {**TOY, "kwargs": {"features_format": "bed", "flank": 3_000_000, "local": True, "clr_weight_name": None,
+                                                 "min_diag": 0, "nshifts": 2, "seed": 6}},
+    "scc1_loops_igd0": {**SCC1, "features": "CH12_loops_Rao.bed", "features_schema": "bedpe6",
+                        "kwargs": dict(features_format="bedpe", clr_weight_name=None, flank=100_000, mindist=0, min_diag=0)},
+    "scc1_loops_igd5_ctrl": {**SCC1, "features": "CH12_loops_Rao.bed", "features_schema": "bedpe6",
+                             "kwargs": dict(features_format="bedpe", clr_weight_name=None, flank=100_000, mindist=0, min_diag=5,
+                                            nshifts=2, seed=8)},
     "scc1_ctcf_pairs_arms": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "view": "scc1_arms_view.bed",
                              "kwargs": dict(features_format="bed", clr_weight_name=None, flank=50_000, mindist=0, maxdist=2_000_000,
                                             nshifts=1, seed=4)},
