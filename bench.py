@@ -283,14 +283,10 @@ def main():
     # to different ranks with the matrix replicated (windows are independent, the accumulators add up);
     # otherwise chr1 alone (13 % of the work) caps 8 ranks at 7.6x.  The e2e pass keeps whole chromosomes per rank:
     # there the matrix upload, not the pile-up, is the cost of a unit.
-    units, ucost = [], []
-    share = sum(cost) / max(world, 1)
-    for c, k in zip(names, cost):
-        parts = 1 if world == 1 else int(min(world, max(1, np.ceil(k / (0.5 * share)))))
-        for part in range(parts):
-            units.append((c, part, parts))
-            ucost.append(k / parts)
-    uowner = lpt(ucost, world if args.impl == "b200" else 1)
+    from coolpuppy_b200.multigpu import part_bounds, split_heavy
+
+    iunits, ucost, uowner = split_heavy(cost, world if args.impl == "b200" else 1)
+    units = [(names[i], part, parts) for i, part, parts in iunits]
     my_units = [u for u, o in zip(units, uowner) if o == (rank if args.impl == "b200" else 0)]
     split = sorted({c for c, _, n in units if n > 1}, key=names.index)
     if split:
@@ -321,8 +317,7 @@ def main():
         del t
     for c, part, parts in my_units:
         w = windows[c]
-        n = len(w["r0"])
-        lo, hi = (n * part) // parts, (n * (part + 1)) // parts
+        lo, hi = part_bounds(len(w["r0"]), part, parts)
         dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][lo:hi])).to(dev) for k in ("r0", "c0", "slot"))
     torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()

@@ -24,6 +24,29 @@ def lpt_assign(costs, n_ranks):
     return owner
 
 
+def split_heavy(costs, n_ranks, max_share=0.5):
+    """Work units for ``n_ranks`` ranks: item ``i`` is cut into ``parts`` equal parts when its cost exceeds
+    ``max_share`` of a rank's fair share (a region's *window list* can be split across GPUs with its matrix
+    replicated, because windows are independent and the accumulators add up).  Returns
+    ``(units, unit_costs, owners)`` with ``units[j] = (item, part, parts)`` and ``owners[j]`` the LPT rank of unit ``j``;
+    part ``p`` of an item with ``n`` windows covers ``[n * p // parts, n * (p + 1) // parts)``."""
+    units, ucost = [], []
+    share = float(sum(costs)) / max(n_ranks, 1)
+    for i, k in enumerate(costs):
+        parts = 1
+        if n_ranks > 1 and share > 0:
+            parts = int(min(n_ranks, max(1, np.ceil(float(k) / (max_share * share)))))
+        for part in range(parts):
+            units.append((i, part, parts))
+            ucost.append(float(k) / parts)
+    return units, ucost, lpt_assign(ucost, n_ranks)
+
+
+def part_bounds(n, part, parts):
+    """Half-open window range of part ``part`` of ``parts`` of a list of ``n`` windows."""
+    return (n * part) // parts, (n * (part + 1)) // parts
+
+
 class RegionSharder:
     """Deterministic region -> rank assignment + the collectives the pile-up needs."""
 

@@ -64,3 +64,29 @@ def test_two_rank_gloo_pileup_matches_golden(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"RESULT {r} True" in o, o
+
+
+def test_split_heavy_units_cover_every_window_once_and_balance():
+    """bench.py's N-GPU sharding: heavy regions are cut by windows; every window belongs to exactly one unit."""
+    import numpy as np
+
+    from coolpuppy_b200.multigpu import part_bounds, split_heavy
+    from coolpuppy_b200.synthetic import HG38
+
+    nb = np.array([-(-v // 10_000) for v in HG38.values()], dtype=np.float64)
+    nwin = np.round(1.1e7 * nb**2 / (nb**2).sum()).astype(int)  # all-vs-all pairs ~ n^2
+    cost = list(nwin * nb / 1e4)
+    for world in (1, 2, 4, 8):
+        units, ucost, owner = split_heavy(cost, world)
+        assert len(units) == len(ucost) == len(owner)
+        if world == 1:
+            assert units == [(i, 0, 1) for i in range(len(cost))]
+        covered = [np.zeros(n, dtype=int) for n in nwin]
+        for (i, part, parts), o in zip(units, owner):
+            assert 0 <= o < world and 0 <= part < parts <= world
+            lo, hi = part_bounds(int(nwin[i]), part, parts)
+            covered[i][lo:hi] += 1
+        assert all((c == 1).all() for c in covered)
+        load = np.bincount(owner, weights=ucost, minlength=world)
+        assert load.max() <= 1.06 * sum(cost) / world  # whole chromosomes only: 1.17 at 8 ranks
+        assert abs(sum(ucost) - sum(cost)) < 1e-6 * sum(cost)
