@@ -196,24 +196,32 @@ def build_region_windows(cc, region, control):
     if nctrl == 0 or i_arr.shape[0] == 0:
         kind = np.zeros(k_arr.shape[0], dtype=np.int8)
         return RegionWindows(region, sel, stbin[k_arr], stbin[l_arr], kind, k_arr, l_arr, dist, paired=True)
-    # controls are drawn once per offset block, ROI rows of the block first, then its nshifts replicas
+    # controls are drawn once per offset block, ROI rows of the block first, then its nshifts replicas.  Only the
+    # np.random calls (whose sizes and order pin the reference's stream, coolpup.py:392-396, 697-699) run per block;
+    # the block layout itself is computed for all blocks at once.
     q = np.bincount(i_arr, minlength=nfeat)
-    block_start = np.concatenate([[0], np.cumsum(q)])
-    parts_k, parts_l, parts_shift, parts_kind = [], [], [], []
-    for i in np.nonzero(q)[0]:
-        a, b = block_start[i], block_start[i + 1]
-        n = int(q[i])
-        dbin = _draw_shifts(n * nctrl, cc.minshift, cc.maxshift, res)
-        kk, ll = k_arr[a:b], l_arr[a:b]
-        parts_k.append(np.concatenate([kk, np.tile(kk, nctrl)]))
-        parts_l.append(np.concatenate([ll, np.tile(ll, nctrl)]))
-        parts_shift.append(np.concatenate([np.zeros(n, dtype=np.int64), dbin]))
-        kd = np.ones(n * (nctrl + 1), dtype=np.int8)
-        kd[:n] = 0
-        parts_kind.append(kd)
-    kk = np.concatenate(parts_k)
-    ll = np.concatenate(parts_l)
-    sh = np.concatenate(parts_shift)
-    kind = np.concatenate(parts_kind)
-    dist_all = center[ll] - center[kk]
+    blocks = np.nonzero(q)[0]
+    nq = q[blocks].astype(np.int64)                      # ROI rows per block
+    n_ctrl_total = int(nq.sum()) * nctrl
+    shift = np.empty(n_ctrl_total, dtype=np.int64)
+    sign = np.empty(n_ctrl_total, dtype=np.int64)
+    pos = 0
+    for n in nq * nctrl:
+        n = int(n)
+        shift[pos : pos + n] = np.random.randint(cc.minshift, cc.maxshift, n)
+        sign[pos : pos + n] = np.random.choice([-1, 1], n)
+        pos += n
+    dbin = np.round(shift * sign / res).astype(np.int64)
+    src_start = np.concatenate([[0], np.cumsum(nq)[:-1]])  # first ROI row of every block in k_arr / l_arr
+    out_len = nq * (nctrl + 1)
+    out_start = np.concatenate([[0], np.cumsum(out_len)[:-1]])
+    blk = np.repeat(np.arange(blocks.shape[0], dtype=np.int64), out_len)
+    j = np.arange(int(out_len.sum()), dtype=np.int64) - out_start[blk]
+    src = src_start[blk] + j % nq[blk]
+    kind = (j >= nq[blk]).astype(np.int8)
+    sh = np.zeros(j.shape[0], dtype=np.int64)
+    sh[kind == 1] = dbin  # the control part of a block is contiguous and in draw order
+    kk = k_arr[src]
+    ll = l_arr[src]
+    dist_all = dist[src]
     return RegionWindows(region, sel, stbin[kk] + sh, stbin[ll] + sh, kind, kk, ll, dist_all, paired=True)
