@@ -10,8 +10,9 @@ A step = one pass of the hot path over every window of every chromosome:
   value : region matrices and window arrays resident in HBM; per chromosome pup_accumulate() = device sort of the
           windows + vector kernel + main pile-up kernel; N > 1: chromosomes sharded over ranks (LPT), one NCCL
           all-reduce of the accumulators inside the timed region.
-  e2e   : the same pass through pup_accumulate_region() with HOST (pinned) CSR / weight / window buffers, i.e.
-          including the H2D upload + device-side indexing of every chromosome and the D2H read of the accumulators.
+  e2e   : the same pass through pup_region_create_upper() + pup_upload() + pup_accumulate() with HOST (pinned)
+          upper-triangle CSR / weight / window buffers, i.e. including the H2D upload + device-side indexing of every
+          chromosome and the D2H read of the accumulators.
   cpu_baseline / --impl reference : the restated reference path (oracle/pileup_oracle.py: scipy-CSR slice per
           window, NaN masks, nansum) on the host cores, on a bounded uniform sample of the same windows.
 """

@@ -126,7 +126,8 @@ class Region:
     def __init__(self, device, nb, indptr, col, count, weight=None, expected=None, coverage=None, ignore_diags=2,
                  flags=0, stream=0, upper=False):
         """``upper=True``: ``indptr/col/count`` hold the upper triangle as cooler stores it (columns >= nb are
-        dropped, the lower triangle is mirrored in on the device); else the symmetric-filled CSR."""
+        dropped; the lower triangle is mirrored in on the device only when the diagonal mask keeps it, i.e.
+        ``ignore_diags < 0``); else the symmetric-filled CSR."""
         self._h = C.c_void_p()
         self.nb = int(nb)
         self.nnz = int(col.shape[0]) if col is not None else 0

@@ -434,7 +434,7 @@ class PileUpper:
         nb = hi - lo
         upper = False
         if hasattr(self.clr, "region_upper_csr"):
-            indptr, col, cnt = self.clr.region_upper_csr(lo, hi)  # mirrored into a symmetric CSR on the device
+            indptr, col, cnt = self.clr.region_upper_csr(lo, hi)  # indexed as stored (pup_region_create_upper)
             upper = True
         else:  # a real cooler.Cooler
             m = self.clr.matrix(sparse=True, balance=False).fetch((r["chrom"], r["start"], r["end"])).tocsr()
