@@ -90,3 +90,57 @@ def test_split_heavy_units_cover_every_window_once_and_balance():
         load = np.bincount(owner, weights=ucost, minlength=world)
         assert load.max() <= 1.06 * sum(cost) / world  # whole chromosomes only: 1.17 at 8 ranks
         assert abs(sum(ucost) - sum(cost)) < 1e-6 * sum(cost)
+
+
+SPLIT_WORKER = textwrap.dedent(
+    """
+    import os, sys
+    sys.path[:0] = [{root!r}, os.path.join({root!r}, "tests")]
+    import numpy as np, torch
+    import torch.distributed as dist
+    rank = int(sys.argv[1])
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+    import emulator
+    from synth import random_region, random_windows
+    from coolpuppy_b200.multigpu import part_bounds, split_heavy
+    from oracle.pileup_oracle import oracle_accumulate
+    W, n_slots = 11, 3
+    stride = emulator.layout(W)["stride"]
+    regs, wins, ref = [], [], None
+    for k, (nb, dens, nwin) in enumerate([(400, 40, 900), (120, 10, 60), (90, 8, 40)]):
+        ip, col, cnt, w, e, cov = random_region(nb, dens, seed=k, nan_frac=0.05, with_expected=True)
+        r0, c0, sl = random_windows(nb, W, nwin, n_slots, seed=10 + k)
+        regs.append(emulator.EmuRegion(0, nb, ip, col, cnt, w, e, None, ignore_diags=2, flags=1))
+        wins.append((r0, c0, sl))
+        o = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+        ref = o if ref is None else {{f: ref[f] + o[f] for f in ("sum", "num", "n")}}
+    units, ucost, owner = split_heavy([len(w[0]) * r.nb for w, r in zip(wins, regs)], 2)
+    assert any(parts > 1 for _, _, parts in units)          # the big region is cut by windows
+    acc = torch.zeros(n_slots * stride, dtype=torch.float64)
+    for (i, part, parts), o in zip(units, owner):
+        if o != rank:
+            continue
+        lo, hi = part_bounds(len(wins[i][0]), part, parts)
+        regs[i].accumulate(wins[i][0][lo:hi], wins[i][1][lo:hi], wins[i][2][lo:hi], W, n_slots, 0, acc)
+    dist.all_reduce(acc)
+    out = emulator.emu_export(acc, W, n_slots)
+    ok = np.array_equal(out["n"], ref["n"]) and np.array_equal(out["num"], ref["num"])
+    m = np.isfinite(ref["sum"])
+    ok &= np.allclose(out["sum"][m], ref["sum"][m], rtol=1e-9)
+    print("RESULT", rank, bool(ok))
+    dist.destroy_process_group()
+    """
+)
+
+
+def test_two_rank_gloo_window_split_units(tmp_path):
+    """A region's window list split across two ranks (matrix replicated) + one all-reduce == all windows on one rank."""
+    port = 31500 + os.getpid() % 2000
+    script = tmp_path / "split_worker.py"
+    script.write_text(SPLIT_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"RESULT {r} True" in o, o
