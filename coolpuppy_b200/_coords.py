@@ -129,18 +129,6 @@ def _draw_shifts(n, minshift, maxshift, resolution):
     return np.round(shift / resolution).astype(np.int64)
 
 
-def pair_offsets(m):
-    """All ordered pairs (k, k+i), ordered by offset i then k (coolpup.py:682-689)."""
-    if m < 2:
-        z = np.zeros(0, dtype=np.int64)
-        return z, z
-    counts = np.arange(m - 1, 0, -1, dtype=np.int64)  # offset i = 1..m-1 has m-i pairs
-    i_arr = np.repeat(np.arange(1, m, dtype=np.int64), counts)
-    starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
-    k_arr = np.arange(i_arr.shape[0], dtype=np.int64) - np.repeat(starts, counts)
-    return i_arr, k_arr
-
-
 def build_region_windows(cc, region, control):
     """Windows of one view region ``(chrom, start, end)`` (reference: coolpup.py:546-563, 598-746)."""
     chrom, start, end = region
@@ -187,41 +175,25 @@ def build_region_windows(cc, region, control):
             idx = np.concatenate([idx, cidx])
         return RegionWindows(region, sel, st1, st2, kind, idx, idx, None, paired=True)
 
-    i_arr, k_arr = pair_offsets(nfeat)
-    l_arr = k_arr + i_arr
+    # all ordered pairs (k, k + i), by offset i then k, distance-filtered; per offset block the ROI rows, then the
+    # nshifts shifted replicas.  The layout is native host code (pup_pair_windows_*); only the np.random calls, whose
+    # sizes and order pin the reference's stream (coolpup.py:392-396, 697-699: one draw per offset), stay here.
+    from . import _native
+
     center = sel["center"].values.astype(np.float64)
-    dist = center[l_arr] - center[k_arr]
-    keep = (cc.mindist <= np.abs(dist)) & (np.abs(dist) <= cc.maxdist)
-    i_arr, k_arr, l_arr, dist = i_arr[keep], k_arr[keep], l_arr[keep], dist[keep]
-    if nctrl == 0 or i_arr.shape[0] == 0:
-        kind = np.zeros(k_arr.shape[0], dtype=np.int8)
-        return RegionWindows(region, sel, stbin[k_arr], stbin[l_arr], kind, k_arr, l_arr, dist, paired=True)
-    # controls are drawn once per offset block, ROI rows of the block first, then its nshifts replicas.  Only the
-    # np.random calls (whose sizes and order pin the reference's stream, coolpup.py:392-396, 697-699) run per block;
-    # the block layout itself is computed for all blocks at once.
-    q = np.bincount(i_arr, minlength=nfeat)
-    blocks = np.nonzero(q)[0]
-    nq = q[blocks].astype(np.int64)                      # ROI rows per block
-    n_ctrl_total = int(nq.sum()) * nctrl
-    shift = np.empty(n_ctrl_total, dtype=np.int64)
-    sign = np.empty(n_ctrl_total, dtype=np.int64)
-    pos = 0
-    for n in nq * nctrl:
-        n = int(n)
-        shift[pos : pos + n] = np.random.randint(cc.minshift, cc.maxshift, n)
-        sign[pos : pos + n] = np.random.choice([-1, 1], n)
-        pos += n
-    dbin = np.round(shift * sign / res).astype(np.int64)
-    src_start = np.concatenate([[0], np.cumsum(nq)[:-1]])  # first ROI row of every block in k_arr / l_arr
-    out_len = nq * (nctrl + 1)
-    out_start = np.concatenate([[0], np.cumsum(out_len)[:-1]])
-    blk = np.repeat(np.arange(blocks.shape[0], dtype=np.int64), out_len)
-    j = np.arange(int(out_len.sum()), dtype=np.int64) - out_start[blk]
-    src = src_start[blk] + j % nq[blk]
-    kind = (j >= nq[blk]).astype(np.int8)
-    sh = np.zeros(j.shape[0], dtype=np.int64)
-    sh[kind == 1] = dbin  # the control part of a block is contiguous and in draw order
-    kk = k_arr[src]
-    ll = l_arr[src]
-    dist_all = dist[src]
-    return RegionWindows(region, sel, stbin[kk] + sh, stbin[ll] + sh, kind, kk, ll, dist_all, paired=True)
+    q, total = _native.pair_windows_count(center, cc.mindist, cc.maxdist)
+    dbin = None
+    if nctrl > 0 and total > 0:
+        shift = np.empty(total * nctrl, dtype=np.int64)
+        sign = np.empty(total * nctrl, dtype=np.int64)
+        pos = 0
+        for n in q[q > 0] * nctrl:
+            n = int(n)
+            shift[pos : pos + n] = np.random.randint(cc.minshift, cc.maxshift, n)
+            sign[pos : pos + n] = np.random.choice([-1, 1], n)
+            pos += n
+        dbin = np.round(shift * sign / res).astype(np.int64)
+    else:
+        nctrl = 0
+    st1, st2, kind, kk, ll, dist_all = _native.pair_windows_fill(stbin, center, cc.mindist, cc.maxdist, nctrl, dbin, total)
+    return RegionWindows(region, sel, st1, st2, kind, kk, ll, dist_all, paired=True)

@@ -21,7 +21,7 @@ _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200
 
 SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",
-    "pup_region_destroy", "pup_upload", "pup_expected_cis",
+    "pup_region_destroy", "pup_upload", "pup_expected_cis", "pup_pair_windows_count", "pup_pair_windows_fill",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
 ]
@@ -51,6 +51,9 @@ def lib():
     L.pup_region_destroy.argtypes = [vp]
     L.pup_upload.argtypes = [C.c_int, vp, vp, i64, vp]
     L.pup_expected_cis.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pup_pair_windows_count.argtypes = [i32, vp, C.c_double, C.c_double, vp]
+    L.pup_pair_windows_count.restype = i64
+    L.pup_pair_windows_fill.argtypes = [i32, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
     L.pup_acc_stride.argtypes = [C.c_int]
@@ -192,6 +195,32 @@ def upload(device, dst, src, stream=0):
     tensor ``dst`` through the library's upload stream (FIFO with the region matrices); ``stream`` waits for it."""
     nbytes = src.numel() * src.element_size() if hasattr(src, "numel") else src.nbytes
     check(lib().pup_upload(device, ptr(dst), ptr(src), int(nbytes), stream))
+
+
+def pair_windows_count(center, mindist, maxdist):
+    """``pup_pair_windows_count`` (host code): kept all-vs-all pairs per offset, int64[m]."""
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    q = np.zeros(max(1, center.shape[0]), dtype=np.int64)
+    total = lib().pup_pair_windows_count(int(center.shape[0]), ptr(center), float(mindist), float(maxdist), ptr(q))
+    if total < 0:
+        raise NativeError(f"libpileup_b200: {lib().pup_last_error().decode()}")
+    return q[: center.shape[0]], int(total)
+
+
+def pair_windows_fill(stbin, center, mindist, maxdist, nctrl, dbin, total):
+    """``pup_pair_windows_fill`` (host code): ``(st1, st2, kind, idx1, idx2, distance)`` of the region's windows."""
+    stbin = np.ascontiguousarray(stbin, dtype=np.int64)
+    center = np.ascontiguousarray(center, dtype=np.float64)
+    n = int(total) * (1 + int(nctrl))
+    st1, st2 = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    kind = np.empty(n, dtype=np.int8)
+    i1, i2 = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    dist = np.empty(n, dtype=np.float64)
+    if dbin is not None:
+        dbin = np.ascontiguousarray(dbin, dtype=np.int64)
+    check(lib().pup_pair_windows_fill(int(center.shape[0]), ptr(stbin), ptr(center), float(mindist), float(maxdist),
+                                      int(nctrl), ptr(dbin), ptr(st1), ptr(st2), ptr(kind), ptr(i1), ptr(i2), ptr(dist)))
+    return st1, st2, kind, i1, i2, dist
 
 
 def expected_cis_sums(device, nb, indptr_upper, col_upper, count_upper, weight=None, stream=0):

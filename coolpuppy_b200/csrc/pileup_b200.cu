@@ -2064,6 +2064,61 @@ int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* i
   return PUP_OK;
 }
 
+// ------------------------------------------------------------------------------------------ host-side window layout
+// (plain host code: no device involved)
+int64_t pup_pair_windows_count(int32_t m, const double* center, double mindist, double maxdist, int64_t* per_offset) {
+  if (m < 0 || (m > 0 && (!center || !per_offset))) {
+    fail(PUP_E_ARG, "pup_pair_windows_count: bad arguments");
+    return -1;
+  }
+  int64_t total = 0;
+  if (m > 0) per_offset[0] = 0;
+  for (int32_t i = 1; i < m; ++i) {
+    int64_t q = 0;
+    for (int32_t k = 0; k + i < m; ++k) {
+      const double d = std::fabs(center[k + i] - center[k]);
+      q += (mindist <= d && d <= maxdist) ? 1 : 0;
+    }
+    per_offset[i] = q;
+    total += q;
+  }
+  return total;
+}
+
+int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center, double mindist, double maxdist,
+                          int32_t nctrl, const int64_t* dbin, int64_t* st1, int64_t* st2, int8_t* kind, int64_t* idx1,
+                          int64_t* idx2, double* distance) {
+  if (m < 0 || nctrl < 0 || (m > 1 && (!stbin || !center || !st1 || !st2 || !kind || !idx1 || !idx2 || !distance)))
+    return fail(PUP_E_ARG, "pup_pair_windows_fill: bad arguments");
+  int64_t out = 0, drawn = 0;
+  std::vector<int32_t> ks;
+  for (int32_t i = 1; i < m; ++i) {
+    ks.clear();
+    for (int32_t k = 0; k + i < m; ++k) {
+      const double d = std::fabs(center[k + i] - center[k]);
+      if (mindist <= d && d <= maxdist) ks.push_back(k);
+    }
+    const int64_t n = (int64_t)ks.size();
+    if (n == 0) continue;
+    if (nctrl > 0 && !dbin) return fail(PUP_E_ARG, "pup_pair_windows_fill: control shifts missing");
+    for (int32_t rep = 0; rep <= nctrl; ++rep) {  // rep 0: the ROI rows of the block, then its nctrl shifted replicas
+      for (int64_t j = 0; j < n; ++j) {
+        const int32_t k = ks[(size_t)j], l = k + i;
+        const int64_t sh = rep == 0 ? 0 : dbin[drawn + (int64_t)(rep - 1) * n + j];
+        st1[out] = stbin[k] + sh;
+        st2[out] = stbin[l] + sh;
+        kind[out] = rep == 0 ? 0 : 1;
+        idx1[out] = k;
+        idx2[out] = l;
+        distance[out] = center[l] - center[k];
+        ++out;
+      }
+    }
+    drawn += n * nctrl;
+  }
+  return PUP_OK;
+}
+
 int pup_algorithmic_bytes(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0, int W,
                           unsigned flags, void* stream, int64_t* bytes_out, int64_t* nnz_out) {
   if (!m || n_win < 0 || W <= 0 || !bytes_out) return fail(PUP_E_ARG, "pup_algorithmic_bytes: bad arguments");

@@ -174,6 +174,24 @@ int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* i
                      const int32_t* count_upper, const double* weight, double* count_sum, double* balanced_sum,
                      int64_t* n_valid, void* stream);
 
+/*
+ * Host-side window layout of one view region for bed features paired all-vs-all (replaces the pair loop of
+ * CoordCreator.get_combinations and the row replication of _control_regions, coolpup.py:682-714, 387-453).  Plain
+ * host code.  The m features of the region are sorted by position; pairs (k, k + i) are emitted by offset i = 1..m-1,
+ * then k, and kept when mindist <= |center[k+i] - center[k]| <= maxdist.
+ *   pup_pair_windows_count: per_offset[i] = kept pairs of offset i (per_offset[0] = 0); returns their total (-1 on bad
+ *       arguments).  The caller draws the control shifts per offset with exactly these sizes (per_offset[i] * nctrl),
+ *       which is what pins the reference's np.random stream.
+ *   pup_pair_windows_fill: per offset block the ROI rows, then nctrl replicas shifted by dbin (block order, replica-
+ *       major: dbin of block i starts after the draws of the previous blocks); outputs have
+ *       total * (1 + nctrl) entries: st1 / st2 = first row / column bin (stbin + shift), kind (0 ROI, 1 control),
+ *       idx1 / idx2 = feature indices k, l, distance = center[l] - center[k].
+ */
+int64_t pup_pair_windows_count(int32_t m, const double* center, double mindist, double maxdist, int64_t* per_offset);
+int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center, double mindist, double maxdist,
+                          int32_t nctrl, const int64_t* dbin, int64_t* st1, int64_t* st2, int8_t* kind, int64_t* idx1,
+                          int64_t* idx2, double* distance);
+
 /* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
  * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */
 int pup_last_launches(void);

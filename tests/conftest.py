@@ -11,6 +11,10 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the host pipeline calls into libpileup_b200.so (window layout is native host code): build it when missing
+    from coolpuppy_b200.build import build_native
+
+    build_native(force=False)
 
 
 @pytest.fixture(scope="session")

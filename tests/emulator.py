@@ -213,9 +213,17 @@ def install(monkeypatch):
     monkeypatch.setattr(_native, "current_stream", lambda device: 0)
     monkeypatch.setattr(_native, "acc_stride", lambda W: layout(int(W))["stride"])
 
+    real = _native.lib()  # host-side entry points (window layout) are the real library: they need no device
+
     class _L:
         @staticmethod
         def pup_last_launches():
             return 0
 
-    monkeypatch.setattr(_native, "lib", lambda: _L)
+        def __getattr__(self, name):
+            if name.startswith("pup_pair_windows") or name == "pup_last_error":
+                return getattr(real, name)
+            raise AttributeError(name)
+
+    stub = _L()
+    monkeypatch.setattr(_native, "lib", lambda: stub)

@@ -68,3 +68,44 @@ def test_bad_arguments_are_rejected_before_any_device_work():
     assert out["n"].tolist() == [4, 0]
     assert np.array_equal(out["sum"][0], np.arange(9.0).reshape(3, 3))
     assert out["num"][0].tolist() == [[2, 2, 1], [3, 3, 1], [3, 3, 1]]
+
+
+def test_pair_window_layout_host_code_matches_numpy():
+    """pup_pair_windows_count / _fill (plain host code, no device) against a direct numpy restatement of the pair loop
+    of CoordCreator.get_combinations + _control_regions (coolpup.py:682-714, 387-453)."""
+    rng = np.random.default_rng(5)
+    for m, nctrl in [(0, 2), (1, 0), (2, 3), (37, 0), (60, 4)]:
+        center = np.sort(rng.integers(0, 5_000_000, m)).astype(np.float64) + 0.5
+        stbin = (center // 10_000).astype(np.int64) - 10
+        mind, maxd = 300_000.0, 2_500_000.0
+        q, total = _native.pair_windows_count(center, mind, maxd)
+        exp_k, exp_l = [], []
+        for i in range(1, m):
+            k = np.arange(m - i)
+            d = np.abs(center[k + i] - center[k])
+            kk = k[(mind <= d) & (d <= maxd)]
+            assert q[i] == len(kk)
+            exp_k.append(kk)
+            exp_l.append(kk + i)
+        assert total == sum(len(x) for x in exp_k)
+        dbin = rng.integers(-100, 100, total * nctrl).astype(np.int64) if nctrl else None
+        st1, st2, kind, i1, i2, dist = _native.pair_windows_fill(stbin, center, mind, maxd, nctrl, dbin, total)
+        e1, e2, ek, ekk, ell = [], [], [], [], []
+        pos = 0
+        for kk, ll in zip(exp_k, exp_l):
+            n = len(kk)
+            sh = np.concatenate([np.zeros(n, dtype=np.int64), dbin[pos : pos + n * nctrl]]) if nctrl else np.zeros(n, dtype=np.int64)
+            pos += n * nctrl
+            rk, rl = np.tile(kk, nctrl + 1), np.tile(ll, nctrl + 1)
+            e1.append(stbin[rk] + sh)
+            e2.append(stbin[rl] + sh)
+            kd = np.ones(n * (nctrl + 1), dtype=np.int8)
+            kd[:n] = 0
+            ek.append(kd)
+            ekk.append(rk)
+            ell.append(rl)
+        cat = lambda x, dt: np.concatenate(x).astype(dt) if x else np.zeros(0, dtype=dt)
+        assert np.array_equal(st1, cat(e1, np.int64)) and np.array_equal(st2, cat(e2, np.int64))
+        assert np.array_equal(kind, cat(ek, np.int8))
+        assert np.array_equal(i1, cat(ekk, np.int64)) and np.array_equal(i2, cat(ell, np.int64))
+        assert np.array_equal(dist, center[i2] - center[i1])
