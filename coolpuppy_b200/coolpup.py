@@ -705,6 +705,29 @@ class PileUpper:
         mi = pd.MultiIndex.from_arrays([s["chrom"].values, s["start"].values, s["end"].values])
         return self._ident_index.reindex(mi).values.astype(np.int64)
 
+    @staticmethod
+    def _unique_rows(flat):
+        """``(unique rows, index of each one's first occurrence, inverse)`` of an integer key matrix, by hashing one
+        mixed-radix int64 per row instead of ``np.unique(axis=0)``'s lexicographic sort."""
+        n = flat.shape[0]
+        if n == 0 or flat.shape[1] == 0:
+            return flat[:0], np.zeros(0, dtype=np.int64), np.zeros(n, dtype=np.int64)
+        lo = flat.min(axis=0)
+        radix = (flat.max(axis=0) - lo + 1).astype(object)
+        span = 1
+        for r in radix:
+            span *= int(r)
+        if span >= 2**62:  # cannot happen with group codes; keep the exact (slow) path for safety
+            uniq, idx, inv = np.unique(flat, axis=0, return_index=True, return_inverse=True)
+            return uniq, idx, np.asarray(inv).reshape(-1)
+        ck = np.zeros(n, dtype=np.int64)
+        for j in range(flat.shape[1]):
+            ck = ck * int(radix[j]) + (flat[:, j] - lo[j])
+        inv, _ = pd.factorize(ck)
+        first = np.empty(int(inv.max()) + 1, dtype=np.int64)
+        first[inv[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)  # the smallest index is written last
+        return flat[first], first, inv.astype(np.int64)
+
     def _assign_group_ids(self, built, plan, table, dist):
         """Dense group ids.  Returns (groups, gids, all_pos): ``groups`` lists the group keys in the reference's
         row order (first valid ROI emission, regions in view order), ``all_pos`` is where the reference's
@@ -722,7 +745,7 @@ class PileUpper:
                 ok = np.repeat(ok, ntarget)
                 if not ok.any():
                     continue
-                uniq, idx = np.unique(flat[ok], axis=0, return_index=True)
+                uniq, idx, _ = self._unique_rows(flat[ok])
                 pos = np.nonzero(ok)[0][idx]
                 for u, p in zip(map(tuple, uniq.tolist()), pos.tolist()):
                     cand = (ctrl_only, b["index"], p)
@@ -752,7 +775,7 @@ class PileUpper:
         for b in built:
             flat = b.pop("_flat")
             ntarget = b["keys"].shape[1]
-            uniq, inv = np.unique(flat, axis=0, return_inverse=True)
+            uniq, _, inv = self._unique_rows(flat)
             # keys that never occur in a valid window are skipped by the kernel anyway: park them in group 0
             m = np.array([lookup.get(tuple(u), 0) for u in uniq.tolist()], dtype=np.int64)
             gid = m[np.asarray(inv).reshape(-1)]
