@@ -21,6 +21,7 @@ cooler runs on.  The layout facts were established in SURVEY.md Appendix B.
 from __future__ import annotations
 
 import struct
+import os
 import zlib
 
 import numpy as np
@@ -85,9 +86,12 @@ class _Dataset:
             out_view = out.view(np.uint8)
             out[:] = 0
             if btree != _UNDEF:
-                for nbytes, mask, off, addr in self._f._iter_chunks(btree, 2):
+                filters = list(reversed(list(enumerate(self._filters))))
+
+                def decode(entry):
+                    nbytes, mask, off, addr = entry
                     raw = bytes(buf[addr : addr + nbytes])
-                    for i, (fid, cd) in reversed(list(enumerate(self._filters))):
+                    for i, (fid, cd) in filters:
                         if mask & (1 << i):
                             continue
                         if fid == 1:
@@ -102,11 +106,23 @@ class _Dataset:
                             raise HDF5FormatError(f"{self.name}: unsupported filter id {fid}")
                     start = off[0]
                     count = min(chunk, n - start)
-                    if count <= 0:
-                        continue
-                    out_view[start * itemsize : (start + count) * itemsize] = np.frombuffer(
-                        raw, dtype=np.uint8, count=count * itemsize
-                    )
+                    if count > 0:  # chunks cover disjoint ranges: safe to fill from several threads
+                        out_view[start * itemsize : (start + count) * itemsize] = np.frombuffer(
+                            raw, dtype=np.uint8, count=count * itemsize
+                        )
+
+                entries = list(self._f._iter_chunks(btree, 2))
+                workers = min(len(entries) // 4, os.cpu_count() or 1, 16)
+                if workers >= 2:  # zlib and the numpy copies release the GIL
+                    from concurrent.futures import ThreadPoolExecutor
+
+                    step = max(1, len(entries) // (workers * 4))  # a few batches per thread: chunks can be tiny
+                    batches = [entries[i : i + step] for i in range(0, len(entries), step)]
+                    with ThreadPoolExecutor(max_workers=workers) as pool:
+                        list(pool.map(lambda batch: [decode(e) for e in batch], batches))
+                else:
+                    for e in entries:
+                        decode(e)
         return out
 
     def __getitem__(self, key):
