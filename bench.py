@@ -46,8 +46,8 @@ def parse_args():
     ap.add_argument("--nshifts", type=int, default=10)
     ap.add_argument("--chroms", default=os.environ.get("PUP_BENCH_CHROMS", "all"), help="'all' or comma list (debug)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample", type=int, default=6000, help="windows in the cpu_baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=800, help="windows per chromosome per step, --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=30000, help="windows in the cpu_baseline sample (~10 s on one core)")
+    ap.add_argument("--ref-sample", type=int, default=2400, help="windows per chromosome per step, --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
