@@ -814,7 +814,23 @@ struct MainParams {
   int Gb;        // lane groups (= strips of a window) per band
   int n_groups;  // strips a window can touch: ceil((W + R - 1) / R)
   int n_bands;
+  int TW;        // tile row stride in doubles (>= W; chosen for the shared-memory bank mapping)
+  int* work;     // dynamic scheduling: global work-item counter (zeroed by the caller); null = static round-robin
   double* acc;
+};
+
+// Barrier-free dynamic work distribution inside a CTA.  All lane groups of a CTA must walk the SAME sequence of work
+// items (they own different rows of the same tile), but they drift apart freely.  The sequence is therefore kept in
+// a small shared-memory ring: entry `it` is produced by whichever group gets there first (it claims the entry with an
+// atomicCAS on `head`, takes the next item from the global counter and publishes {it + 1, item} with one 64-bit
+// store); the others read it.  `cnt[slot]` counts the reads of a ring slot, so that the producer of entry it + NSQ
+// only overwrites entry `it` once every group of the CTA has consumed it.
+constexpr int NSQ = 32;
+struct DynSched {
+  unsigned long long seq[NSQ];
+  int cnt[NSQ];
+  int head;
+  int pad;
 };
 
 __device__ __forceinline__ double lds_f64(unsigned a) {
@@ -834,11 +850,12 @@ __device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st
 // WU windows advance in lockstep per group (two register sets, ping-pong), so WU independent 16-byte loads are in
 // flight per lane while the previous S pixels of every window are added to the tile.  A group's load covers
 // S * 16 contiguous, aligned bytes: with S >= 8 every warp-wide load touches 4 full 128-byte lines.
-template <int R, int S, int WU, int PF>
-__global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_main(const MainParams p) {
+template <int R, int S, int WU, int PF, int MINB, bool QI>
+__global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, MINB) k_pileup_main(const MainParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int LR = (R == 1) ? 0 : (R == 2) ? 1 : (R == 4) ? 2 : 3;
   const int W = p.W;
+  const int TW = p.TW;
   const AccLayout L(W);
   const int lane = threadIdx.x & 31;
   const int sub = lane / S;
@@ -846,15 +863,25 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
   const int g = (threadIdx.x >> 5) * (32 / S) + sub;  // group id inside the band
   const unsigned gmask = (S == 32) ? 0xffffffffu : (((1u << S) - 1u) << (sub * S));
   const int ns = p.ns;
+  DynSched* ds = reinterpret_cast<DynSched*>(smem_raw + (size_t)p.Gb * R * TW * 8);
+  if (p.work != nullptr) {  // the only CTA-wide barrier of the kernel: the scheduler ring starts empty
+    for (int i = threadIdx.x; i < (int)(sizeof(DynSched) / 4); i += blockDim.x) reinterpret_cast<int*>(ds)[i] = 0;
+    __syncthreads();
+  }
   if (g >= p.Gb) return;  // no barriers below: idle groups may leave
 
-  unsigned trow = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(g * R * W) * 8u;  // my R tile rows
+  unsigned trow = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)(g * R * TW) * 8u;  // my R tile rows
   asm volatile("mov.u32 %0, %0;" : "+r"(trow));  // keep the address in a register (no rematerialisation)
-  for (int i = ls; i < R * W; i += S) sts_f64(trow + i * 8, 0.0);
+  for (int i = ls; i < R * TW; i += S) sts_f64(trow + i * 8, 0.0);
   __syncwarp(gmask);
   int cur_slot = -1, cur_band = 0;  // extended slot
   const int total_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
   const int total_items = total_chunks * p.n_bands;
+
+  // cell (q, dj) of my rows: row-major with stride TW, or (QI) the R rows interleaved column by column
+  auto cell = [&](int q, int dj) -> unsigned {
+    return QI ? trow + (unsigned)(dj * R + q) * 8u : trow + (unsigned)(q * TW + dj) * 8u;
+  };
 
   auto flush_rows = [&]() {
     // this group's tile rows -> global accumulator (red.global.add.f64), then clear them
@@ -865,24 +892,56 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       const int di = t0 + q - m;
-      const unsigned row = trow + (unsigned)(q * W) * 8u;
       if ((unsigned)di < (unsigned)W) {
         double* a = abase + (int64_t)di * W;
         for (int dj = ls; dj < W; dj += S) {
-          const double v = lds_f64(row + dj * 8);
+          const unsigned ad = cell(q, dj);
+          const double v = lds_f64(ad);
           if (v != 0.0) {
             atomicAdd(a + dj, v);
-            sts_f64(row + dj * 8, 0.0);
+            sts_f64(ad, 0.0);
           }
         }
       } else {
-        for (int dj = ls; dj < W; dj += S) sts_f64(row + dj * 8, 0.0);
+        for (int dj = ls; dj < W; dj += S) sts_f64(cell(q, dj), 0.0);
       }
     }
     __syncwarp(gmask);
   };
 
-  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+  // next work item of this CTA's sequence (static: blockIdx.x, + gridDim.x, ...; dynamic: see DynSched)
+  int it = 0;
+  auto next_item = [&]() -> int {
+    if (p.work == nullptr) return blockIdx.x + (it++) * gridDim.x;
+    int item = 0;
+    if (ls == 0) {
+      const int slot = it & (NSQ - 1);
+      volatile unsigned long long* sq = &ds->seq[slot];
+      volatile int* head = &ds->head;
+      for (;;) {
+        const unsigned long long v = *sq;
+        if ((int)(v >> 32) == it + 1) {
+          item = (int)(unsigned)v;
+          break;
+        }
+        if (*head == it && atomicCAS(&ds->head, it, it + 1) == it) {
+          // I produce entry `it`: wait until all groups have read the previous occupant of the ring slot
+          const int need = p.Gb * (it / NSQ);
+          while (*(volatile int*)&ds->cnt[slot] < need) {
+          }
+          item = atomicAdd(p.work, 1);
+          if (item > total_items) item = total_items;
+          *sq = ((unsigned long long)(unsigned)(it + 1) << 32) | (unsigned)item;
+          break;
+        }
+      }
+      atomicAdd(&ds->cnt[slot], 1);
+    }
+    ++it;
+    return __shfl_sync(gmask, item, sub * S);
+  };
+
+  for (int item = next_item(); item < total_items; item = next_item()) {
     const int band = item / total_chunks;
     int slot, w_lo, w_hi;
     locate_chunk(p.chunks, item - band * total_chunks, slot, w_lo, w_hi);
@@ -896,9 +955,8 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
 
     for (int w = w_lo; w < w_hi; w += WU) {
       // Two register sets (A, B) of raw pixel records {col, q, val} per window in flight.  Every half-step loads
-      // the next record of every run unconditionally: a lane whose current pixel already lies right of the window
-      // reads a sentinel (col = INT_MAX) from the block at the start of pix[] instead, which ends its run -- no
-      // predicated loads, no register copies.
+      // the next record of every run with a predicated load that lands directly in the other register set; a lane
+      // whose current pixel already lies right of the window gets col = INT_MAX instead, which ends its run.
       int idx[WU], c0s[WU];
       int4 A[WU], B[WU];
       // stage A: window records -> strip pointers (WU independent chains)
@@ -936,7 +994,7 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
     }                                                                                            \
     _Pragma("unroll") for (int u = 0; u < WU; ++u) {                                             \
       if ((unsigned)dj[u] < (unsigned)W) {                                                       \
-        const unsigned a = trow + (unsigned)(dj[u] + (R > 1 ? C[u].y * W : 0)) * 8u;             \
+        const unsigned a = cell(R > 1 ? C[u].y : 0, dj[u]);                                      \
         sts_f64(a, lds_f64(a) + __hiloint2double(C[u].w, C[u].z));                               \
       }                                                                                          \
     }                                                                                            \
@@ -945,6 +1003,10 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, 2) k_pileup_ma
       // lanes still inside execute the same predicated instruction stream, so the read-modify-writes of one tile
       // row are ordered by the program order of a converged SIMT group (racecheck reports them as intra-warp
       // hazards "without barrier"; a group-voted exit was measured 6 % slower and changes nothing about ordering).
+      // Two lanes of a group never hold the same tile cell in the same half-step: the S pixels a group loads per
+      // window and half-step are S distinct (col, q) entries of one strip, and the WU windows of a half-step are
+      // added one after the other (pinned by tests/test_gpu_parity.py::test_adversarial_duplicate_windows and
+      // the SASS excerpt in profiles/).
       for (;;) {
         PUP_HALF_STEP(A, B)
         PUP_HALF_STEP(B, A)
@@ -1159,12 +1221,11 @@ __global__ void k_diag_sums(const int32_t* __restrict__ indptr_u, const int32_t*
       const int c = col_u[i];
       if (c < (int)r || c >= nb) continue;  // pixels that leave the region
       const double cnt = (double)cnt_u[i];
+      atomicAdd(count_sum + (c - (int)r), cnt);  // raw counts: every stored pixel, masked bins included (cooltools)
       if (weight) {
         const double v = wr * weight[c] * cnt;
-        if (v != v) continue;  // a masked bin: the position is not valid
-        atomicAdd(bal_sum + (c - (int)r), v);
+        if (v == v) atomicAdd(bal_sum + (c - (int)r), v);  // NaN: a masked bin, the position is not valid
       }
-      atomicAdd(count_sum + (c - (int)r), cnt);
     }
   }
 }
@@ -1193,9 +1254,9 @@ __global__ void k_n_valid(const int32_t* __restrict__ badpre, const unsigned lon
 }
 
 // occ != nullptr: only query the occupancy; else launch
-template <int R, int S, int PF>
-cudaError_t launch_main_rsp(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
-  auto kern = k_pileup_main<R, S, 4, PF>;
+template <int R, int S, int PF, int MINB, bool QI>
+cudaError_t launch_main_t(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
+  auto kern = k_pileup_main<R, S, 4, PF, MINB, QI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (occ) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, threads, smem);
@@ -1205,9 +1266,16 @@ cudaError_t launch_main_rsp(const MainParams& p, int grid, int threads, size_t s
 
 template <int R, int S>
 cudaError_t launch_main_rs(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
-  const int pf = env_int("PUP_PREFETCH", 2);
-  if (R == 2 && S == 8 && pf == 0) return launch_main_rsp<R, S, 0>(p, grid, threads, smem, st, occ);
-  return launch_main_rsp<R, S, 2>(p, grid, threads, smem, st, occ);
+  // tuning variants (PUP_PREFETCH=0: no L2 prefetch, PUP_MINB=3: register budget for 3 CTAs per SM,
+  // PUP_TILE_INTERLEAVE=1: tile rows of a strip interleaved by column) exist for the default geometry only
+  if (R == 2 && S == 8) {
+    const int pf = env_int("PUP_PREFETCH", 2), minb = env_int("PUP_MINB", 2), qi = env_int("PUP_TILE_INTERLEAVE", 0);
+    if (pf == 0) return launch_main_t<R, S, 0, 2, false>(p, grid, threads, smem, st, occ);
+    if (minb == 3 && qi) return launch_main_t<R, S, 2, 3, true>(p, grid, threads, smem, st, occ);
+    if (minb == 3) return launch_main_t<R, S, 2, 3, false>(p, grid, threads, smem, st, occ);
+    if (qi) return launch_main_t<R, S, 2, 2, true>(p, grid, threads, smem, st, occ);
+  }
+  return launch_main_t<R, S, 2, 2, false>(p, grid, threads, smem, st, occ);
 }
 
 cudaError_t launch_main(int R, int S, const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st,
@@ -1842,15 +1910,19 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     // one lane group per strip of the window; a band = the groups whose R x W fp64 tile rows fit PUP_TILE_KB
     const int n_groups = (W + 2 * R - 2) / R;  // ceil((W + R - 1) / R): a window touches at most that many strips
     const int tile_kb = env_int("PUP_TILE_KB", 72);
-    int Gb = (int)std::min<int64_t>(n_groups, ((int64_t)tile_kb * 1024) / (8ll * W * R));
+    // tile row stride: W plus PUP_TILE_PAD doubles (bank mapping of the rows a half-warp works on)
+    const int TW = W + std::max(0, env_int("PUP_TILE_PAD", 0));
+    int Gb = (int)std::min<int64_t>(n_groups, ((int64_t)tile_kb * 1024) / (8ll * TW * R));
     const int nt_max = (S == 32) ? NT_MAX : NT_MAX - 32;  // the kernel's launch bound
     Gb = std::min(Gb, nt_max / S);
     if (Gb < 1) Gb = 1;
     const int n_bands = (n_groups + Gb - 1) / Gb;
     Gb = (n_groups + n_bands - 1) / n_bands;  // balance the bands
     const int threads = std::min(nt_max, ((Gb * S + 31) / 32) * 32);
-    const size_t smem = (size_t)Gb * R * W * 8;
-    MainParams mp{W, m->ns, m->lb, m->pix, m->bucket, win, chunks, Gb, n_groups, n_bands, d_acc};
+    const bool dynamic = env_int("PUP_SCHED", 1) != 0;
+    const size_t smem = (size_t)Gb * R * TW * 8 + sizeof(DynSched);
+    MainParams mp{W, m->ns, m->lb, m->pix, m->bucket, win, chunks, Gb, n_groups, n_bands, TW,
+                  dynamic ? counters : nullptr, d_acc};
     int occ = 1;
     cudaError_t e = launch_main(R, S, mp, 0, threads, smem, st, &occ);
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "main kernel occupancy query", e);

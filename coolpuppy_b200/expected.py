@@ -11,8 +11,12 @@ external tool.
 Semantics (cooltools ``expected_cis`` with ``smooth=False``): for every view
 region and diagonal ``d``: ``n_valid`` = number of pixel positions on the
 diagonal whose two bins are both valid (non-NaN weight when balanced, all bins
-otherwise), ``*.sum`` = sum over those positions, ``*.avg = sum / n_valid``;
-the first ``ignore_diags`` diagonals are NaN.
+otherwise), ``balanced.sum`` = sum of the balanced values over those
+positions, ``count.sum`` = sum of the raw counts over *every* stored pixel of
+the diagonal (cooltools does not mask raw counts), ``*.avg = *.sum / n_valid``;
+the first ``ignore_diags`` diagonals are NaN.  Pinned against the
+cooltools-made table the reference ships (``tests/data/CN.mm9.toy_expected.tsv``)
+by ``tests/test_expected.py``.
 """
 from __future__ import annotations
 
@@ -45,7 +49,9 @@ def expected_cis(clr, view_df=None, clr_weight_name=None, ignore_diags=2):
             val = w[b1 - lo] * w[b2 - lo] * cnt
             good = ~np.isnan(val)
             bal_sum = np.bincount(d[good], weights=val[good], minlength=nb)[:nb]
-            cnt_sum = np.bincount(d[good], weights=cnt[good].astype(np.float64), minlength=nb)[:nb]
+            # cooltools sums the raw counts over ALL stored pixels of the diagonal (masked bins included) and still
+            # divides by n_valid (pinned by tests/fixtures/CN.mm9.toy_expected.tsv)
+            cnt_sum = np.bincount(d, weights=cnt.astype(np.float64), minlength=nb)[:nb]
         else:
             n_valid = (nb - dist).astype(np.int64)
             cnt_sum = np.bincount(d, weights=cnt.astype(np.float64), minlength=nb)[:nb]

@@ -165,10 +165,12 @@ int pup_stripes(const pup_region_t* region, int64_t n_win, const int32_t* r0, co
  * Per-diagonal sums of one view region, the arithmetic of `cooltools expected-cis` whose table the reference takes
  * through --expected / expected_df (CLI.py:484-508, coolpup.py:861-918), from the region's upper triangle as cooler
  * stores it (same layout as pup_region_create_upper; columns >= nb are ignored).  Outputs, host or device, [nb] each:
- *   count_sum[d]     sum of raw counts on diagonal d over positions whose two bins are valid
+ *   count_sum[d]     sum of raw counts over EVERY stored pixel of diagonal d, masked bins included (cooltools does
+ *                    not mask raw counts; pinned by the reference's tests/data/CN.mm9.toy_expected.tsv)
  *   balanced_sum[d]  sum of (weight[row] * weight[col]) * count; NULL exactly when weight is NULL
  *   n_valid[d]       number of positions (i, i + d) whose two bins are valid (all nb - d without weights)
- * A bin is valid when its weight is not NaN.  expected = sum / n_valid; masking the first diagonals is the caller's.
+ * A bin is valid when its weight is not NaN.  expected = sum / n_valid (for count_sum too); masking the first
+ * diagonals is the caller's.
  */
 int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* indptr_upper, const int32_t* col_upper,
                      const int32_t* count_upper, const double* weight, double* count_sum, double* balanced_sum,

@@ -585,11 +585,21 @@ def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_
     # "all" (1272-1282)
     empty_pup = {"data": empty, "horizontal_stripe": [], "vertical_stripe": [], "n": 0, "num": empty,
                  "cov_start": np.zeros(W), "cov_end": np.zeros(W), "coordinates": []}
+    # NB the reference's sum_pups rebinds ``pup["data"] = np.nan_to_num(pup["data"])`` on BOTH of its inputs
+    # (lib/puputils.py:97-98), so building "all" leaves every group of the region with NaN -> 0 and
+    # +inf -> 1.797e308 in its own ``data`` (verified against the real reference: by-window groups that live in one
+    # region only still show 1.797e308 / num)
+    def all_of(groups):
+        tot = reduce(sum_pups, groups.values(), empty_pup)
+        for p in groups.values():
+            p["data"] = np.nan_to_num(p["data"])
+        return tot
+
     if "all" not in out["ROI"]:
-        out["ROI"]["all"] = reduce(sum_pups, out["ROI"].values(), empty_pup)
+        out["ROI"]["all"] = all_of(out["ROI"])
     if control or (E is not None and not ooe):
         if "all" not in out["control"]:
-            out["control"]["all"] = reduce(sum_pups, out["control"].values(), empty_pup)
+            out["control"]["all"] = all_of(out["control"])
     for k in ("st1", "st2", "kind", "flip"):
         log[k] = np.asarray(log[k], dtype=np.int64)
     return out, log

@@ -1,7 +1,8 @@
 """Tuning sweep of the main pile-up kernel on the bench workload (run on the GPU box).
 
 One process: the synthetic genome and the window lists are generated once; for every variant
-``R:S[:bucket_target[:chunk]]`` (strip height, lanes per strip run, pixels per bucket, windows per chunk) the regions are
+``R:S[:bucket_target[:chunk[:prefetch]]][;KEY=VALUE...]`` (strip height, lanes per strip run, pixels per bucket,
+windows per chunk; ``KEY=VALUE`` sets the tuning variable ``PUP_KEY``, e.g. ``SCHED=0``, ``MINB=3``) the regions are
 re-indexed (the strip geometry is fixed at region creation), the full pass is timed with CUDA events and the
 accumulators are compared with the first variant's: ``num`` / ``n`` exactly, ``sum`` to 1e-9 relative.
 
@@ -54,11 +55,20 @@ def main():
     ref = None
     rows = []
     for v in a.variants:
-        parts = v.split(":")
+        toks = v.split(";")
+        parts = toks[0].split(":")
+        for k in [k for k in os.environ if k.startswith("PUP_") and not k.startswith("PUP_BENCH")]:
+            del os.environ[k]  # every variant starts from the defaults
         os.environ["PUP_STRIP"], os.environ["PUP_LANES"] = parts[0], parts[1]
-        os.environ["PUP_BUCKET_TARGET"] = parts[2] if len(parts) > 2 else "4"
-        os.environ["PUP_CHUNK"] = parts[3] if len(parts) > 3 else "64"
-        os.environ["PUP_PREFETCH"] = parts[4] if len(parts) > 4 else "2"
+        if len(parts) > 2:
+            os.environ["PUP_BUCKET_TARGET"] = parts[2]
+        if len(parts) > 3:
+            os.environ["PUP_CHUNK"] = parts[3]
+        if len(parts) > 4:
+            os.environ["PUP_PREFETCH"] = parts[4]
+        for t in toks[1:]:  # KEY=VALUE -> PUP_KEY
+            k, val = t.split("=")
+            os.environ["PUP_" + k] = val
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         regions = {c: _native.Region(0, d["nb"], d["indptr"], d["col"], d["count"], d["weight"], None, None, ignore_diags=2,

@@ -77,6 +77,19 @@ CASES = {
     "scc1_loops_igd5_ctrl": {**SCC1, "features": "CH12_loops_Rao.bed", "features_schema": "bedpe6",
                              "kwargs": dict(features_format="bedpe", clr_weight_name=None, flank=100_000, mindist=0, min_diag=5,
                                             nshifts=2, seed=8)},
+    # ---- expected == 0 under non-zero counts (x / 0 = +inf): the reference's merge of >= 2 regions / groups turns
+    # +inf into 1.797e308 (np.nan_to_num in sum_pups, lib/puputils.py:97-98) instead of NaN
+    "toy_zero_expected_ooe": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"foo": [3, 4], "bar": [4]},
+                              "kwargs": {**TOYKW, "ooe": True}},
+    "toy_zero_expected_strand": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"foo": [3, 4], "bar": [4, 6]},
+                                 "kwargs": {**TOYKW, "ooe": True, "by_strand": True}},
+    "toy_zero_expected_bywindow": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"foo": [4, 5], "bar": [3, 4]},
+                                   "kwargs": {**TOYKW, "ooe": True, "by_window": True}},
+    "toy_zero_expected_flip_dist": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"bar": [2, 3, 4, 5, 6, 7]},
+                                    "kwargs": {**TOYKW, "ooe": True, "by_strand": True, "by_distance": True,
+                                               "flip_negative_strand": True}},
+    "toy_zero_expected_one_region": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"foo": [3]},
+                                     "view_rows": [0], "kwargs": {**TOYKW, "ooe": True}},
     "scc1_ctcf_pairs_arms": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "view": "scc1_arms_view.bed",
                              "kwargs": dict(features_format="bed", clr_weight_name=None, flank=50_000, mindist=0, maxdist=2_000_000,
                                             nshifts=1, seed=4)},
@@ -98,6 +111,8 @@ def load_view(spec):
         return None
     df = pd.read_csv(os.path.join(FIX, spec["view"]), sep="\t", header=None)
     df.columns = ["chrom", "start", "end", "name"]
+    if "view_rows" in spec:
+        df = df.iloc[spec["view_rows"]].reset_index(drop=True)
     return df
 
 
@@ -107,7 +122,13 @@ def load_expected(spec, clr, view, expected_cis_func):
         return None
     if e.startswith("compute:"):
         return expected_cis_func(clr, view_df=view, clr_weight_name=None, ignore_diags=2)
-    return pd.read_csv(os.path.join(FIX, e), sep="\t", dtype={"region1": str, "region2": str})
+    tab = pd.read_csv(os.path.join(FIX, e), sep="\t", dtype={"region1": str, "region2": str})
+    for region, dists in spec.get("expected_zero", {}).items():  # zero the expected at these distances
+        hit = (tab["region1"] == region) & (tab["region2"] == region) & tab["dist"].isin(dists)
+        for c in tab.columns:
+            if c.endswith(".avg") or c.endswith(".sum"):
+                tab.loc[hit, c] = 0.0
+    return tab
 
 
 def write_derived_fixtures():

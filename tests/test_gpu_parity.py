@@ -169,6 +169,66 @@ def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots)
     np.testing.assert_allclose(ver, ever, rtol=RTOL, equal_nan=True)
 
 
+@pytest.mark.parametrize("env", [{"PUP_SCHED": "0"}, {"PUP_SCHED": "1"}, {"PUP_MINB": "3"}, {"PUP_TILE_PAD": "1"},
+                                 {"PUP_TILE_PAD": "5", "PUP_MINB": "3"}, {"PUP_TILE_INTERLEAVE": "1"},
+                                 {"PUP_TILE_INTERLEAVE": "1", "PUP_MINB": "3", "PUP_CHUNK": "16"}, {"PUP_CHUNK": "7"}])
+@pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(700, 83, 200, 2500, 3), (900, 203, 400, 90, 2), (300, 21, 30, 4000, 5)])
+def test_main_kernel_variants(monkeypatch, env, nb, W, dens, nwin, n_slots):
+    """Scheduling (static round-robin / barrier-free dynamic ring), occupancy and tile-layout variants of the main
+    kernel all give the oracle's accumulators."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb + W + 1, nan_frac=0.05, with_expected=True)
+    r0, c0, sl = random_windows(nb, W, nwin, n_slots, seed=5 * nb + W)
+    ref = oracle_accumulate(nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, ooe=True)
+    acc = np.zeros(n_slots * nat.acc_stride(W))
+    nv = nat.accumulate_region(0, nb, ip, col, cnt, w, e, None, r0, c0, sl, W, 2, n_slots, nat.PUP_F_OOE, acc)
+    _check_against_oracle(nv, nat.acc_export(acc, W, n_slots), ref)
+
+
+@pytest.mark.parametrize("strip,lanes", [(2, 8), (4, 8), (1, 4), (8, 32)])
+def test_adversarial_duplicate_windows(monkeypatch, strip, lanes):
+    """The tile read-modify-write has no atomics: correctness rests on (a) one lane group owning its tile rows and
+    (b) the windows a group has in flight being added one after the other.  Worst cases for both: thousands of
+    IDENTICAL windows in one slot (every window in flight hits the same cells in the same half-step), windows that
+    differ only in c0 by 1 (neighbouring lanes / windows hit neighbouring and identical cells), and a dense block
+    so that every lane of a group holds a pixel in every half-step.  Integer counts and power-of-two weights make
+    the expected sums exact, so any lost update shows up as an inequality, not a tolerance failure."""
+    nat = _cuda()
+    monkeypatch.setenv("PUP_STRIP", str(strip))
+    monkeypatch.setenv("PUP_LANES", str(lanes))
+    from scipy import sparse
+
+    nb, W = 400, 21
+    rng = np.random.default_rng(42)
+    dense = sparse.random(nb, nb, density=0.9, random_state=7, data_rvs=lambda n: rng.integers(1, 9, n)).tocsr()
+    dense = sparse.triu(dense) + sparse.triu(dense, 1).T
+    dense = sparse.csr_matrix(dense)
+    dense.sort_indices()
+    ip, col, cnt = dense.indptr.astype(np.int32), dense.indices.astype(np.int32), dense.data.astype(np.int32)
+    r0 = np.concatenate([np.full(4096, 100), np.full(4, 37), np.full(1000, 101), np.arange(60, 64)]).astype(np.int32)
+    c0 = np.concatenate([np.full(4096, 230), 300 + np.arange(4), np.full(1000, 230), np.full(4, 200)]).astype(np.int32)
+    sl = np.concatenate([np.zeros(4096), np.ones(4), np.zeros(1000), np.ones(4)]).astype(np.int32)
+    full = dense.toarray().astype(np.float64)
+    want = np.zeros((2, W, W))
+    for a, c, s_ in zip(r0, c0, sl):
+        blk = full[a : a + W, c : c + W].copy()
+        ii, jj = np.arange(W)[:, None] + a, np.arange(W)[None, :] + c
+        blk[(jj - ii) < 2] = 0.0
+        want[s_] += blk
+    for order in (np.arange(len(r0)), rng.permutation(len(r0))):
+        acc = np.zeros(2 * nat.acc_stride(W))
+        nv = nat.accumulate_region(0, nb, ip, col, cnt, None, None, None, np.ascontiguousarray(r0[order]),
+                                   np.ascontiguousarray(c0[order]), np.ascontiguousarray(sl[order]), W, 2, 2, 0, acc)
+        out = nat.acc_export(acc, W, 2)
+        assert nv == len(r0)
+        assert np.array_equal(out["sum"], want)  # exact: small integers
+        assert np.array_equal(out["n"], [5096, 8])
+
+
 @pytest.mark.parametrize("ignore_diags", [2, 0, -4])
 @pytest.mark.parametrize("nb,W,dens", [(300, 21, 30), (900, 83, 300), (64, 5, 2), (2000, 11, 1)])
 def test_upper_triangle_input_is_mirrored_on_device(nb, W, dens, ignore_diags):
