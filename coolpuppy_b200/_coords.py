@@ -58,6 +58,13 @@ class RegionWindows:
     def __len__(self):
         return int(self.st1.shape[0])
 
+    def take(self, sel):
+        """The windows ``sel`` (index array, emission order kept) as a new RegionWindows over the same feature table."""
+        if self.frame is not None:
+            raise NotImplementedError("cannot subset windows after a user callback has materialised the frame")
+        return RegionWindows(self.region, self.sel, self.st1[sel], self.st2[sel], self.kind[sel], self.idx1[sel],
+                             self.idx2[sel], None if self.distance is None else self.distance[sel], self.paired)
+
     def column(self, name, swap=None):
         """Values of 2-D interval column ``name`` for every window.
 
@@ -129,8 +136,12 @@ def _draw_shifts(n, minshift, maxshift, resolution):
     return np.round(shift / resolution).astype(np.int64)
 
 
-def build_region_windows(cc, region, control):
-    """Windows of one view region ``(chrom, start, end)`` (reference: coolpup.py:546-563, 598-746)."""
+def build_region_windows(cc, region, control, draw_only=False):
+    """Windows of one view region ``(chrom, start, end)`` (reference: coolpup.py:546-563, 598-746).
+
+    ``draw_only``: make exactly the ``np.random`` calls the region's control shifts need (same sizes, same order) and
+    return ``None`` -- how a rank keeps the global random stream in step with the serial reference for view regions
+    that another rank piles up, without laying out their windows."""
     chrom, start, end = region
     df = cc.intervals
     nctrl = cc.nshifts if control else 0
@@ -150,6 +161,8 @@ def build_region_windows(cc, region, control):
         kind = np.zeros(q, dtype=np.int8)
         if nctrl > 0 and q > 0:
             dbin = _draw_shifts(q * nctrl, cc.minshift, cc.maxshift, res)
+            if draw_only:
+                return None
             cidx = np.tile(idx, nctrl)
             st1 = np.concatenate([st1, st1[cidx] + dbin])
             st2 = np.concatenate([st2, st2[cidx] + dbin])
@@ -169,6 +182,8 @@ def build_region_windows(cc, region, control):
         st1 = st2 = st
         if nctrl > 0 and nfeat > 0:
             dbin = _draw_shifts(nfeat * nctrl, cc.minshift, cc.maxshift, res)
+            if draw_only:
+                return None
             cidx = np.tile(idx, nctrl)
             st1 = st2 = np.concatenate([st, st[cidx] + dbin])
             kind = np.concatenate([kind, np.ones(nfeat * nctrl, dtype=np.int8)])
@@ -183,6 +198,11 @@ def build_region_windows(cc, region, control):
     center = sel["center"].values.astype(np.float64)
     q, total = _native.pair_windows_count(center, cc.mindist, cc.maxdist)
     dbin = None
+    if draw_only:
+        for n in q[q > 0] * nctrl:
+            np.random.randint(cc.minshift, cc.maxshift, int(n))
+            np.random.choice([-1, 1], int(n))
+        return None
     if nctrl > 0 and total > 0:
         shift = np.empty(total * nctrl, dtype=np.int64)
         sign = np.empty(total * nctrl, dtype=np.int64)

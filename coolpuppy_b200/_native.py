@@ -123,6 +123,20 @@ def acc_stride(W):
     return int(lib().pup_acc_stride(int(W)))
 
 
+def acc_counts(acc, W, n_slots):
+    """Windows accumulated per slot (the ``n`` field of every slot of a torch accumulator) as a host int64 array."""
+    stride = acc_stride(W)
+    n = acc.view(int(n_slots), stride)[:, stride - 8]  # AccLayout: off_n = stride - 8
+    return np.rint(n.cpu().numpy()).astype(np.int64)
+
+
+def make_pipeline(device, W, n_slots, flags):
+    """The two-stream region pipeline (:mod:`coolpuppy_b200.pipeline`) on ``device``."""
+    from .pipeline import RegionPipeline
+
+    return RegionPipeline(device, W, n_slots, flags)
+
+
 class Region:
     """A region matrix resident in HBM (``pup_region_t``)."""
 

@@ -265,37 +265,23 @@ class CoordCreator:
 
 
 # ------------------------------------------------------------------------------------------ group bookkeeping
+def _isnull(v):
+    return v is None or (isinstance(v, float) and v != v)
+
+
 class _GroupTable:
-    """Dense integer ids for group keys, shared by all regions (and ranks) of one run."""
+    """Dense integer codes for the values of group columns, identical on all regions and ranks of one run.
 
-    def __init__(self, cc, groupby, by_window):
+    A column that exists in the feature table gets its code dictionary from the whole table up front (sorted values,
+    missing values last).  A column that only a user ``modify_2Dintervals_func`` creates is *dynamic*: codes are handed
+    out in order of appearance while the regions are laid out and :meth:`finalize` replaces them by positions in the
+    dictionary merged over all ranks.
+    """
+
+    def __init__(self, cc):
         self.cc = cc
-        self.groupby = list(groupby)
-        self.by_window = by_window
-        self._uniques = {}  # column -> list of values; code = position
-
-    def _codes(self, col, values):
-        """Global codes of ``values`` for group column ``col`` (codes are stable across regions)."""
-        if col not in self._uniques:
-            self._uniques[col] = self._global_uniques(col)
-        uni = self._uniques[col]
-        if uni is None:  # unknown globally (callback-made column): grow on demand
-            uni = self._uniques[col] = {"_dynamic": True, "vals": [], "index": {}}
-        if isinstance(uni, dict):
-            codes, u = pd.factorize(pd.Series(list(values), dtype=object))
-            m = np.empty(len(u), dtype=np.int64)
-            for j, v in enumerate(u):
-                if v not in uni["index"]:
-                    uni["index"][v] = len(uni["vals"])
-                    uni["vals"].append(v)
-                m[j] = uni["index"][v]
-            return m[codes]
-        codes, u = pd.factorize(pd.Series(values))
-        lut = pd.Series(np.arange(len(uni), dtype=np.int64), index=pd.Index(uni))
-        m = lut.reindex(u).values
-        if np.isnan(m.astype(float)).any():
-            raise ValueError(f"group column {col!r}: value not present in the feature table")
-        return m.astype(np.int64)[codes]
+        self._static = {}   # column -> (values list, has_na)
+        self._dynamic = {}  # column -> {"vals": [...], "index": {...}, "lut": None}
 
     def _global_uniques(self, col):
         df = self.cc.intervals
@@ -305,21 +291,110 @@ class _GroupTable:
             base = col
         else:
             return None
-        vals = pd.unique(df[base])
+        vals = pd.unique(df[base]).tolist()
+        has_na = any(_isnull(v) for v in vals)
+        vals = [v for v in vals if not _isnull(v)]
         try:
-            return sorted(vals.tolist())
+            vals = sorted(vals)
         except TypeError:
-            return vals.tolist()
+            pass
+        return vals, has_na
+
+    def is_dynamic(self, col):
+        if col not in self._static and col not in self._dynamic:
+            u = self._global_uniques(col)
+            if u is None:
+                self._dynamic[col] = {"vals": [], "index": {}, "lut": None}
+            else:
+                self._static[col] = u
+        return col in self._dynamic
+
+    def codes(self, col, values):
+        """Codes of ``values`` for group column ``col``; a missing value (NaN / None) is a group of its own."""
+        if self.is_dynamic(col):
+            dyn = self._dynamic[col]
+
+            def code_of(k, v):
+                if k not in dyn["index"]:
+                    dyn["index"][k] = len(dyn["vals"])
+                    dyn["vals"].append(v)
+                return dyn["index"][k]
+
+            codes, u = pd.factorize(pd.Series(list(values), dtype=object), use_na_sentinel=True)
+            m = np.full(len(u) + 1, -1, dtype=np.int64)
+            for j, v in enumerate(u):
+                m[j] = code_of(v, v)
+            if (codes < 0).any():
+                m[-1] = code_of("__na__", None)
+            return m[codes]  # code -1 (missing value) picks the last entry
+        vals, has_na = self._static[col]
+        codes, u = pd.factorize(pd.Series(values), use_na_sentinel=True)
+        lut = pd.Series(np.arange(len(vals), dtype=np.int64), index=pd.Index(vals, dtype=object) if len(vals) else None)
+        m = lut.reindex(pd.Index(list(u), dtype=object)).values.astype(np.float64) if len(u) else np.zeros(0)
+        if np.isnan(m).any():
+            raise ValueError(f"group column {col!r}: value not present in the feature table")
+        m = np.append(m.astype(np.int64), len(vals))  # missing values -> the extra last code
+        if (codes < 0).any() and not has_na:
+            raise ValueError(f"group column {col!r}: missing value not present in the feature table")
+        return m[codes]
+
+    def finalize(self, dist):
+        """Make the dynamic dictionaries global: merge them over the ranks and remember local -> global codes."""
+        for col, dyn in sorted(self._dynamic.items()):
+            lists = [dyn["vals"]] if dist is None else dist.all_gather_object(dyn["vals"])
+            merged, seen = [], set()
+            for lst in lists:
+                for v in lst:
+                    k = "__na__" if _isnull(v) else v
+                    if k not in seen:
+                        seen.add(k)
+                        merged.append(v)
+            na = [v for v in merged if _isnull(v)]
+            rest = [v for v in merged if not _isnull(v)]
+            try:
+                rest = sorted(rest)
+            except TypeError:
+                pass
+            merged = rest + na[:1]
+            pos = {("__na__" if _isnull(v) else v): i for i, v in enumerate(merged)}
+            dyn["lut"] = np.array([pos["__na__" if _isnull(v) else v] for v in dyn["vals"]], dtype=np.int64)
+            dyn["global"] = merged
+
+    def remap(self, col, codes):
+        if col in self._dynamic:
+            lut = self._dynamic[col]["lut"]
+            return lut[codes] if len(lut) else codes
+        return codes
+
+    def radix(self, col):
+        if col in self._dynamic:
+            return max(1, len(self._dynamic[col]["global"]))
+        vals, has_na = self._static[col]
+        return len(vals) + 1
 
     def value(self, col, code):
-        uni = self._uniques[col]
-        if isinstance(uni, dict):
-            return uni["vals"][code]
-        return uni[code]
+        if col in self._dynamic:
+            return self._dynamic[col]["global"][code]
+        vals, _ = self._static[col]
+        return vals[code] if code < len(vals) else np.nan
 
 
 def _band_ids(distance, edges):
     return np.searchsorted(edges, distance, side="right").astype(np.int64)
+
+
+def _first_positions(keys, ok, pos):
+    """{key: smallest pos} over the entries with ``ok`` (keys: int64 array)."""
+    if not ok.any():
+        return {}
+    k, p = keys[ok], pos[ok]
+    order = np.argsort(k, kind="stable")  # pos ascends inside the input, so the first of every run is the minimum
+    ks, ps = k[order], p[order]
+    head = np.ones(len(ks), dtype=bool)
+    head[1:] = ks[1:] != ks[:-1]
+    # positions are not necessarily ascending for strided parts of by-window targets: take the true minimum
+    mins = np.minimum.reduceat(ps, np.nonzero(head)[0])
+    return dict(zip(ks[head].tolist(), mins.tolist()))
 
 
 # ------------------------------------------------------------------------------------------ PileUpper
@@ -391,6 +466,16 @@ class PileUpper:
             lo, hi = self.clr.extent((region["chrom"], region["start"], region["end"]))
             chroffset = self.clr.offset(region["chrom"])
             self.view_df_extents[region_name] = lo - chroffset, hi - chroffset
+        if self.expected is True:
+            # cooltools.lib.checks.is_valid_expected(..., verify_cooler=clr) at coolpup.py:875-906: every view region
+            # needs one expected row per diagonal; a missing region would silently give an all-NaN pile-up here
+            for region_name, (lo_rel, hi_rel) in self.view_df_extents.items():
+                have = len(self._expected_values.get(region_name, ()))
+                if have == 0:
+                    raise ValueError(f"provided expected is not valid: no cis rows for view region {region_name!r}")
+                if have < hi_rel - lo_rel:
+                    raise ValueError(f"provided expected is not valid: {have} diagonals for view region "
+                                     f"{region_name!r} of {hi_rel - lo_rel} bins")
         self.chroms = natsorted(list(set(self.CC.final_chroms) & set(self.clr.chromnames)))
         self.view_df = self.view_df[self.view_df["chrom"].isin(self.chroms)]
         if self.view_df["chrom"].unique().shape[0] == 0:
@@ -496,17 +581,21 @@ class PileUpper:
         return dict(by_window=by_window, flip=flip, flipby=flipby, groupby=list(groupby),
                     ignore_group_order=ignore_group_order, modify=modify_2Dintervals_func)
 
+    def _band_edges(self, plan):
+        modify = plan["modify"]
+        if isinstance(modify, partial) and modify.func is bin_distance_intervals:
+            e = modify.keywords.get("band_edges", "default")
+            if isinstance(e, str) and e == "default":
+                e = default_band_edges()
+            return np.asarray(e)
+        return None
+
     def _region_group_codes(self, rw: RegionWindows, plan, table: _GroupTable):
-        """(flip flags, list of (target code arrays)) of a region's windows; codes are tuples of ints per column."""
+        """(flip flags, [(column, codes)]) of a region's windows; ``None`` instead of the list for by-window."""
         n = len(rw)
         modify = plan["modify"]
-        band_edges = None
-        if isinstance(modify, partial) and modify.func is bin_distance_intervals:
-            band_edges = modify.keywords.get("band_edges", "default")
-            if isinstance(band_edges, str) and band_edges == "default":
-                band_edges = default_band_edges()
-            band_edges = np.asarray(band_edges)
-        elif modify is not None:
+        band_edges = plan["band_edges"]
+        if modify is not None and band_edges is None:
             # user callback: materialise the reference's DataFrame, let the callback annotate it
             fr = modify(rw.to_frame())
             if len(fr) != n:
@@ -520,72 +609,160 @@ class PileUpper:
                 fb = plan["flipby"]
                 flipf = np.asarray(rw.column(fb + "1") > rw.column(fb + "2"))
         swap = flipf if (plan["flip"] and plan["ignore_group_order"]) else None
-        cols = []
         if plan["by_window"]:
-            return flipf, None, band_edges
+            return flipf, None
+        cols = []
         for g in plan["groupby"]:
             if g == "distance_band" and band_edges is not None:
-                cols.append(("band", _band_ids(rw.distance, band_edges)))
+                cols.append((g, _band_ids(rw.distance, band_edges)))
             else:
-                cols.append((g, table._codes(g, rw.column(g, swap=swap)) if n else np.zeros(0, dtype=np.int64)))
-        return flipf, cols, band_edges
+                table.is_dynamic(g)  # registers the column even when this region has no windows
+                cols.append((g, table.codes(g, rw.column(g, swap=swap)) if n else np.zeros(0, dtype=np.int64)))
+        return flipf, cols
+
+    def _region_nnz(self, name):
+        """Stored pixels of a view region's rows (cheap, from the cooler's row index) or None."""
+        off = getattr(self.clr, "_bin1_offset", None)
+        if off is None:
+            return None
+        r = self.view_df.loc[name]
+        lo, hi = self.clr.extent((r["chrom"], r["start"], r["end"]))
+        return int(off[hi] - off[lo])
+
+    def _region_cost(self, name):
+        """Predicted algorithmic bytes of a view region (per window 16 + 4(W+1) [+16W balanced] + 8 per
+        stored pixel), for the LPT sharding.  Stored pixels per window are modelled as W^2 * min(1, A / separation)
+        with A fitted to the region's pixel count (contact density falls like 1 / separation)."""
+        r = self.view_df.loc[name]
+        df = self.CC.intervals
+        W = 2 * self.pad_bins + 1
+        lo, hi = self.view_df_extents[name]
+        nb = max(2, hi - lo)
+        nnz = self._region_nnz(name)
+        A = 1.0 if nnz is None else max(1e-3, nnz / (nb * max(1.0, np.log(nb) - 1.0)))
+        fixed = 16 + 4 * (W + 1) + (16 * W if self.clr_weight_name else 0)
+        reps = 1 + (self.CC.nshifts if self.control else 0)
+
+        def cost_of(sep_bins):
+            px = W * W * np.minimum(1.0, A / np.maximum(np.abs(sep_bins), 1.0))
+            return float(np.sum(fixed + 8.0 * px)) * reps
+
+        if self.CC.kind == "bedpe":
+            m = ((df["chrom1"].values == r["chrom"]) & (df["start1"].values >= r["start"]) & (df["end1"].values < r["end"]))
+            return cost_of(df["distance"].values[m] / self.resolution)
+        m = (df["chrom"].values == r["chrom"]) & (df["start"].values >= r["start"]) & (df["end"].values < r["end"])
+        c = np.sort(df["center"].values[m]) / self.resolution
+        if self.local:
+            return cost_of(np.zeros(len(c)))
+        if len(c) > 3000:  # quadratic: sample the sites, scale to all pairs
+            sub = c[:: len(c) // 1500]
+            d = (sub[None, :] - sub[:, None])[np.triu_indices(len(sub), 1)]
+            return cost_of(d[np.abs(d) * self.resolution >= self.mindist]) * (len(c) / len(sub)) ** 2
+        d = (c[None, :] - c[:, None])[np.triu_indices(len(c), 1)]
+        return cost_of(d[(np.abs(d) * self.resolution >= self.mindist) & (np.abs(d) * self.resolution <= self.maxdist)])
+
+    def _needs_exact_merge(self):
+        """True when a pixel can become +inf (x / 0 with ooe): the reference's region / group merge then turns it
+        into 1.797e308 (np.nan_to_num inside sum_pups, lib/puputils.py:97-98), which depends on how the partial
+        pile-ups were grouped -- reproduced by :meth:`_exact_merge` from per-region accumulators."""
+        if not (self.expected is True and self.ooe):
+            return False
+        return any(np.any(v == 0) for v in self._expected_values.values())
 
     def _prepare(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions=None,
                  dist=None):
-        """Host phase: window arrays, group dictionary and accumulator slots of my view regions (no GPU needed)."""
+        """Host phase: window arrays, dense group keys and accumulator slots of my sharding units (no GPU needed)."""
         plan = self._plan(groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func)
+        plan["band_edges"] = self._band_edges(plan)
         W = 2 * self.pad_bins + 1
-        table = _GroupTable(self.CC, plan["groupby"], plan["by_window"])
+        table = _GroupTable(self.CC)
         region_names = list(self.view_df.index) if regions is None else list(regions)
-        my_regions = region_names if dist is None else dist.my_items(region_names, self._region_cost)
         do_control = bool(self.control)
         expctrl = bool(self.expected is True and not self.ooe)
+        splittable = not (self.store_stripes or (modify_2Dintervals_func is not None and plan["band_edges"] is None))
+        imbalance = 1.0
+        if dist is None or dist.world_size == 1:
+            my_units = {name: (0, 1) for name in region_names}
+        else:
+            costs = [self._region_cost(n) for n in region_names]
+            units, imbalance = dist.my_units(region_names, costs, max_share=0.25 if splittable else 1e9)
+            my_units = {name: (part, parts) for name, part, parts in units}
         built = []
         for ri, name in enumerate(region_names):
             r = self.view_df.loc[name]
-            if name not in my_regions:
+            region = (r["chrom"], r["start"], r["end"])
+            if name not in my_units:
                 if do_control and self.CC.nshifts > 0:
-                    # another rank's region: still draw its control shifts so that every rank consumes the
-                    # np.random stream exactly like the reference's serial (nproc=1) run
-                    self.CC.region_windows((r["chrom"], r["start"], r["end"]), control=True)
+                    # another rank's region: make its np.random draws (no window layout) so that every rank consumes
+                    # the random stream exactly like the reference's serial (nproc=1) run
+                    build_region_windows(self.CC, region, True, draw_only=True)
                 continue
-            rw = self.CC.region_windows((r["chrom"], r["start"], r["end"]), control=do_control)
+            rw = self.CC.region_windows(region, control=do_control)
             if len(rw) == 0:
                 continue
-            flipf, cols, band_edges = self._region_group_codes(rw, plan, table)
+            part, parts = my_units[name]
+            pos0 = np.arange(len(rw), dtype=np.int64)
+            if parts > 1:  # my strided share of the region's windows (matrix replicated on the other owners)
+                pos0 = pos0[part::parts]
+                rw = rw.take(pos0)
+            flipf, cols = self._region_group_codes(rw, plan, table)
             lo_rel, hi_rel = self.view_df_extents[name]
             nb = hi_rel - lo_rel
             r0 = rw.st1 - lo_rel
             c0 = rw.st2 - lo_rel
             valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
+            built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, cols=cols, pos0=pos0,
+                              part=part, parts=parts))
+        # dense group keys: mixed radix over the group columns (identical on every rank), or the feature id (by-window)
+        table.finalize(dist)
+        if plan["by_window"]:
+            self._feature_ident(None)
+            colspec = [("window", len(self._ident_values))]
+        else:
+            colspec = []
+            for g in plan["groupby"]:
+                if g == "distance_band" and plan["band_edges"] is not None:
+                    colspec.append((g, len(plan["band_edges"]) + 1))
+                else:
+                    table.is_dynamic(g)
+                    colspec.append((g, table.radix(g)))
+        n_keys = 1
+        for _, radix in colspec:
+            n_keys *= int(radix)
+        if n_keys >= 2**31:
+            raise ValueError("too many possible groups for dense accumulator slots")
+        nk = 2 if do_control else 1
+        nf = 2 if plan["flip"] else 1
+        first = {}  # key -> (is_control_only, region index, position of the first valid emission)
+        for b in built:
+            rw = b["rw"]
+            n = len(rw)
             if plan["by_window"]:
                 # every window goes to the groups of both anchors (group_by_region, lib/puputils.py:218-223)
                 ident = self._feature_ident(rw)
-                keys = np.stack([ident[rw.idx1], ident[rw.idx2]], axis=1)[:, :, None]  # [n, 2, 1]
-            elif cols:
-                keys = np.stack([c for _, c in cols], axis=1)[:, None, :]  # [n, 1, ncols]
+                key = np.stack([ident[rw.idx1], ident[rw.idx2]], axis=1).reshape(-1)  # [n * 2]
+                ntarget = 2
             else:
-                keys = None
-            built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, keys=keys,
-                              band_edges=band_edges, colnames=[c for c, _ in cols] if cols else []))
-        # group dictionary: unique keys in order of first appearance (region order, stream order)
-        groups, gids, all_pos = self._assign_group_ids(built, plan, table, dist)
-        nk = 2 if do_control else 1
-        nf = 2 if plan["flip"] else 1
-        for b, gid in zip(built, gids):
-            rw = b["rw"]
-            if gid.ndim == 2:  # by-window: two targets per window
-                b["w_r0"] = np.repeat(b["r0"], 2)
-                b["w_c0"] = np.repeat(b["c0"], 2)
-                kind = np.repeat(rw.kind, 2)
-                flip = np.repeat(b["flip"], 2)
-                g = gid.reshape(-1)
-                b["targets"] = 2
-            else:
-                b["w_r0"], b["w_c0"], kind, flip, g = b["r0"], b["c0"], rw.kind, b["flip"], gid
-                b["targets"] = 1
-            b["gid"] = g
-            b["slot"] = (g * nk + kind.astype(np.int64)) * nf + flip.astype(np.int64)
+                key = np.zeros(n, dtype=np.int64)
+                for (g, radix), (_, codes) in zip(colspec, b["cols"]):
+                    key = key * int(radix) + table.remap(g, codes)
+                ntarget = 1
+            b["targets"] = ntarget
+            kind = np.repeat(rw.kind, ntarget).astype(np.int64)
+            flip = np.repeat(b["flip"], ntarget).astype(np.int64)
+            b["w_r0"] = np.repeat(b["r0"], ntarget)
+            b["w_c0"] = np.repeat(b["c0"], ntarget)
+            b["key"] = key
+            b["slot"] = (key * nk + kind) * nf + flip
+            pos = np.repeat(b["pos0"], ntarget) * ntarget + np.tile(np.arange(ntarget), n)
+            valid = np.repeat(b["valid"], ntarget)
+            for ctrl_only, ok in ((0, valid & (kind == 0)), (1, valid & (kind != 0))):
+                for k, p_ in _first_positions(key, ok, pos).items():
+                    cand = (ctrl_only, b["index"], p_)
+                    if k not in first or cand < first[k]:
+                        first[k] = cand
+        if dist is not None:
+            first = dist.merge_min(first)
         flags = 0
         if self.expected is True and self.ooe:
             flags |= _native.PUP_F_OOE
@@ -593,8 +770,31 @@ class PileUpper:
             flags |= _native.PUP_F_EXPCTRL
         if self.coverage_norm:
             flags |= _native.PUP_F_COVERAGE
-        return dict(plan=plan, W=W, built=built, groups=groups, all_pos=all_pos, nk=nk, nf=nf,
-                    n_slots=max(1, len(groups)) * nk * nf, flags=flags, do_control=do_control, expctrl=expctrl)
+        return dict(plan=plan, W=W, built=built, colspec=colspec, table=table, first=first, nk=nk, nf=nf, n_keys=n_keys,
+                    n_slots=n_keys * nk * nf, flags=flags, do_control=do_control, expctrl=expctrl,
+                    region_names=region_names, imbalance=imbalance)
+
+    def _decode_key(self, job, key):
+        """Group key tuple (as the reference builds it, coolpup.py:71-75) of dense key ``key``."""
+        plan = job["plan"]
+        if not plan["groupby"] and not plan["by_window"]:
+            return "all"
+        if plan["by_window"]:
+            c, s_, e = self._ident_values[key]
+            return (c, int(s_), int(e))
+        vals = []
+        for g, radix in reversed(job["colspec"]):
+            key, code = divmod(key, int(radix))
+            if g == "distance_band" and plan["band_edges"] is not None:
+                vals.append(tuple(plan["band_edges"][code - 1 : code + 1]))
+            else:
+                vals.append(job["table"].value(g, code))
+        return tuple(reversed(vals))
+
+    def _region_kwargs(self, name, flags):
+        nb, indptr, col, cnt, weight, exp, cov, upper = self._region_arrays(name)
+        return dict(nb=nb, indptr=indptr, col=col, count=cnt, weight=weight, expected=exp, coverage=cov,
+                    ignore_diags=self.ignore_diags, flags=flags & (_native.PUP_F_OOE | _native.PUP_F_NODIAG), upper=upper)
 
     def _run(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions=None,
              dist=None):
@@ -603,53 +803,208 @@ class PileUpper:
         job = self._prepare(groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions, dist)
         W, n_slots, flags = job["W"], job["n_slots"], job["flags"]
         stride = _native.acc_stride(W)
+        exact = self._needs_exact_merge()
         acc = _native.alloc_accumulator(n_slots * stride, self._device)
-        stream = _native.current_stream(self._device)
-        self._last_stats = {"windows": 0, "launches": 0, "regions": 0}
+        pipe = _native.make_pipeline(self._device, W, n_slots, flags)
+        region_acc = {}
         for b in job["built"]:
-            nb, indptr, col, cnt, weight, exp, cov, upper = self._region_arrays(b["name"])
-            region = _native.Region(self._device, nb, indptr, col, cnt, weight, exp, cov,
-                                    ignore_diags=self.ignore_diags, flags=flags, stream=stream, upper=upper)
-            self._last_stats["launches"] += int(_native.lib().pup_last_launches())
-            try:
-                nv = region.accumulate(
-                    np.ascontiguousarray(b["w_r0"], dtype=np.int32), np.ascontiguousarray(b["w_c0"], dtype=np.int32),
-                    np.ascontiguousarray(b["slot"], dtype=np.int32), W, n_slots, flags, acc,
-                    stream=stream, want_n_valid=True)
-                if self.store_stripes:
+            target = acc
+            if exact:  # per-region accumulators: the reference's merge is not a plain sum when +inf occurs
+                target = region_acc[b["name"]] = _native.alloc_accumulator(n_slots * stride, self._device)
+            after = None
+            if self.store_stripes:
+                def after(region, stream, b=b):
                     # per-ROI centre row / column (coolpup.py:1164-1182); a by-window pair is computed once
                     sel = np.nonzero(b["valid"] & (b["rw"].kind == 0))[0]
                     hor, ver = region.stripes(np.ascontiguousarray(b["r0"][sel], dtype=np.int32),
                                               np.ascontiguousarray(b["c0"][sel], dtype=np.int32), W, stream=stream)
                     b["stripes"] = (sel, hor, ver)
-            finally:
-                region.close()
-            self._last_stats["windows"] += int(nv)
-            self._last_stats["launches"] += int(_native.lib().pup_last_launches())
-            self._last_stats["regions"] += 1
+            pipe.submit(self._region_kwargs(b["name"], flags), (b["w_r0"], b["w_c0"], b["slot"]), target, after=after)
             n_roi = int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))) * b["targets"]
             if n_roi > 0:
                 logger.info(f"{(b['name'], b['name'])}: {n_roi}")
+        pipe.finish()
+        if exact:
+            for a in region_acc.values():
+                acc += a
         if dist is not None:
             dist.all_reduce(acc)
-        out = _native.acc_export(acc, W, n_slots, device=self._device, stream=stream, want_expected=job["expctrl"],
-                                 want_cov=bool(self.coverage_norm))
+        stream = _native.current_stream(self._device)
+        out, used = self._export_used(acc, job, stream)
+        self._last_stats = {"windows": int(out["n"].sum()), "launches": pipe.launches, "regions": pipe.regions,
+                            "imbalance": job["imbalance"], "n_slots": n_slots, "used_slots": int(len(used))}
         plan = job["plan"]
-        roi, ctrl = self._slots_to_pups(out, job["groups"], job["nk"], job["nf"], W, job["expctrl"], job["do_control"],
-                                        grouped=bool(plan["groupby"]) or plan["by_window"], all_pos=job["all_pos"])
+        grouped = bool(plan["groupby"]) or plan["by_window"]
+        roi, ctrl = self._slots_to_pups(out, used, job, grouped)
+        if exact:
+            self._exact_merge(job, region_acc, roi, ctrl, grouped, dist, stream)
         if self.store_stripes:
-            if dist is not None and dist.world_size > 1:
-                raise NotImplementedError("store_stripes is a per-ROI output and is not gathered across ranks")
-            self._attach_stripes(job, roi)
+            self._attach_stripes(job, roi, dist)
         return roi, ctrl
 
-    def _attach_stripes(self, job, roi):
+    def _export_used(self, acc, job, stream):
+        """Decode the accumulator slots that hold at least one window (``n > 0``): with dense group keys most slots
+        of a by-strand / by-distance / by-window run stay empty and are neither copied to the host nor decoded."""
+        W, n_slots = job["W"], job["n_slots"]
+        stride = _native.acc_stride(W)
+        n_all = _native.acc_counts(acc, W, n_slots)
+        used = np.nonzero(n_all > 0)[0]
+        if len(used) == n_slots or n_slots <= 8:
+            used = np.arange(n_slots)
+            sub = acc
+        else:
+            import torch
+
+            idx = torch.from_numpy(used).to(acc.device)
+            sub = acc.view(n_slots, stride).index_select(0, idx).reshape(-1) if len(used) else acc[:0]
+        out = _native.acc_export(sub, W, len(used), device=self._device, stream=stream, want_expected=job["expctrl"],
+                                 want_cov=bool(self.coverage_norm)) if len(used) else {
+            "sum": np.zeros((0, W, W)), "num": np.zeros((0, W, W), dtype=np.int64), "n": np.zeros(0, dtype=np.int64)}
+        return out, used
+
+    def _slot_pups(self, out, used, job):
+        """{key: {kind: pup}} of the exported slots, flipped slots anti-transposed (coolpup.py:130) and merged."""
+        nk, nf, W = job["nk"], job["nf"], job["W"]
+        row_of = {int(s_): i for i, s_ in enumerate(used)}
+
+        def antit(a):
+            return a[..., ::-1, ::-1].swapaxes(-1, -2)
+
+        def gather(field, key, kind):
+            v = None
+            for f in range(nf):
+                i = row_of.get((key * nk + kind) * nf + f)
+                if i is None:
+                    continue
+                w = out[field][i]
+                if f == 1 and w.ndim == 2 and field in ("sum", "num"):
+                    w = antit(w)
+                v = w if v is None else v + w
+            return v
+
+        pups = {}
+        for key in sorted({int(s_) // (nk * nf) for s_ in used}):
+            per_kind = {}
+            for kind in range(nk):
+                n = gather("n", key, kind)
+                if n is None or int(n) == 0:
+                    continue
+                p = {"data": gather("sum", key, kind), "num": gather("num", key, kind), "n": int(n),
+                     "horizontal_stripe": [], "vertical_stripe": [], "coordinates": []}
+                if "cov_start" in out:
+                    p["cov_start"] = gather("cov_start", key, kind)
+                    p["cov_end"] = gather("cov_end", key, kind)
+                else:
+                    p["cov_start"] = np.zeros(W)
+                    p["cov_end"] = np.zeros(W)
+                per_kind[kind] = p
+            if job["expctrl"] and 0 in per_kind:
+                # bare expected blocks are Toeplitz, hence invariant under the anti-transpose flip
+                p = per_kind[0]
+                per_kind[1] = {"data": gather("exp_sum", key, 0), "num": gather("exp_num", key, 0), "n": p["n"],
+                               "cov_start": p["cov_start"].copy(), "cov_end": p["cov_end"].copy(),
+                               "horizontal_stripe": [], "vertical_stripe": [], "coordinates": []}
+            if per_kind:
+                pups[key] = per_kind
+        return pups
+
+    def _slots_to_pups(self, out, used, job, grouped):
+        """Per-group ROI / control pile-ups in the reference's row order: groups by first valid ROI emission (regions
+        in view order), ``"all"`` = sum over groups placed after the groups first seen in the first view region
+        (coolpup.py:1272-1275, 1511-1520)."""
+        W = job["W"]
+        first = job["first"]
+        pups = self._slot_pups(out, used, job)
+        order = sorted((k for k in pups if k in first), key=lambda k: first[k])
+        roi, ctrl = {}, {}
+        for key in order:
+            name = self._decode_key(job, key)
+            if 0 in pups[key]:
+                roi[name] = pups[key][0]
+            if 1 in pups[key]:
+                ctrl[name] = pups[key][1]
+        has_ctrl = job["do_control"] or job["expctrl"]
+        if not grouped:
+            roi.setdefault("all", _empty_pup(W))
+            if has_ctrl:
+                ctrl.setdefault("all", _empty_pup(W))
+            return roi, ctrl
+        first_region = min((v[1] for v in first.values()), default=0)
+        n_first_region = sum(1 for k in order if 0 in pups[k] and first[k][0] == 0 and first[k][1] == first_region)
+        for d, present in ((roi, True), (ctrl, has_ctrl)):
+            if not present:
+                continue
+            tot = _empty_pup(W)
+            for p in d.values():
+                tot["data"] = tot["data"] + np.nan_to_num(p["data"])
+                tot["num"] = tot["num"] + p["num"]
+                tot["n"] += p["n"]
+                tot["cov_start"] = tot["cov_start"] + p["cov_start"]
+                tot["cov_end"] = tot["cov_end"] + p["cov_end"]
+            items = list(d.items())
+            items.insert(min(n_first_region, len(items)), ("all", tot))
+            d.clear()
+            d.update(items)
+        return roi, ctrl
+
+    def _exact_merge(self, job, region_acc, roi, ctrl, grouped, dist, stream):
+        """Replace ``data`` of the merged pile-ups by what the reference's reduce produces when +inf pixels exist.
+
+        Reference semantics (coolpup.py:1272-1282, 1511-1531; lib/puputils.py:88-113): inside a region nansum keeps
+        +inf; building the region's ``"all"`` from its groups rebinds every group's ``data`` to ``nan_to_num(data)``
+        (+inf -> 1.797e308) and sums them; merging regions applies ``nan_to_num`` again whenever a key occurs in at
+        least two regions (a single occurrence is taken as it is).  1.797e308 + 1.797e308 overflows back to +inf, which
+        the final ``== inf -> NaN`` rule removes.  Every other field is additive and comes from the summed accumulator.
+        """
+        W = job["W"]
+        per_region = {}
+        for name, a in region_acc.items():
+            out, used = self._export_used(a, job, stream)
+            pups = self._slot_pups(out, used, job)
+            per_region[name] = {kind: {self._decode_key(job, k): v[kind]["data"] for k, v in pups.items() if kind in v}
+                                for kind in (0, 1)}
+        if dist is not None and dist.world_size > 1:
+            merged = {}
+            for part in dist.all_gather_object(per_region):
+                for name, kinds in part.items():
+                    tgt = merged.setdefault(name, {0: {}, 1: {}})
+                    for kind, groups in kinds.items():
+                        for g, data in groups.items():  # a region split over ranks: nansum semantics, inf kept
+                            tgt[kind][g] = data if g not in tgt[kind] else tgt[kind][g] + data
+            per_region = merged
+        has_ctrl = job["do_control"] or job["expctrl"]
+        for kind, d in ((0, roi), (1, ctrl)):
+            if kind == 1 and not has_ctrl:
+                continue
+            contrib = {}  # key -> [data per region, view order]
+            for name in job["region_names"]:  # every view region the reference maps pileup_region over
+                groups = dict(per_region.get(name, {0: {}, 1: {}})[kind])
+                if grouped:
+                    tot = np.zeros((W, W))
+                    for g in groups:
+                        groups[g] = np.nan_to_num(groups[g])
+                        tot = np.nan_to_num(tot) + groups[g]
+                    groups["all"] = tot
+                elif "all" not in groups:
+                    groups["all"] = np.zeros((W, W))
+                for g, data in groups.items():
+                    contrib.setdefault(g, []).append(data)
+            for g, p in d.items():
+                lst = contrib.get(g, [])
+                if len(lst) == 1:
+                    p["data"] = lst[0]
+                elif lst:
+                    total = lst[0]
+                    for x in lst[1:]:
+                        total = np.nan_to_num(total) + np.nan_to_num(x)
+                    p["data"] = total
+
+    def _attach_stripes(self, job, roi, dist=None):
         """Per-group lists of stripes / coordinates in the reference's order: regions in view order; within a region
         the groups in order of first appearance, each in stream order; "all" concatenates the region's groups
         (sum_pups list concatenation, lib/puputils.py:105-107; coolpup.py:1272-1275)."""
         grouped = bool(job["plan"]["groupby"]) or job["plan"]["by_window"]
-        groups = job["groups"]
-        lists = {k: {"horizontal_stripe": [], "vertical_stripe": [], "coordinates": []} for k in roi}
+        per_region = {}
         for b in job["built"]:
             if "stripes" not in b:
                 continue
@@ -662,36 +1017,34 @@ class PileUpper:
             else:
                 cols = [s_[c].to_numpy()[rw.idx1[sel]] for c in ("chrom1", "start1", "end1", "chrom2", "start2", "end2")]
             coords = [".".join(str(x.item() if isinstance(x, np.generic) else x) for x in row) for row in zip(*cols)]
-            gid = b["gid"].reshape(len(rw), -1)[sel]  # [n_sel, targets]
+            keys = b["key"].reshape(len(rw), -1)[sel]  # [n_sel, targets]
             per_group = {}
             order = []
             for j in range(len(sel)):
-                for g in gid[j]:
-                    key = groups[int(g)] if grouped else "all"
-                    if key not in per_group:
-                        per_group[key] = []
-                        order.append(key)
-                    per_group[key].append(j)
-            for key in order:
-                if key not in lists:
+                for k in keys[j]:
+                    name = self._decode_key(job, int(k)) if grouped else "all"
+                    if name not in per_group:
+                        per_group[name] = []
+                        order.append(name)
+                    per_group[name].append(j)
+            per_region[b["index"]] = [(name, [(hor[j], ver[j], coords[j]) for j in per_group[name]]) for name in order]
+        if dist is not None and dist.world_size > 1:  # whole regions per rank (stripes are never window-split)
+            merged = {}
+            for part in dist.all_gather_object(per_region):
+                merged.update(part)
+            per_region = merged
+        lists = {k: {"horizontal_stripe": [], "vertical_stripe": [], "coordinates": []} for k in roi}
+        for index in sorted(per_region):
+            for name, rows in per_region[index]:
+                if name not in lists:
                     continue
-                for j in per_group[key]:
-                    for dst in ([key, "all"] if grouped else [key]):
-                        lists[dst]["horizontal_stripe"].append(hor[j])
-                        lists[dst]["vertical_stripe"].append(ver[j])
-                        lists[dst]["coordinates"].append(coords[j])
+                for h, v, c in rows:
+                    for dst in ([name, "all"] if grouped else [name]):
+                        lists[dst]["horizontal_stripe"].append(h)
+                        lists[dst]["vertical_stripe"].append(v)
+                        lists[dst]["coordinates"].append(c)
         for k, p in roi.items():
             p.update(lists[k])
-
-    def _region_cost(self, name):
-        """Predicted relative cost of a region (for LPT sharding): number of feature pairs."""
-        r = self.view_df.loc[name]
-        df = self.CC.intervals
-        if self.CC.kind == "bedpe":
-            n = int(((df["chrom1"] == r["chrom"]) & (df["start1"] >= r["start"]) & (df["end1"] < r["end"])).sum())
-            return n
-        n = int(((df["chrom"] == r["chrom"]) & (df["start"] >= r["start"]) & (df["end"] < r["end"])).sum())
-        return n if self.local else n * (n - 1) // 2
 
     def _feature_ident(self, rw):
         """Global integer identity of each feature of the region table for by-window grouping."""
@@ -701,153 +1054,11 @@ class PileUpper:
             uniq = triples.unique()
             self._ident_values = list(uniq)
             self._ident_index = pd.Series(np.arange(len(uniq), dtype=np.int64), index=uniq)
+        if rw is None:
+            return None
         s = rw.sel
         mi = pd.MultiIndex.from_arrays([s["chrom"].values, s["start"].values, s["end"].values])
         return self._ident_index.reindex(mi).values.astype(np.int64)
-
-    @staticmethod
-    def _unique_rows(flat):
-        """``(unique rows, index of each one's first occurrence, inverse)`` of an integer key matrix, by hashing one
-        mixed-radix int64 per row instead of ``np.unique(axis=0)``'s lexicographic sort."""
-        n = flat.shape[0]
-        if n == 0 or flat.shape[1] == 0:
-            return flat[:0], np.zeros(0, dtype=np.int64), np.zeros(n, dtype=np.int64)
-        lo = flat.min(axis=0)
-        radix = (flat.max(axis=0) - lo + 1).astype(object)
-        span = 1
-        for r in radix:
-            span *= int(r)
-        if span >= 2**62:  # cannot happen with group codes; keep the exact (slow) path for safety
-            uniq, idx, inv = np.unique(flat, axis=0, return_index=True, return_inverse=True)
-            return uniq, idx, np.asarray(inv).reshape(-1)
-        ck = np.zeros(n, dtype=np.int64)
-        for j in range(flat.shape[1]):
-            ck = ck * int(radix[j]) + (flat[:, j] - lo[j])
-        inv, _ = pd.factorize(ck)
-        first = np.empty(int(inv.max()) + 1, dtype=np.int64)
-        first[inv[::-1]] = np.arange(n - 1, -1, -1, dtype=np.int64)  # the smallest index is written last
-        return flat[first], first, inv.astype(np.int64)
-
-    def _assign_group_ids(self, built, plan, table, dist):
-        """Dense group ids.  Returns (groups, gids, all_pos): ``groups`` lists the group keys in the reference's
-        row order (first valid ROI emission, regions in view order), ``all_pos`` is where the reference's
-        ``"all"`` row sits among them (after the groups first seen in the first view region, coolpup.py:1272-1275,
-        1511-1520)."""
-        if not plan["groupby"] and not plan["by_window"]:
-            return ["all"], [np.zeros(len(b["rw"]), dtype=np.int64) for b in built], 0
-        first = {}  # code tuple -> (is_control_only, region index, position of first valid emission)
-        for b in built:
-            keys = b["keys"]
-            ntarget = keys.shape[1]
-            flat = keys.reshape(len(keys) * ntarget, -1)
-            b["_flat"] = flat
-            for ctrl_only, ok in ((0, b["valid"] & (b["rw"].kind == 0)), (1, b["valid"] & (b["rw"].kind != 0))):
-                ok = np.repeat(ok, ntarget)
-                if not ok.any():
-                    continue
-                uniq, idx, _ = self._unique_rows(flat[ok])
-                pos = np.nonzero(ok)[0][idx]
-                for u, p in zip(map(tuple, uniq.tolist()), pos.tolist()):
-                    cand = (ctrl_only, b["index"], p)
-                    if u not in first or cand < first[u]:
-                        first[u] = cand
-        if dist is not None:
-            first = dist.merge_min(first)
-        order = sorted(first, key=lambda u: first[u])
-        lookup = {u: i for i, u in enumerate(order)}
-        all_pos = sum(1 for u in order if first[u][0] == 0 and first[u][1] == 0)
-        colnames = next((b["colnames"] for b in built), [])
-        edges = next((b["band_edges"] for b in built if b["band_edges"] is not None), None)
-        groups = []
-        for u in order:
-            if plan["by_window"]:
-                c, s, e = self._ident_values[u[0]]
-                groups.append((c, int(s), int(e)))
-            else:
-                vals = []
-                for colname, code in zip(colnames, u):
-                    if colname == "band":
-                        vals.append(tuple(edges[code - 1 : code + 1]))
-                    else:
-                        vals.append(table.value(colname, code))
-                groups.append(tuple(vals))
-        gids = []
-        for b in built:
-            flat = b.pop("_flat")
-            ntarget = b["keys"].shape[1]
-            uniq, _, inv = self._unique_rows(flat)
-            # keys that never occur in a valid window are skipped by the kernel anyway: park them in group 0
-            m = np.array([lookup.get(tuple(u), 0) for u in uniq.tolist()], dtype=np.int64)
-            gid = m[np.asarray(inv).reshape(-1)]
-            gids.append(gid.reshape(-1, ntarget) if ntarget == 2 else gid)
-        return groups, gids, all_pos
-
-    def _slots_to_pups(self, out, groups, nk, nf, W, expctrl, do_control, grouped, all_pos=0):
-        """Per-group pile-ups from per-slot accumulators; flipped slots are anti-transposed (coolpup.py:130)."""
-
-        def antit(a):
-            return a[..., ::-1, ::-1].swapaxes(-1, -2)
-
-        def gather(field, g, kind):
-            s0 = (g * nk + kind) * nf
-            v = out[field][s0]
-            if nf == 2:
-                w = out[field][s0 + 1]
-                v = v + (antit(w) if w.ndim == 2 else w)
-            return v
-
-        roi, ctrl = {}, {}
-        for g, key in enumerate(groups):
-            p = {"data": gather("sum", g, 0), "num": gather("num", g, 0), "n": int(gather("n", g, 0)),
-                 "horizontal_stripe": [], "vertical_stripe": [], "coordinates": []}
-            if "cov_start" in out:
-                p["cov_start"] = gather("cov_start", g, 0)
-                p["cov_end"] = gather("cov_end", g, 0)
-            else:
-                p["cov_start"] = np.zeros(W)
-                p["cov_end"] = np.zeros(W)
-            roi[key] = p
-            if do_control:
-                c = {"data": gather("sum", g, 1), "num": gather("num", g, 1), "n": int(gather("n", g, 1)),
-                     "horizontal_stripe": [], "vertical_stripe": [], "coordinates": []}
-                if "cov_start" in out:
-                    c["cov_start"] = gather("cov_start", g, 1)
-                    c["cov_end"] = gather("cov_end", g, 1)
-                else:
-                    c["cov_start"] = np.zeros(W)
-                    c["cov_end"] = np.zeros(W)
-                ctrl[key] = c
-            elif expctrl:
-                # bare expected blocks are Toeplitz, hence invariant under the anti-transpose flip
-                s0 = g * nk * nf
-                es = sum(out["exp_sum"][s0 + f] for f in range(nf))
-                en = sum(out["exp_num"][s0 + f] for f in range(nf))
-                ctrl[key] = {"data": es, "num": en, "n": p["n"], "cov_start": p["cov_start"].copy(),
-                             "cov_end": p["cov_end"].copy(), "horizontal_stripe": [], "vertical_stripe": [],
-                             "coordinates": []}
-        # groups without any accumulated window do not exist in the reference's dictionaries
-        n_first_region = sum(1 for k in list(roi)[:all_pos] if roi[k]["n"] > 0)
-        for d in (roi, ctrl):
-            for k in [k for k, p in d.items() if p["n"] == 0 and not (isinstance(k, str) and k == "all")]:
-                del d[k]
-        if grouped:  # "all" = sum over groups (coolpup.py:1272-1282), placed where the reference's DataFrame has it
-            for which, d, present in (("roi", roi, True), ("ctrl", ctrl, do_control or expctrl)):
-                if not present:
-                    continue
-                tot = {"data": np.zeros((W, W)), "num": np.zeros((W, W), dtype=np.int64), "n": 0,
-                       "cov_start": np.zeros(W), "cov_end": np.zeros(W), "horizontal_stripe": [],
-                       "vertical_stripe": [], "coordinates": []}
-                for p in d.values():
-                    tot["data"] = tot["data"] + np.nan_to_num(p["data"])
-                    tot["num"] = tot["num"] + p["num"]
-                    tot["n"] += p["n"]
-                    tot["cov_start"] = tot["cov_start"] + p["cov_start"]
-                    tot["cov_end"] = tot["cov_end"] + p["cov_end"]
-                items = list(d.items())
-                items.insert(min(n_first_region, len(items)), ("all", tot))
-                d.clear()
-                d.update(items)
-        return roi, ctrl
 
     def pileup_region(self, region1, region2=None, groupby=[], modify_2Dintervals_func=None, postprocess_func=None,
                       extra_sum_funcs=None):
@@ -1033,6 +1244,11 @@ class PileUpper:
         pups = pd.concat([_sort_rows(pups.drop(i), ["orientation", "distance_band"]), pups.iloc[i, :]],
                          ignore_index=True)
         return pups.reset_index(drop=True)
+
+
+def _empty_pup(W):
+    return {"data": np.zeros((W, W)), "num": np.zeros((W, W), dtype=np.int64), "n": 0, "cov_start": np.zeros(W),
+            "cov_end": np.zeros(W), "horizontal_stripe": [], "vertical_stripe": [], "coordinates": []}
 
 
 def _objcol(values):

@@ -186,6 +186,8 @@ class EmuRegion:
 def emu_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):
     L = layout(W)
     a = (acc.numpy() if hasattr(acc, "numpy") else acc).reshape(n_slots, L["stride"])
+    if n_slots == 0:
+        return {"sum": np.zeros((0, W, W)), "num": np.zeros((0, W, W), dtype=np.int64), "n": np.zeros(0, dtype=np.int64)}
     out = {"sum": a[:, : L["w2"]].reshape(n_slots, W, W).copy(), "n": np.rint(a[:, L["n"]]).astype(np.int64)}
     numt = a[:, L["num"] : L["num"] + L["w2"]].reshape(n_slots, W, W)
     rb = a[:, L["rb"] : L["rb"] + W]
@@ -202,6 +204,26 @@ def emu_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_co
     return out
 
 
+class SerialPipeline:
+    """Stand-in for coolpuppy_b200.pipeline.RegionPipeline: same interface, regions done one after the other."""
+
+    def __init__(self, device, W, n_slots, flags):
+        self.W, self.n_slots, self.flags = W, n_slots, flags
+        self.launches = 0
+        self.regions = 0
+
+    def submit(self, region_kwargs, windows, acc, after=None, windows_on_device=None):
+        region = EmuRegion(0, **region_kwargs)
+        r0, c0, slot = windows
+        region.accumulate(np.asarray(r0), np.asarray(c0), np.asarray(slot), self.W, self.n_slots, self.flags, acc)
+        if after is not None:
+            after(region, 0)
+        self.regions += 1
+
+    def finish(self):
+        pass
+
+
 def install(monkeypatch):
     """Route coolpuppy_b200._native's device entry points to the emulator (tests only)."""
     import torch
@@ -212,6 +234,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_native, "alloc_accumulator", lambda n, device: torch.zeros(int(n), dtype=torch.float64))
     monkeypatch.setattr(_native, "current_stream", lambda device: 0)
     monkeypatch.setattr(_native, "acc_stride", lambda W: layout(int(W))["stride"])
+    monkeypatch.setattr(_native, "make_pipeline", SerialPipeline)
 
     real = _native.lib()  # host-side entry points (window layout) are the real library: they need no device
 

@@ -169,9 +169,9 @@ def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots)
     np.testing.assert_allclose(ver, ever, rtol=RTOL, equal_nan=True)
 
 
-@pytest.mark.parametrize("env", [{"PUP_SCHED": "0"}, {"PUP_SCHED": "1"}, {"PUP_MINB": "3"}, {"PUP_TILE_PAD": "1"},
-                                 {"PUP_TILE_PAD": "5", "PUP_MINB": "3"}, {"PUP_TILE_INTERLEAVE": "1"},
-                                 {"PUP_TILE_INTERLEAVE": "1", "PUP_MINB": "3", "PUP_CHUNK": "16"}, {"PUP_CHUNK": "7"}])
+@pytest.mark.parametrize("env", [{"PUP_SCHED": "0"}, {"PUP_SCHED": "1"}, {"PUP_TILE_PAD": "1"},
+                                 {"PUP_TILE_PAD": "5", "PUP_TILE_INTERLEAVE": "0"}, {"PUP_TILE_INTERLEAVE": "1"},
+                                 {"PUP_TILE_INTERLEAVE": "0", "PUP_CHUNK": "16"}, {"PUP_SORT_C0_BITS": "0"}, {"PUP_SORT_C0_BITS": "3"}, {"PUP_CHUNK": "7"}])
 @pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(700, 83, 200, 2500, 3), (900, 203, 400, 90, 2), (300, 21, 30, 4000, 5)])
 def test_main_kernel_variants(monkeypatch, env, nb, W, dens, nwin, n_slots):
     """Scheduling (static round-robin / barrier-free dynamic ring), occupancy and tile-layout variants of the main

@@ -114,3 +114,57 @@ def test_custom_modify_func_and_extra_groupby(emu):
     a = out.loc[out["group"] == "all", "data"].iloc[0]
     b = base.loc[base["group"] == "all", "data"].iloc[0]
     np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=1e-12)
+
+
+def test_missing_group_values_form_their_own_group(emu):
+    """A NaN in a groupby column must neither wrap around to the last group nor crash: the windows of
+    that feature land in a (nan, ...) group, every other count is unchanged."""
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs("toy_strand_balanced")
+    feats = feats.copy()
+    feats["strand"] = feats["strand"].astype(object)
+    feats.loc[0, "strand"] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = cp.pileup(clr, feats, **kw)
+        base = cp.pileup(clr, gu.case_inputs("toy_strand_balanced")[1], **kw)
+    tot = int(out.loc[out["group"] == "all", "n"].iloc[0])
+    assert tot == int(base.loc[base["group"] == "all", "n"].iloc[0]) == 6
+    groups = [g for g in out["group"] if not isinstance(g, str)]
+    nan_groups = [g for g in groups if any(isinstance(x, float) and x != x for x in g)]
+    assert nan_groups, groups
+    assert sum(int(n) for g, n in zip(out["group"], out["n"]) if not isinstance(g, str)) == 6
+
+
+def test_dynamic_group_dictionaries_are_merged_over_ranks():
+    """Columns made by a user callback get rank-local codes while the regions are laid out; finalize() must map
+    them onto ONE dictionary (the same integer meant different values on different ranks)."""
+    from coolpuppy_b200.coolpup import _GroupTable
+
+    class CC:
+        kind = "bed"
+        import pandas as pd
+
+        intervals = pd.DataFrame({"chrom": ["chr1"], "start": [0], "end": [1]})
+
+    class FakeDist:
+        world_size = 2
+
+        def __init__(self, other):
+            self.other = other
+
+        def all_gather_object(self, obj):
+            return [obj, self.other]
+
+    t0, t1 = _GroupTable(CC), _GroupTable(CC)
+    c0 = t0.codes("cls", np.array(["b", "a", "b", None], dtype=object))
+    c1 = t1.codes("cls", np.array(["c", "a"], dtype=object))
+    assert list(c0) == [0, 1, 0, 2] and list(c1) == [0, 1]
+    t0.finalize(FakeDist(t1._dynamic["cls"]["vals"]))
+    t1.finalize(FakeDist(t0._dynamic["cls"]["vals"]))
+    assert t0.radix("cls") == t1.radix("cls") == 4
+    v0 = [t0.value("cls", k) for k in t0.remap("cls", c0)]
+    v1 = [t1.value("cls", k) for k in t1.remap("cls", c1)]
+    assert v0 == ["b", "a", "b", None] and v1 == ["c", "a"]
+    assert [t0.value("cls", k) for k in range(4)] == [t1.value("cls", k) for k in range(4)] == ["a", "b", "c", None]
