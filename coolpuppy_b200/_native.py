@@ -24,6 +24,7 @@ SYMBOLS = [
     "pup_region_destroy", "pup_upload", "pup_expected_cis", "pup_pair_windows_count", "pup_pair_windows_fill",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
+    "pup_rng_create", "pup_rng_read", "pup_rng_destroy", "pup_control_shifts", "pup_pair_windows_device",
 ]
 
 
@@ -64,6 +65,13 @@ def lib():
     L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pup_algorithmic_bytes.argtypes = [vp, i64, vp, vp, C.c_int, u32, vp, C.POINTER(i64), C.POINTER(i64)]
     L.pup_stripes.argtypes = [vp, i64, vp, vp, C.c_int, vp, vp, vp]
+    L.pup_rng_create.argtypes = [C.c_int, vp, C.c_int, vp, C.POINTER(vp)]
+    L.pup_rng_read.argtypes = [vp, vp, C.POINTER(C.c_int), vp]
+    L.pup_rng_destroy.argtypes = [vp]
+    L.pup_control_shifts.argtypes = [vp, i64, vp, i64, i64, C.c_double, vp, vp]
+    L.pup_pair_windows_device.argtypes = [C.c_int, i32, vp, vp, C.c_double, C.c_double, i32, vp, vp, i32, C.c_int, vp,
+                                          vp, vp, i32, i64, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, i32, i32, i32,
+                                          vp, vp, vp, vp, vp, vp]
     L.pup_timing_enable.argtypes = [C.c_int]
     L.pup_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
     _LIB = L
@@ -128,6 +136,12 @@ def acc_counts(acc, W, n_slots):
     stride = acc_stride(W)
     n = acc.view(int(n_slots), stride)[:, stride - 8]  # AccLayout: off_n = stride - 8
     return np.rint(n.cpu().numpy()).astype(np.int64)
+
+
+def device_windows_supported():
+    """True when windows can be generated on the device (always, with the real library; the CPU test emulator
+    replaces this by False)."""
+    return True
 
 
 def make_pipeline(device, W, n_slots, flags):
@@ -235,6 +249,65 @@ def pair_windows_fill(stbin, center, mindist, maxdist, nctrl, dbin, total):
     check(lib().pup_pair_windows_fill(int(center.shape[0]), ptr(stbin), ptr(center), float(mindist), float(maxdist),
                                       int(nctrl), ptr(dbin), ptr(st1), ptr(st2), ptr(kind), ptr(i1), ptr(i2), ptr(dist)))
     return st1, st2, kind, i1, i2, dist
+
+
+class DeviceRng:
+    """numpy's global legacy MT19937 state on the device (``pup_rng_t``): loaded from ``np.random.get_state()``,
+    advanced by :meth:`control_shifts`, written back with :meth:`store` so that host code continues the stream."""
+
+    def __init__(self, device, stream=0):
+        st = np.random.get_state()
+        if st[0] != "MT19937":
+            raise NativeError("np.random is not the legacy MT19937 generator")
+        self.device = int(device)
+        self._legacy = st
+        self._h = C.c_void_p()
+        key = np.ascontiguousarray(st[1], dtype=np.uint32)
+        check(lib().pup_rng_create(self.device, ptr(key), int(st[2]), stream, C.byref(self._h)))
+
+    def control_shifts(self, seg_sizes, minshift, maxshift, resolution, dbin, stream=0):
+        """Replay ``randint(minshift, maxshift, n); choice([-1, 1], n)`` for every ``n`` of ``seg_sizes``; ``dbin``:
+        int32 device tensor of ``sum(seg_sizes)`` bins (``None``: only advance the stream)."""
+        seg = np.ascontiguousarray(seg_sizes, dtype=np.int64)
+        if seg.size == 0:
+            return
+        check(lib().pup_control_shifts(self._h, int(seg.size), ptr(seg), int(minshift), int(maxshift), float(resolution),
+                                       ptr(dbin), stream))
+
+    def store(self, stream=0):
+        """Write the advanced state back into ``np.random`` (synchronises ``stream``)."""
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int(0)
+        check(lib().pup_rng_read(self._h, ptr(key), C.byref(pos), stream))
+        st = self._legacy
+        np.random.set_state((st[0], key, int(pos.value), st[3], st[4]))
+
+    def close(self):
+        if self._h:
+            lib().pup_rng_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pair_windows_device(device, stbin, center, mindist, maxdist, nctrl, per_offset, dbin, nb, W, key1, key2, band_edges,
+                        band_weight, flip_mode, swap_on_flip, flipval, ident, nk, nf, part, parts, region_index, r0, c0,
+                        slot, first_seen=None, n_roi=None, stream=0):
+    """``pup_pair_windows_device``: all-vs-all windows + slots of one region written into the device tensors
+    ``r0 / c0 / slot`` in the reference's emission order."""
+    m = int(center.shape[0])
+    if int(r0.shape[0]) == 0:  # this strided share holds no window
+        return
+    check(lib().pup_pair_windows_device(
+        int(device), m, ptr(stbin, np.int32), ptr(center, np.float64), float(mindist), float(maxdist),
+        int(nctrl), ptr(per_offset, np.int64), ptr(dbin), int(nb), int(W), ptr(key1), ptr(key2), ptr(band_edges),
+        0 if band_edges is None else int(band_edges.shape[0]), int(band_weight), int(flip_mode), int(bool(swap_on_flip)),
+        ptr(flipval), ptr(ident), int(nk), int(nf), int(part), int(parts), int(region_index), ptr(r0), ptr(c0),
+        ptr(slot), ptr(first_seen), ptr(n_roi), stream))
 
 
 def expected_cis_sums(device, nb, indptr_upper, col_upper, count_upper, weight=None, stream=0):

@@ -669,11 +669,9 @@ class PileUpper:
             return False
         return any(np.any(v == 0) for v in self._expected_values.values())
 
-    def _prepare(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions=None,
-                 dist=None):
+    def _prepare(self, plan, regions=None, dist=None):
         """Host phase: window arrays, dense group keys and accumulator slots of my sharding units (no GPU needed)."""
-        plan = self._plan(groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func)
-        plan["band_edges"] = self._band_edges(plan)
+        modify_2Dintervals_func = plan["modify"]
         W = 2 * self.pad_bins + 1
         table = _GroupTable(self.CC)
         region_names = list(self.view_df.index) if regions is None else list(regions)
@@ -796,17 +794,199 @@ class PileUpper:
         return dict(nb=nb, indptr=indptr, col=col, count=cnt, weight=weight, expected=exp, coverage=cov,
                     ignore_diags=self.ignore_diags, flags=flags & (_native.PUP_F_OOE | _native.PUP_F_NODIAG), upper=upper)
 
-    def _run(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions=None,
-             dist=None):
-        """Accumulate all (or the given) view regions on the GPU; returns the merged ROI / control pile-ups."""
-        _native.require_device()
-        job = self._prepare(groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions, dist)
+    def _device_windows_ok(self, plan):
+        """Can the windows of this run be generated on the GPU (``pup_pair_windows_device``)?  Yes for bed features
+        paired all-vs-all grouped by feature columns / strands / distance bands / by window; bedpe, local pile-ups,
+        user callbacks and per-ROI stripes keep the host window builder."""
+        if os.environ.get("PUP_DEVICE_WINDOWS", "1") == "0" or not _native.device_windows_supported():
+            return False
+        if self.CC.kind != "bed" or self.local or self.store_stripes:
+            return False
+        if plan["modify"] is not None and plan["band_edges"] is None:
+            return False
+        df = self.CC.intervals
+        for g in plan["groupby"]:
+            if g == "distance_band" and plan["band_edges"] is not None:
+                continue
+            if not (g[-1] in "12" and g[:-1] in df.columns):
+                return False
+        if plan["flip"] and not self.flip_negative_strand and plan["flipby"] not in df.columns:
+            return False
+        if plan["flip"] and self.flip_negative_strand and "strand" not in df.columns:
+            return False
+        if self.control and self.CC.nshifts > 0:
+            lo, hi = int(self.CC.minshift), int(self.CC.maxshift)
+            if not (lo + 1 < hi and -2**31 < lo and hi < 2**31 and hi - 1 - lo < 2**32 - 1):
+                return False
+        return True
+
+    def _prepare_device(self, plan, regions, dist):
+        """Host phase of the device-window path: per view region only the feature table is touched (window bins,
+        centres, per-feature group-key parts, kept pairs per offset); windows, control shifts, slots and the
+        first-appearance order of the groups are produced on the GPU."""
+        W = 2 * self.pad_bins + 1
+        table = _GroupTable(self.CC)
+        df = self.CC.intervals
+        region_names = list(self.view_df.index) if regions is None else list(regions)
+        do_control = bool(self.control) and self.CC.nshifts > 0
+        expctrl = bool(self.expected is True and not self.ooe)
+        imbalance = 1.0
+        if dist is None or dist.world_size == 1:
+            my_units = {name: (0, 1) for name in region_names}
+        else:
+            costs = [self._region_cost(n) for n in region_names]
+            units, imbalance = dist.my_units(region_names, costs, max_share=0.25)
+            my_units = {name: (part, parts) for name, part, parts in units}
+        # dense key space (static columns only on this path)
+        if plan["by_window"]:
+            self._feature_ident(None)
+            colspec = [("window", len(self._ident_values))]
+        else:
+            colspec = []
+            for g in plan["groupby"]:
+                if g == "distance_band" and plan["band_edges"] is not None:
+                    colspec.append((g, len(plan["band_edges"]) + 1))
+                else:
+                    table.is_dynamic(g)
+                    colspec.append((g, table.radix(g)))
+        weights, wgt = [], 1
+        for _, radix in reversed(colspec):
+            weights.append(wgt)
+            wgt *= int(radix)
+        weights = weights[::-1]
+        n_keys = wgt
+        if n_keys >= 2**31:
+            raise ValueError("too many possible groups for dense accumulator slots")
+        nk = 2 if bool(self.control) else 1
+        nf = 2 if plan["flip"] else 1
+        nctrl = self.CC.nshifts if do_control else 0
+        chrom_v, start_v, end_v = df["chrom"].values, df["start"].values, df["end"].values
+        items = []
+        for ri, name in enumerate(region_names):
+            r = self.view_df.loc[name]
+            m_ = (chrom_v == r["chrom"]) & (start_v >= r["start"]) & (end_v < r["end"])
+            sel = df[m_]
+            center = np.ascontiguousarray(sel["center"].values, dtype=np.float64)
+            q, total = _native.pair_windows_count(center, self.CC.mindist, self.CC.maxdist)
+            it = dict(index=ri, name=name, total=total, nctrl=nctrl, segs=(q[q > 0] * nctrl) if nctrl else np.zeros(0, np.int64),
+                      owned=name in my_units and total > 0)
+            if it["owned"]:
+                lo_rel, hi_rel = self.view_df_extents[name]
+                part, parts = my_units[name]
+                it.update(nb=hi_rel - lo_rel, part=part, parts=parts, center=center, per_offset=q,
+                          stbin=np.ascontiguousarray(sel["stBin"].values - lo_rel, dtype=np.int32),
+                          key1=None, key2=None, flipval=None, ident=None, band_weight=0)
+                if plan["by_window"]:
+                    mi = pd.MultiIndex.from_arrays([sel["chrom"].values, sel["start"].values, sel["end"].values])
+                    it["ident"] = np.ascontiguousarray(self._ident_index.reindex(mi).values, dtype=np.int32)
+                else:
+                    k1 = np.zeros(len(sel), dtype=np.int64)
+                    k2 = np.zeros(len(sel), dtype=np.int64)
+                    for (g, _), wt in zip(colspec, weights):
+                        if g == "distance_band" and plan["band_edges"] is not None:
+                            it["band_weight"] = wt
+                            continue
+                        codes = table.codes(g, sel[g[:-1]].to_numpy())
+                        if g[-1] == "1":
+                            k1 += codes * wt
+                        else:
+                            k2 += codes * wt
+                    it["key1"], it["key2"] = k1, k2
+                if plan["flip"]:
+                    if self.flip_negative_strand:
+                        it["flipval"] = np.ascontiguousarray(sel["strand"].values == "-", dtype=np.int32)
+                    else:
+                        fb = plan["flipby"]
+                        table.is_dynamic(fb + "1")
+                        it["flipval"] = np.ascontiguousarray(table.codes(fb + "1", sel[fb].to_numpy()), dtype=np.int32)
+            items.append(it)
+        flags = 0
+        if self.expected is True and self.ooe:
+            flags |= _native.PUP_F_OOE
+        if expctrl:
+            flags |= _native.PUP_F_EXPCTRL
+        if self.coverage_norm:
+            flags |= _native.PUP_F_COVERAGE
+        return dict(plan=plan, W=W, built=[], items=items, colspec=colspec, table=table, first={}, nk=nk, nf=nf,
+                    n_keys=n_keys, n_slots=n_keys * nk * nf, flags=flags, do_control=bool(self.control), expctrl=expctrl,
+                    region_names=region_names, imbalance=imbalance)
+
+    def _execute_device(self, job, acc, region_acc, exact, dist):
+        """Device-window path: per region, control shifts (MT19937 replay) on a side stream, window generation on the
+        prepare stream, pile-up on the compute stream.  Nothing here waits for the GPU."""
+        import torch
+
+        W, n_slots, flags, plan = job["W"], job["n_slots"], job["flags"], job["plan"]
+        dev = torch.device("cuda", self._device)
+        pipe = _native.make_pipeline(self._device, W, n_slots, flags)
+        s_rng = torch.cuda.Stream(dev)
+        s_rng.wait_stream(torch.cuda.current_stream(dev))
+        need_rng = any(len(it["segs"]) for it in job["items"])
+        rng = _native.DeviceRng(self._device, stream=s_rng.cuda_stream) if need_rng else None
+        first = torch.full((job["n_keys"],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
+        n_roi = torch.zeros(max(1, len(job["items"])), dtype=torch.int64, device=dev)
+        pipe.s_prep.wait_stream(torch.cuda.current_stream(dev))
+        edges = plan["band_edges"]
+        edges = None if edges is None else np.ascontiguousarray(edges, dtype=np.float64)
+        stride = _native.acc_stride(W)
+        try:
+            for it in job["items"]:
+                dbin, shifts_ready = None, None
+                if rng is not None and len(it["segs"]):
+                    with torch.cuda.stream(s_rng):
+                        if it["owned"]:
+                            dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)
+                            dbin.record_stream(pipe.s_prep)
+                        rng.control_shifts(it["segs"], self.CC.minshift, self.CC.maxshift, self.resolution, dbin,
+                                           stream=s_rng.cuda_stream)
+                        shifts_ready = s_rng.record_event()
+                if not it["owned"]:
+                    continue
+                targets = 2 if it["ident"] is not None else 1
+                n_all = int(it["total"]) * (1 + it["nctrl"])
+                n_mine = (n_all - it["part"] + it["parts"] - 1) // it["parts"]
+
+                def generate(stream, it=it, dbin=dbin, shifts_ready=shifts_ready, n_mine=n_mine, targets=targets):
+                    if shifts_ready is not None:
+                        stream.wait_event(shifts_ready)
+                    outs = tuple(torch.empty(n_mine * targets, dtype=torch.int32, device=dev) for _ in range(3))
+                    _native.pair_windows_device(
+                        self._device, it["stbin"], it["center"], self.CC.mindist, self.CC.maxdist, it["nctrl"],
+                        it["per_offset"], dbin, it["nb"], W, it["key1"], it["key2"], edges, it["band_weight"],
+                        0 if it["flipval"] is None else (1 if self.flip_negative_strand else 2),
+                        bool(plan["flip"] and plan["ignore_group_order"]), it["flipval"], it["ident"], job["nk"], job["nf"],
+                        it["part"], it["parts"], it["index"], outs[0], outs[1], outs[2], first_seen=first,
+                        n_roi=n_roi[it["index"] : it["index"] + 1], stream=stream.cuda_stream)
+                    return outs
+
+                target = acc
+                if exact:
+                    target = region_acc[it["name"]] = _native.alloc_accumulator(n_slots * stride, self._device)
+                pipe.submit(self._region_kwargs(it["name"], flags), None, target, windows_on_device=generate)
+            pipe.finish()
+            s_rng.synchronize()
+            if rng is not None:
+                rng.store(stream=s_rng.cuda_stream)  # np.random continues where the reference's stream would be
+        finally:
+            if rng is not None:
+                rng.close()
+        if dist is not None and dist.world_size > 1:
+            dist.all_reduce_min(first)
+            dist.all_reduce(n_roi)
+        fv = first.cpu().numpy()
+        job["first"] = {int(k): (int(fv[k] >> 62), int((fv[k] >> 40) & 0xFFFFF), int(fv[k] & ((1 << 40) - 1)))
+                        for k in np.nonzero(fv != np.iinfo(np.int64).max)[0]}
+        counts = n_roi.cpu().numpy()
+        for it in job["items"]:
+            if counts[it["index"]] > 0:
+                logger.info(f"{(it['name'], it['name'])}: {int(counts[it['index']])}")
+        return pipe
+
+    def _execute_host(self, job, acc, region_acc, exact):
+        """Host-window path: the window arrays of :meth:`_prepare` are uploaded region by region."""
         W, n_slots, flags = job["W"], job["n_slots"], job["flags"]
         stride = _native.acc_stride(W)
-        exact = self._needs_exact_merge()
-        acc = _native.alloc_accumulator(n_slots * stride, self._device)
         pipe = _native.make_pipeline(self._device, W, n_slots, flags)
-        region_acc = {}
         for b in job["built"]:
             target = acc
             if exact:  # per-region accumulators: the reference's merge is not a plain sum when +inf occurs
@@ -824,6 +1004,32 @@ class PileUpper:
             if n_roi > 0:
                 logger.info(f"{(b['name'], b['name'])}: {n_roi}")
         pipe.finish()
+        return pipe
+
+    def _run(self, groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func, regions=None,
+             dist=None):
+        """Accumulate all (or the given) view regions on the GPU; returns the merged ROI / control pile-ups."""
+        import time
+
+        _native.require_device()
+        t0 = time.perf_counter()
+        plan = self._plan(groupby, ignore_group_order, modify_2Dintervals_func, postprocess_func)
+        plan["band_edges"] = self._band_edges(plan)
+        on_device = self._device_windows_ok(plan)
+        if on_device:
+            job = self._prepare_device(plan, regions, dist)
+        else:
+            job = self._prepare(plan, regions, dist)
+        t1 = time.perf_counter()
+        W, n_slots = job["W"], job["n_slots"]
+        stride = _native.acc_stride(W)
+        exact = self._needs_exact_merge()
+        acc = _native.alloc_accumulator(n_slots * stride, self._device)
+        region_acc = {}
+        if on_device:
+            pipe = self._execute_device(job, acc, region_acc, exact, dist)
+        else:
+            pipe = self._execute_host(job, acc, region_acc, exact)
         if exact:
             for a in region_acc.values():
                 acc += a
@@ -831,9 +1037,10 @@ class PileUpper:
             dist.all_reduce(acc)
         stream = _native.current_stream(self._device)
         out, used = self._export_used(acc, job, stream)
+        t2 = time.perf_counter()
         self._last_stats = {"windows": int(out["n"].sum()), "launches": pipe.launches, "regions": pipe.regions,
-                            "imbalance": job["imbalance"], "n_slots": n_slots, "used_slots": int(len(used))}
-        plan = job["plan"]
+                            "imbalance": job["imbalance"], "n_slots": n_slots, "used_slots": int(len(used)),
+                            "device_windows": bool(on_device), "host_prepare_s": t1 - t0, "gpu_phase_s": t2 - t1}
         grouped = bool(plan["groupby"]) or plan["by_window"]
         roi, ctrl = self._slots_to_pups(out, used, job, grouped)
         if exact:

@@ -1253,6 +1253,260 @@ __global__ void k_n_valid(const int32_t* __restrict__ badpre, const unsigned lon
   n_valid[d] = v;
 }
 
+// ------------------------------------------------------------------------------------------ control shifts (MT19937)
+// The reference draws its random control shifts from numpy's global legacy RandomState (coolpup.py:392-396,
+// 442-445): per block of n windows `np.random.randint(minshift, maxshift, n)` then `np.random.choice([-1, 1], n)`.
+// numpy implements both on the MT19937 32-bit stream (numpy/random/src/mt19937/mt19937.c,
+// distributions.c:random_bounded_uint64_fill -> buffered_bounded_masked_uint32): a randint is
+// `low + v` for the first `v = next32() & mask` with `v <= rng` (mask = smallest 2^k - 1 >= rng = high - 1 - low);
+// a choice is `next32() & 1`.  k_mt_shifts replays exactly that stream on the device, one CTA, so that a seeded run
+// sees the same control windows as the reference without a host-side draw or a 1e7-row upload.
+// Restated (and pinned against numpy) in oracle/mt19937_ref.py.
+constexpr int MT_N = 624, MT_M = 397;
+constexpr int MT_THREADS = 640;  // >= MT_N, a multiple of 32
+
+struct pup_rng_state {
+  uint32_t key[MT_N];
+  int32_t pos;  // next word of key[] to use; MT_N = regenerate first
+};
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b, uint32_t c) {
+  const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+// block-wide inclusive scan of one int per thread (MT_THREADS threads); returns the inclusive prefix, *total = sum
+__device__ __forceinline__ int mt_block_scan(int v, int* warp_sums, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < MT_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    if (lane < MT_THREADS / 32) warp_sums[lane] = w;
+  }
+  __syncthreads();
+  const int before = warp > 0 ? warp_sums[warp - 1] : 0;
+  *total = warp_sums[MT_THREADS / 32 - 1];
+  __syncthreads();  // warp_sums is reused by the next call
+  return x + before;
+}
+
+// seg_n[s] randint draws followed by seg_n[s] sign draws per segment s; dbin[draw] = rint(shift * sign / resolution)
+// in draw order (segment after segment); dbin == nullptr only advances the generator.
+__global__ void __launch_bounds__(MT_THREADS) k_mt_shifts(pup_rng_state* st, const int64_t* __restrict__ seg_n,
+                                                          int64_t n_seg, int64_t low, uint32_t rng, uint32_t mask,
+                                                          double resolution, int32_t* __restrict__ dbin) {
+  __shared__ uint32_t key[MT_N];
+  __shared__ uint32_t out[MT_N];  // tempered words of the current block
+  __shared__ int warp_sums[MT_THREADS / 32];
+  __shared__ int s_cut;
+  const int t = threadIdx.x;
+  if (t < MT_N) key[t] = st->key[t];
+  int pos = st->pos;
+  __syncthreads();
+  auto temper_all = [&]() {
+    if (t < MT_N) {
+      uint32_t y = key[t];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      out[t] = y;
+    }
+    __syncthreads();
+  };
+  auto regenerate = [&]() {
+    // key[i] = key[i + M] ^ twist(key[i], key[i + 1]): entries [0, N - M) read old values only, the next N - M read
+    // entries the first phase wrote, and so on -- three dependent phases (+ the last word, which reads new key[0])
+    uint32_t v = 0;
+    if (t < MT_N - MT_M) v = mt_twist(key[t], key[t + 1], key[t + MT_M]);
+    __syncthreads();
+    if (t < MT_N - MT_M) key[t] = v;
+    __syncthreads();
+    if (t >= MT_N - MT_M && t < 2 * (MT_N - MT_M)) v = mt_twist(key[t], key[t + 1], key[t - (MT_N - MT_M)]);
+    __syncthreads();
+    if (t >= MT_N - MT_M && t < 2 * (MT_N - MT_M)) key[t] = v;
+    __syncthreads();
+    if (t >= 2 * (MT_N - MT_M) && t < MT_N - 1) v = mt_twist(key[t], key[t + 1], key[t - (MT_N - MT_M)]);
+    __syncthreads();
+    if (t >= 2 * (MT_N - MT_M) && t < MT_N - 1) key[t] = v;
+    __syncthreads();
+    if (t == MT_N - 1) key[t] = mt_twist(key[t], key[0], key[MT_M - 1]);
+    __syncthreads();
+    temper_all();
+  };
+  temper_all();  // (only meaningful for pos < MT_N)
+  int64_t outbase = 0;
+  for (int64_t seg = 0; seg < n_seg; ++seg) {
+    const int64_t n = seg_n[seg];
+    // ---- n accepted bounded integers
+    int64_t got = 0;
+    while (got < n) {
+      if (pos >= MT_N) {
+        regenerate();
+        pos = 0;
+      }
+      const bool mine = t >= pos && t < MT_N;
+      const uint32_t v = mine ? (out[t] & mask) : 0u;
+      const int acc = (mine && v <= rng) ? 1 : 0;
+      int total;
+      const int incl = mt_block_scan(acc, warp_sums, &total);
+      const int64_t need = n - got;
+      if ((int64_t)total <= need) {
+        if (acc && dbin) dbin[outbase + got + incl - 1] = (int32_t)(low + (int64_t)v);
+        got += total;
+        pos = MT_N;
+      } else {  // the need-th accepted word ends this phase inside the block
+        if (acc && (int64_t)incl <= need && dbin) dbin[outbase + got + incl - 1] = (int32_t)(low + (int64_t)v);
+        if (acc && (int64_t)incl == need) s_cut = t;
+        __syncthreads();
+        pos = s_cut + 1;
+        got = n;
+        __syncthreads();
+      }
+    }
+    // ---- n signs
+    int64_t done = 0;
+    while (done < n) {
+      if (pos >= MT_N) {
+        regenerate();
+        pos = 0;
+      }
+      const int take = (int)min((int64_t)(MT_N - pos), n - done);
+      if (t >= pos && t < pos + take && dbin) {
+        const int64_t i = outbase + done + (t - pos);
+        const int64_t sh = (int64_t)dbin[i] * ((out[t] & 1u) ? 1 : -1);
+        dbin[i] = (int32_t)__double2ll_rn((double)sh / resolution);  // np.round: half to even
+      }
+      pos += take;
+      done += take;
+    }
+    outbase += n;
+    __syncthreads();
+  }
+  if (t < MT_N) st->key[t] = key[t];
+  if (t == 0) st->pos = pos;
+}
+
+// ------------------------------------------------------------------------------------------ pair windows on device
+// All-vs-all windows of one view region's bed features, in the reference's emission order (CoordCreator.
+// get_combinations, coolpup.py:682-714: pairs (k, k + i) by offset i then k, distance-filtered; per offset block the
+// ROI rows, then the nctrl shifted replicas, _control_regions 387-453) together with their accumulator slots.
+struct PairGen {
+  int m, nctrl, W, nb, nk, nf, targets, part, parts, region_index;
+  const int32_t* stbin;       // [m] region-relative first bin of every feature's window
+  const double* center;       // [m]
+  double mindist, maxdist;
+  const int64_t* base;        // [m] kept pairs of all smaller offsets (exclusive prefix of per_offset)
+  const int64_t* per_offset;  // [m]
+  const int32_t* dbin;        // control shifts in draw order (k_mt_shifts) or null
+  const int64_t* key1;        // [m] group-key part of a feature on side 1 / side 2 (null: 0)
+  const int64_t* key2;
+  const double* edges;        // distance-band edges (null: no band column)
+  int n_edges;
+  long long band_weight;
+  int flip_mode;              // 0 none, 1: flipval[k] != 0, 2: flipval[k] > flipval[l]
+  int swap_on_flip;           // ignore_group_order: a flipped window swaps the sides of its group key
+  const int32_t* flipval;
+  const int32_t* ident;       // by-window: feature identity (the window goes to both anchors' groups)
+  int32_t *r0, *c0, *slot;    // outputs, [ceil((n - part) / parts) * targets]
+  unsigned long long* first;  // [n_keys] atomicMin of (control?, region, emission position) over valid windows; null: off
+  unsigned long long* n_roi;  // [1] valid ROI windows (x targets) of this call; null: off
+};
+
+__global__ void __launch_bounds__(256) k_pair_windows(const PairGen p) {
+  __shared__ int warp_sums[8];
+  __shared__ int s_base;
+  const int i = blockIdx.x + 1;  // pair offset
+  if (i >= p.m) return;
+  const long long q = p.per_offset[i];
+  if (q == 0) return;
+  const long long blk = p.base[i] * (1 + p.nctrl);  // emission index of the block's first row
+  const long long dr0 = p.base[i] * p.nctrl;        // first draw of the block
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int k0 = 0; k0 + i < p.m; k0 += blockDim.x) {
+    const int k = k0 + threadIdx.x, l = k + i;
+    bool keep = false;
+    double dist = 0.0;
+    if (l < p.m) {
+      dist = p.center[l] - p.center[k];
+      const double ad = fabs(dist);
+      keep = p.mindist <= ad && ad <= p.maxdist;
+    }
+    // rank of this pair among the kept pairs of the offset
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    int x = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += warp_sums[w];
+    const long long j = before + x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += warp_sums[w];
+      s_base += tot;
+    }
+    __syncthreads();
+    if (!keep) continue;
+    // group key and flip flag are properties of the pair; the controls inherit them (coolpup.py:436-450)
+    bool flip = false;
+    if (p.flip_mode == 1) flip = p.flipval[k] != 0;
+    if (p.flip_mode == 2) flip = p.flipval[k] > p.flipval[l];
+    long long key = 0;
+    if (p.ident == nullptr) {
+      const bool sw = flip && p.swap_on_flip;
+      if (p.key1) key += sw ? p.key1[l] : p.key1[k];
+      if (p.key2) key += sw ? p.key2[k] : p.key2[l];
+      if (p.edges) {  // np.searchsorted(edges, distance, side="right")
+        int lo = 0, hi = p.n_edges;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (p.edges[mid] <= dist)
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        key += (long long)lo * p.band_weight;
+      }
+    }
+    for (int rep = 0; rep <= p.nctrl; ++rep) {
+      const long long pos = blk + (long long)rep * q + j;
+      if (pos % p.parts != p.part) continue;  // another rank's strided share
+      const int sh = rep == 0 ? 0 : p.dbin[dr0 + (long long)(rep - 1) * q + j];
+      const int a = p.stbin[k] + sh, b = p.stbin[l] + sh;
+      const bool valid = a >= 0 && b >= 0 && a + p.W <= p.nb && b + p.W <= p.nb;
+      const int kind = rep == 0 ? 0 : 1;
+      const long long o = (pos / p.parts) * p.targets;
+      for (int tg = 0; tg < p.targets; ++tg) {
+        const long long kk = p.ident ? (long long)(tg == 0 ? p.ident[k] : p.ident[l]) : key;
+        p.r0[o + tg] = a;
+        p.c0[o + tg] = b;
+        p.slot[o + tg] = (int32_t)((kk * p.nk + kind) * p.nf + (flip ? 1 : 0));
+        if (valid && p.first) {
+          const unsigned long long cand = ((unsigned long long)kind << 62) | ((unsigned long long)p.region_index << 40) |
+                                          (unsigned long long)(pos * p.targets + tg);
+          atomicMin(p.first + kk, cand);
+        }
+      }
+      if (valid && kind == 0 && p.n_roi) atomicAdd(p.n_roi, (unsigned long long)p.targets);
+    }
+  }
+}
+
 // occ != nullptr: only query the occupancy; else launch
 template <int R, int S, int PF, int MINB, bool QI>
 cudaError_t launch_main_t(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
@@ -1304,7 +1558,7 @@ void choose_strip(int* R_out, int* S_out) {
 // =========================================================================================== C ABI
 extern "C" {
 
-int pup_abi_version(void) { return 2; }
+int pup_abi_version(void) { return 3; }
 
 const char* pup_last_error(void) { return g_err.c_str(); }
 
@@ -2189,6 +2443,176 @@ int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center,
     }
     drawn += n * nctrl;
   }
+  return PUP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ device-side windows
+struct pup_rng {
+  int device;
+  pup_rng_state* st;
+};
+
+int pup_rng_create(int device, const uint32_t* key, int pos, void* stream, pup_rng_t** out) {
+  if (!out || !key || pos < 0 || pos > MT_N) return fail(PUP_E_ARG, "pup_rng_create: bad arguments");
+  *out = nullptr;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_rng_create: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  pup_rng_state h;
+  memcpy(h.key, key, sizeof h.key);
+  h.pos = pos;
+  pup_rng* r = new pup_rng();
+  r->device = device;
+  cudaError_t e = cudaMalloc((void**)&r->st, sizeof(pup_rng_state));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r->st, &h, sizeof h, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `h` lives on this stack frame
+  if (e != cudaSuccess) {
+    if (r->st) cudaFree(r->st);
+    delete r;
+    return fail(PUP_E_CUDA, "pup_rng_create", e);
+  }
+  *out = r;
+  return PUP_OK;
+}
+
+int pup_rng_read(pup_rng_t* r, uint32_t* key, int* pos, void* stream) {
+  if (!r || !key || !pos) return fail(PUP_E_ARG, "pup_rng_read: bad arguments");
+  DeviceGuard guard(r->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_rng_read: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  pup_rng_state h;
+  CK(cudaMemcpyAsync(&h, r->st, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(key, h.key, sizeof h.key);
+  *pos = h.pos;
+  return PUP_OK;
+}
+
+int pup_rng_destroy(pup_rng_t* r) {
+  if (!r) return PUP_OK;
+  DeviceGuard guard(r->device);
+  if (r->st) cudaFree(r->st);
+  delete r;
+  return PUP_OK;
+}
+
+int pup_control_shifts(pup_rng_t* r, int64_t n_segments, const int64_t* seg_n, int64_t minshift, int64_t maxshift,
+                       double resolution, int32_t* dbin, void* stream) {
+  if (!r || n_segments < 0 || (n_segments > 0 && !seg_n)) return fail(PUP_E_ARG, "pup_control_shifts: bad arguments");
+  const int64_t range = maxshift - 1 - minshift;
+  if (range <= 0 || range >= 0xffffffffll || minshift <= -(1ll << 31) || maxshift >= (1ll << 31) || !(resolution > 0))
+    return fail(PUP_E_ARG, "pup_control_shifts: need minshift + 1 < maxshift, both inside int32, and a positive resolution");
+  if (dbin && !is_device_ptr(dbin)) return fail(PUP_E_ARG, "pup_control_shifts: dbin must be device memory");
+  if (n_segments == 0) return PUP_OK;
+  for (int64_t s = 0; s < n_segments; ++s)
+    if (seg_n[s] <= 0) return fail(PUP_E_ARG, "pup_control_shifts: segment sizes must be positive");
+  DeviceGuard guard(r->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_control_shifts: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch tmp(st);
+  int64_t* d_seg;
+  CK(tmp.alloc((void**)&d_seg, (size_t)n_segments * 8));
+  // pageable source: the runtime stages it before returning, so seg_n may be freed by the caller right away
+  CK(cudaMemcpyAsync(d_seg, seg_n, (size_t)n_segments * 8, cudaMemcpyHostToDevice, st));
+  uint32_t mask = (uint32_t)range;
+  mask |= mask >> 1;
+  mask |= mask >> 2;
+  mask |= mask >> 4;
+  mask |= mask >> 8;
+  mask |= mask >> 16;
+  k_mt_shifts<<<1, MT_THREADS, 0, st>>>(r->st, d_seg, n_segments, minshift, (uint32_t)range, mask, resolution, dbin);
+  LAUNCH_CHECK("k_mt_shifts");
+  return PUP_OK;
+}
+
+int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const double* center, double mindist,
+                            double maxdist, int32_t nctrl, const int64_t* per_offset, const int32_t* dbin, int32_t nb,
+                            int W, const int64_t* key1, const int64_t* key2, const double* band_edges, int32_t n_edges,
+                            int64_t band_weight, int flip_mode, int swap_on_flip, const int32_t* flipval,
+                            const int32_t* ident, int nk, int nf, int32_t part, int32_t parts, int32_t region_index,
+                            int32_t* r0, int32_t* c0, int32_t* slot, uint64_t* first_seen, uint64_t* n_roi,
+                            void* stream) {
+  if (m < 0 || nctrl < 0 || W <= 0 || nb <= 0 || nk <= 0 || nf <= 0 || parts <= 0 || part < 0 || part >= parts ||
+      region_index < 0 || region_index >= (1 << 20))
+    return fail(PUP_E_ARG, "pup_pair_windows_device: bad sizes");
+  if (m < 2) return PUP_OK;
+  if (!stbin || !center || !per_offset || !r0 || !c0 || !slot)
+    return fail(PUP_E_ARG, "pup_pair_windows_device: null arrays");
+  if (flip_mode < 0 || flip_mode > 2 || (flip_mode != 0 && !flipval) || (band_edges && n_edges <= 0))
+    return fail(PUP_E_ARG, "pup_pair_windows_device: bad flip / band arguments");
+  if (!is_device_ptr(r0) || !is_device_ptr(c0) || !is_device_ptr(slot) || (dbin && !is_device_ptr(dbin)) ||
+      (first_seen && !is_device_ptr(first_seen)) || (n_roi && !is_device_ptr(n_roi)))
+    return fail(PUP_E_ARG, "pup_pair_windows_device: outputs and dbin must be device memory");
+  int64_t total = 0;
+  std::vector<int64_t> base((size_t)m);
+  for (int32_t i = 0; i < m; ++i) {
+    base[(size_t)i] = total;
+    total += per_offset[i];
+  }
+  if (total == 0) return PUP_OK;
+  if (nctrl > 0 && !dbin) return fail(PUP_E_ARG, "pup_pair_windows_device: control shifts missing");
+  if (total * (1 + (int64_t)nctrl) >= (1ll << 40)) return fail(PUP_E_ARG, "pup_pair_windows_device: too many windows");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_pair_windows_device: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch tmp(st);
+  // small per-feature inputs: staged on the caller's stream (pageable sources are consumed before the call returns)
+  auto stage = [&](const void* src, size_t bytes, const void** dst) -> int {
+    *dst = src;
+    if (!src || bytes == 0 || is_device_ptr(src)) return PUP_OK;
+    void* t;
+    CK(tmp.alloc(&t, bytes));
+    CK(cudaMemcpyAsync(t, src, bytes, cudaMemcpyHostToDevice, st));
+    *dst = t;
+    return PUP_OK;
+  };
+  const void *d_st, *d_ce, *d_po, *d_base, *d_k1, *d_k2, *d_ed, *d_fv, *d_id;
+  int rc;
+  if ((rc = stage(stbin, (size_t)m * 4, &d_st)) != PUP_OK) return rc;
+  if ((rc = stage(center, (size_t)m * 8, &d_ce)) != PUP_OK) return rc;
+  if ((rc = stage(per_offset, (size_t)m * 8, &d_po)) != PUP_OK) return rc;
+  if ((rc = stage(base.data(), (size_t)m * 8, &d_base)) != PUP_OK) return rc;
+  if ((rc = stage(key1, (size_t)m * 8, &d_k1)) != PUP_OK) return rc;
+  if ((rc = stage(key2, (size_t)m * 8, &d_k2)) != PUP_OK) return rc;
+  if ((rc = stage(band_edges, (size_t)n_edges * 8, &d_ed)) != PUP_OK) return rc;
+  if ((rc = stage(flipval, (size_t)m * 4, &d_fv)) != PUP_OK) return rc;
+  if ((rc = stage(ident, (size_t)m * 4, &d_id)) != PUP_OK) return rc;
+  PairGen g;
+  g.m = m;
+  g.nctrl = nctrl;
+  g.W = W;
+  g.nb = nb;
+  g.nk = nk;
+  g.nf = nf;
+  g.targets = ident ? 2 : 1;
+  g.part = part;
+  g.parts = parts;
+  g.region_index = region_index;
+  g.stbin = (const int32_t*)d_st;
+  g.center = (const double*)d_ce;
+  g.mindist = mindist;
+  g.maxdist = maxdist;
+  g.base = (const int64_t*)d_base;
+  g.per_offset = (const int64_t*)d_po;
+  g.dbin = dbin;
+  g.key1 = (const int64_t*)d_k1;
+  g.key2 = (const int64_t*)d_k2;
+  g.edges = (const double*)d_ed;
+  g.n_edges = band_edges ? n_edges : 0;
+  g.band_weight = band_weight;
+  g.flip_mode = flip_mode;
+  g.swap_on_flip = swap_on_flip;
+  g.flipval = (const int32_t*)d_fv;
+  g.ident = (const int32_t*)d_id;
+  g.r0 = r0;
+  g.c0 = c0;
+  g.slot = slot;
+  g.first = (unsigned long long*)first_seen;
+  g.n_roi = (unsigned long long*)n_roi;
+  k_pair_windows<<<m - 1, 256, 0, st>>>(g);
+  LAUNCH_CHECK("k_pair_windows");
+  // no synchronisation: the pageable host sources (incl. `base` on this frame) have been copied to the driver's
+  // staging memory when cudaMemcpyAsync returns
   return PUP_OK;
 }
 

@@ -93,6 +93,11 @@ class RegionSharder:
             self._dist.all_reduce(tensor, op=self._dist.ReduceOp.SUM, group=self.group)
         return tensor
 
+    def all_reduce_min(self, tensor):
+        if self.world_size > 1:
+            self._dist.all_reduce(tensor, op=self._dist.ReduceOp.MIN, group=self.group)
+        return tensor
+
     def merge_min(self, mapping):
         """Union of per-rank ``{key: sortable}`` dictionaries keeping the minimum value per key."""
         if self.world_size == 1:

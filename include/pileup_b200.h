@@ -194,6 +194,57 @@ int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center,
                           int32_t nctrl, const int64_t* dbin, int64_t* st1, int64_t* st2, int8_t* kind, int64_t* idx1,
                           int64_t* idx2, double* distance);
 
+/*
+ * Device-side window generation for bed features paired all-vs-all (no host loop, no window upload).
+ *
+ * pup_rng_t: numpy's legacy MT19937 state (np.random.get_state(): 624 key words + position) held on the device.  The
+ * reference draws its control shifts from the GLOBAL np.random stream (coolpup.py:392-396, 442-445); a seeded run is
+ * reproduced by loading that state, replaying the draws on the device and writing the final state back
+ * (pup_rng_read -> np.random.set_state), so that host code after the pile-up continues the stream exactly where the
+ * reference would.
+ *
+ * pup_control_shifts: for every segment s (one `_control_regions` call of the reference: a bedpe / local region, or
+ * one pair offset of a bed region) seg_n[s] draws of `np.random.randint(minshift, maxshift, n)` followed by seg_n[s]
+ * draws of `np.random.choice([-1, 1], n)`; dbin[draw] = np.round(shift * sign / resolution) (int32, device memory,
+ * draws of all segments one after the other).  dbin == NULL only advances the generator (regions of other ranks).
+ * seg_n is host memory; the call only enqueues work on `stream`.
+ *
+ * pup_pair_windows_device: the windows of CoordCreator.get_combinations (coolpup.py:682-714) + _control_regions
+ * (387-453) for the m features of one view region (sorted like the reference sorts them), written in the
+ * reference's emission order: pairs (k, k + i) by offset i then k, kept when mindist <= |center[k+i] - center[k]|
+ * <= maxdist; per offset block the ROI rows, then nctrl replicas shifted by dbin (block order, replica-major:
+ * draw = nctrl * base[i] + (rep - 1) * per_offset[i] + j).  Window `pos` (emission index) is written at
+ * (pos / parts) * targets when pos % parts == part (strided sharding of a region's windows over ranks).
+ *   stbin[m]        region-relative first bin of every feature's window; center[m] in bp; per_offset[m] from
+ *                   pup_pair_windows_count (host memory; the others host or device)
+ *   slot            = ((key * nk + kind) * nf + flip); key = key1[k] + key2[l] (swapped to key1[l] + key2[k] for a
+ *                   flipped window when swap_on_flip: ignore_group_order, coolpup.py:131-144) + band_weight *
+ *                   searchsorted(band_edges, center[l] - center[k], side="right") (bin_distance_intervals, 28-51);
+ *                   NULL key arrays / band_edges contribute 0
+ *   flip            flip_mode 0: never; 1: flipval[k] != 0 (flip_negative_strand: strand1 == "-"); 2: flipval[k] >
+ *                   flipval[l] (flip_mark_intervals_func, 118-125)
+ *   ident[m]        by-window (group_by_region, lib/puputils.py:218-223): every window is written twice, with keys
+ *                   ident[k] and ident[l]; NULL otherwise
+ *   first_seen      [n_keys] uint64, device, caller-initialised to all ones: atomicMin of
+ *                   (kind << 62 | region_index << 40 | pos * targets + target) over the in-region windows of a key --
+ *                   the order in which the reference's dictionaries first see a group; NULL: not recorded
+ *   n_roi           [1] uint64, device: += number of in-region ROI windows (x targets); NULL: not counted
+ * r0 / c0 / slot are device memory.  The call only enqueues work on `stream`; host arrays may be released on return.
+ */
+typedef struct pup_rng pup_rng_t;
+int pup_rng_create(int device, const uint32_t* key624, int pos, void* stream, pup_rng_t** out);
+int pup_rng_read(pup_rng_t* rng, uint32_t* key624, int* pos, void* stream);
+int pup_rng_destroy(pup_rng_t* rng);
+int pup_control_shifts(pup_rng_t* rng, int64_t n_segments, const int64_t* seg_n, int64_t minshift, int64_t maxshift,
+                       double resolution, int32_t* dbin, void* stream);
+int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const double* center, double mindist,
+                            double maxdist, int32_t nctrl, const int64_t* per_offset, const int32_t* dbin, int32_t nb,
+                            int W, const int64_t* key1, const int64_t* key2, const double* band_edges, int32_t n_edges,
+                            int64_t band_weight, int flip_mode, int swap_on_flip, const int32_t* flipval,
+                            const int32_t* ident, int nk, int nf, int32_t part, int32_t parts, int32_t region_index,
+                            int32_t* r0, int32_t* c0, int32_t* slot, uint64_t* first_seen, uint64_t* n_roi,
+                            void* stream);
+
 /* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
  * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */
 int pup_last_launches(void);

@@ -235,6 +235,7 @@ def install(monkeypatch):
     monkeypatch.setattr(_native, "current_stream", lambda device: 0)
     monkeypatch.setattr(_native, "acc_stride", lambda W: layout(int(W))["stride"])
     monkeypatch.setattr(_native, "make_pipeline", SerialPipeline)
+    monkeypatch.setattr(_native, "device_windows_supported", lambda: False)
 
     real = _native.lib()  # host-side entry points (window layout) are the real library: they need no device
 
