@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the pile-up hot path on B200 (contract: see the task brief, section 4).
 
-Workload (BASELINE.json configs[3], the configuration the metric is quoted on; it fits one GPU): synthetic 3 Gbp
-genome at 10 kb bins (hg38 chromosome lengths, counts ~ Poisson(depth / separation)), all-vs-all cis pairs of
-CTCF-like sites chosen so that ~1e6 pairs pass mindist="auto", pad = 41 bins (W = 83), nshifts = 10 random-shift
-controls (~1.1e7 windows per step), balanced with 3 % NaN bins, no expected.
+Workloads (synthetic 3 Gbp genome at 10 kb bins, hg38 chromosome lengths, counts ~ Poisson(depth / separation),
+balanced with 3 % NaN bins):
+  configs3 (default; BASELINE.json configs[3], the configuration the metric is quoted on; it fits one GPU):
+           all-vs-all cis pairs of CTCF-like sites chosen so that ~1e6 pairs pass mindist="auto", pad = 41 bins
+           (W = 83), nshifts = 10 random-shift controls (~1.1e7 windows per step), no expected.
+  configs2 (BASELINE.json configs[2]): 1e5 bedpe loops, pad = 41, observed / expected.
+  configs4 (BASELINE.json configs[4]): ~5e5 stranded cis pairs, by-strand x by-distance groups, pad = 101 (W = 203),
+           observed / expected, one accumulator slot per (strand1, strand2, distance band).
 
 A step = one pass of the hot path over every window of every chromosome:
-  value : region matrices and window arrays resident in HBM; per chromosome pup_accumulate() = device sort of the
-          windows + vector kernel + main pile-up kernel; N > 1: chromosomes sharded over ranks (LPT), one NCCL
-          all-reduce of the accumulators inside the timed region.
-  e2e   : the same pass through pup_region_create_upper() + pup_upload() + pup_accumulate() with HOST (pinned)
-          upper-triangle CSR / weight / window buffers, i.e. including the H2D upload + device-side indexing of every
-          chromosome and the D2H read of the accumulators.
-  cpu_baseline / --impl reference : the restated reference path (oracle/pileup_oracle.py: scipy-CSR slice per
-          window, NaN masks, nansum) on the host cores, on a bounded uniform sample of the same windows.
+  value   : region matrices and window arrays resident in HBM; per sharding unit pup_accumulate() = device sort of the
+            windows + count kernels + main pile-up kernel; N > 1: chromosomes sharded over ranks by LPT on their exact
+            algorithmic bytes, heavy chromosomes cut into strided window parts (matrix replicated), one NCCL
+            all-reduce of the accumulators inside the timed region.
+  e2e     : the same pass through the product's two-stream region pipeline (coolpuppy_b200.pipeline) with HOST (pinned)
+            buffers: pup_region_create_upper() + pup_upload() + pup_accumulate() per chromosome, i.e. including the
+            H2D upload and device-side indexing of every chromosome and the D2H read of the accumulators.
+  e2e_api : wall time of the public call coolpuppy_b200.coolpup.pileup(clr, features, ...) on the same workload --
+            feature table in, DataFrame out; window generation (on the GPU), uploads, pile-up, export, normalisation.
+  cpu_baseline / --impl reference : the restated reference path (oracle restatement of _stream_snips + _add_snip:
+            scipy-CSR slice per window, NaN masks, expected divide, nansum) on the host cores, on a bounded sample of
+            the same windows drawn in proportion to every chromosome's share of the windows.
 """
 import argparse
 import json
@@ -29,10 +37,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CPU_SAMPLE_REGIONS = ("chr2", "chr9", "chr16", "chr21")
 BINSIZE = 10_000
-FLANK = 410_000
-W = 2 * (FLANK // BINSIZE) + 1
+WORKLOADS = {
+    "configs3": dict(flank=410_000, nshifts=10, pairs=1_000_000, expected=False, features="sites", sites_seed=1237,
+                     kwargs=dict(features_format="bed", nshifts=10, seed=0)),
+    "configs2": dict(flank=410_000, nshifts=0, loops=100_000, expected=True, features="loops",
+                     kwargs=dict(features_format="bedpe", nshifts=0, ooe=True)),
+    "configs4": dict(flank=1_010_000, nshifts=0, pairs=500_000, expected=True, features="sites", sites_seed=1238,
+                     kwargs=dict(features_format="bed", nshifts=0, ooe=True, by_strand=True, by_distance=True)),
+}
 
 
 def parse_args():
@@ -41,15 +54,17 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PUP_BENCH_WORKLOAD", "configs3"), choices=list(WORKLOADS))
     ap.add_argument("--depth", type=float, default=float(os.environ.get("PUP_BENCH_DEPTH", 500.0)))
-    ap.add_argument("--pairs", type=int, default=int(os.environ.get("PUP_BENCH_PAIRS", 1_000_000)))
-    ap.add_argument("--nshifts", type=int, default=10)
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("PUP_BENCH_PAIRS", 0)), help="override the pair target")
     ap.add_argument("--chroms", default=os.environ.get("PUP_BENCH_CHROMS", "all"), help="'all' or comma list (debug)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--api-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=30000, help="windows in the cpu_baseline sample (~10 s on one core)")
-    ap.add_argument("--ref-sample", type=int, default=2400, help="windows per chromosome per step, --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=57600, help="windows per step over all chromosomes, --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-api", action="store_true")
     return ap.parse_args()
 
 
@@ -62,30 +77,30 @@ def chromsizes(args):
     return {c: HG38[c] for c in args.chroms.split(",")}
 
 
-def build_windows(args, sizes):
-    """Host side of the path: features -> per-chromosome window arrays (reference order, seeded control shifts)."""
-    from coolpuppy_b200.coolpup import CoordCreator
-    from coolpuppy_b200.synthetic import synthetic_sites
+def make_features(args, sizes):
+    """Feature table of the workload (bed sites or bedpe loops) and the number of ROI pairs it yields."""
+    from coolpuppy_b200.synthetic import HG38, synthetic_loops, synthetic_sites
 
-    total = float(sum(sizes.values()))
-    from coolpuppy_b200.synthetic import HG38
-
-    target = int(round(args.pairs * (total / float(sum(HG38.values()))) ** 1))
-    sites, n_pairs = synthetic_sites(target, chromsizes=sizes, binsize=BINSIZE, flank=FLANK, seed=1237)
-    np.random.seed(0)
-    cc = CoordCreator(sites, BINSIZE, features_format="bed", flank=FLANK, nshifts=args.nshifts, mindist="auto", seed=0)
-    out = {}
-    for c, L in sizes.items():
-        rw = cc.region_windows((c, 0, L), control=args.nshifts > 0)
-        nb = -(-L // BINSIZE)
-        out[c] = dict(nb=nb, r0=rw.st1.astype(np.int32), c0=rw.st2.astype(np.int32), slot=rw.kind.astype(np.int32))
-    return out, len(sites), n_pairs
+    wl = WORKLOADS[args.workload]
+    scale = float(sum(sizes.values())) / float(sum(HG38.values()))
+    if wl["features"] == "loops":
+        loops = synthetic_loops(int(round(wl["loops"] * scale)), chromsizes=sizes, binsize=BINSIZE, flank=wl["flank"], seed=1236)
+        return loops, len(loops)
+    target = int(round((args.pairs or wl["pairs"]) * scale))
+    sites, n_pairs = synthetic_sites(target, chromsizes=sizes, binsize=BINSIZE, flank=wl["flank"], seed=wl["sites_seed"])
+    return sites, n_pairs
 
 
-def lpt(costs, n):
-    from coolpuppy_b200.multigpu import lpt_assign
-
-    return lpt_assign(costs, n)
+def workload_description(args, n_features, W):
+    wl = WORKLOADS[args.workload]
+    if args.workload == "configs3":
+        return (f"configs[3]: synthetic 3 Gbp @10 kb (hg38 lengths, Poisson(depth/sep)), all-vs-all cis pairs of {n_features} "
+                f"CTCF-like sites, pad=41 (W={W}), nshifts={wl['nshifts']}, balanced (3% NaN bins), no expected")
+    if args.workload == "configs2":
+        return (f"configs[2]: synthetic 3 Gbp @10 kb (hg38 lengths, Poisson(depth/sep)), {n_features} bedpe loops (1-10 Mb), "
+                f"pad=41 (W={W}), balanced (3% NaN bins), observed/expected")
+    return (f"configs[4]: synthetic 3 Gbp @10 kb (hg38 lengths, Poisson(depth/sep)), all-vs-all cis pairs of {n_features} "
+            f"stranded sites, by-strand x by-distance groups, pad=101 (W={W}), balanced (3% NaN bins), observed/expected")
 
 
 class ClockSampler:
@@ -143,11 +158,12 @@ def _cpu_worker_prepare(name):
     from scipy import sparse
 
     d = _CPU["regions"][name]
-    mat = sparse.csr_matrix((d["count"].astype(np.float64), d["col"], d["indptr"]), shape=(d["nb"], d["nb"]))
+    nb = d["nb"]
+    up = sparse.csr_matrix((d["upper_count"].astype(np.float64), d["upper_col"], d["upper_indptr"]), shape=(nb, nb))
+    mat = (up + sparse.triu(up, 1).T).tocoo()  # cooler's fetch mirrors the stored upper triangle
     w = d["weight"]
-    coo = mat.tocoo()
-    coo.data = w[coo.row] * w[coo.col] * coo.data
-    d["mat"] = coo.tocsr()
+    mat.data = w[mat.row] * w[mat.col] * mat.data
+    d["mat"] = mat.tocsr()
     d["isnan"] = np.isnan(w)
     return name
 
@@ -157,48 +173,59 @@ def _cpu_worker_step(name):
     d = _CPU["regions"][name]
     if "mat" not in d:
         _cpu_worker_prepare(name)
-    mat, isnan, nb = d["mat"], d["isnan"], d["nb"]
+    mat, isnan, nb, W = d["mat"], d["isnan"], d["nb"], _CPU["W"]
+    E = d.get("expected")
     acc = {}
     n = 0
     ii0 = np.arange(W)[:, None]
     jj0 = np.arange(W)[None, :]
-    for s1, s2, k in zip(d["r0"], d["c0"], d["slot"]):
-        if s1 < 0 or s1 + W > nb or s2 < 0 or s2 + W > nb:
-            continue
-        data = mat[s1 : s1 + W, s2 : s2 + W].toarray().astype(float)
-        data[isnan[s1 : s1 + W], :] = np.nan
-        data[:, isnan[s2 : s2 + W]] = np.nan
-        data[((s2 + jj0) - (s1 + ii0)) < 2] = np.nan
-        if k not in acc:
-            acc[k] = [data, np.isfinite(data).astype(int)]
-        else:
-            a = acc[k]
-            a[0] = np.nansum([a[0], data], axis=0)
-            a[1] += np.isfinite(data).astype(int)
-        n += 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for s1, s2, k in zip(d["r0"], d["c0"], d["slot"]):
+            if s1 < 0 or s1 + W > nb or s2 < 0 or s2 + W > nb:
+                continue
+            data = mat[s1 : s1 + W, s2 : s2 + W].toarray().astype(float)
+            data[isnan[s1 : s1 + W], :] = np.nan
+            data[:, isnan[s2 : s2 + W]] = np.nan
+            dd = (s2 + jj0) - (s1 + ii0)
+            data[dd < 2] = np.nan
+            if E is not None:
+                data = data / E[np.abs(dd)]
+            if k not in acc:
+                acc[k] = [data, np.isfinite(data).astype(int)]
+            else:
+                a = acc[k]
+                a[0] = np.nansum([a[0], data], axis=0)
+                a[1] += np.isfinite(data).astype(int)
+            n += 1
     return n
 
 
-def cpu_setup(regions_host, windows, per_region, seed=99):
-    """Uniform sample of each region's windows for the CPU arms."""
+def cpu_setup(regions_host, windows, total_sample, W, seed=99):
+    """A sample of the workload's windows for the CPU arms: every region contributes in proportion to its share of
+    the windows (uniformly drawn inside the region)."""
     rng = np.random.default_rng(seed)
+    n_all = sum(len(windows[c]["r0"]) for c in regions_host)
     regs = {}
     for name, d in regions_host.items():
         w = windows[name]
         n = len(w["r0"])
-        k = min(per_region, n)
+        k = min(n, int(round(total_sample * n / max(1, n_all))))
         idx = np.sort(rng.choice(n, k, replace=False)) if k else np.zeros(0, dtype=np.int64)
         regs[name] = dict(d, r0=w["r0"][idx], c0=w["c0"][idx], slot=w["slot"][idx])
     _CPU["regions"] = regs
+    _CPU["W"] = W
 
 
 def run_cpu_pool(names, nproc, steps, warmup):
     """One process per region task like Pool.starmap over regions (coolpup.py:1502-1508); returns windows/s."""
     import multiprocessing as mp
 
+    from coolpuppy_b200.multigpu import lpt_assign
+
     ctx = mp.get_context("fork")
+    names = [n for n in names if len(_CPU["regions"][n]["r0"])]
     nproc = max(1, min(nproc, len(names)))
-    owner = lpt([len(_CPU["regions"][n]["r0"]) * max(1.0, _CPU["regions"][n]["nb"] / 1e4) for n in names], nproc)
+    owner = lpt_assign([len(_CPU["regions"][n]["r0"]) * max(1.0, _CPU["regions"][n]["nb"] / 1e4) for n in names], nproc)
     groups = [[n for n, o in zip(names, owner) if o == r] for r in range(nproc)]
 
     def worker(conn, mine):
@@ -237,111 +264,195 @@ def run_cpu_pool(names, nproc, steps, warmup):
     return total / dt, dt / steps, total // max(steps, 1), nproc
 
 
+# ------------------------------------------------------------------------------------------------ genome + windows
+def generate_genome(args, sizes, dev, keep_device, keep_host, pin):
+    """Per chromosome: the cooler-style upper triangle (+ weights, expected) as device tensors and / or host arrays."""
+    import torch
+
+    from coolpuppy_b200.synthetic import synthetic_region
+
+    dev_data, host_data = {}, {}
+    for ci, (c, L) in enumerate(sizes.items()):
+        nb = -(-L // BINSIZE)
+        t = synthetic_region(nb, depth=args.depth, seed=1234 + ci, device=dev, nan_frac=0.03)
+        keys = ("upper_indptr", "upper_col", "upper_count", "weight", "expected")
+        if c in keep_device:
+            dev_data[c] = {k: t[k] for k in keys}
+            dev_data[c]["nb"] = nb
+        if c in keep_host:
+            h = {}
+            for k in keys:
+                x = t[k].cpu()
+                h[k] = x.pin_memory() if pin else x
+            h["nb"] = nb
+            host_data[c] = h
+        del t
+    torch.cuda.synchronize(dev)
+    torch.cuda.empty_cache()
+    return dev_data, host_data
+
+
+def expected_table(host_or_dev):
+    import pandas as pd
+
+    rows = []
+    for c, d in host_or_dev.items():
+        e = d["expected"]
+        e = e.cpu().numpy() if hasattr(e, "cpu") else np.asarray(e)
+        nb = d["nb"]
+        rows.append(pd.DataFrame({"region1": c, "region2": c, "dist": np.arange(nb), "n_valid": nb - np.arange(nb),
+                                  "balanced.avg": e}))
+    return pd.concat(rows, ignore_index=True)
+
+
+def host_cooler(sizes, host_data, pin):
+    """The workload's genome as a cooler object (coolio.ChromCooler: per-chromosome upper-triangle CSR)."""
+    from coolpuppy_b200.coolio import ChromCooler
+
+    regions = {c: tuple(np.asarray(h[k]) if not hasattr(h[k], "numpy") else h[k].numpy()
+                        for k in ("upper_indptr", "upper_col", "upper_count")) for c, h in host_data.items()}
+    nb = {c: -(-L // BINSIZE) for c, L in sizes.items()}
+    weight = np.concatenate([(host_data[c]["weight"].numpy() if c in host_data else np.full(nb[c], np.nan)) for c in sizes])
+    clr = ChromCooler(sizes, BINSIZE, regions, {"weight": weight}, filename="synthetic_3Gbp_10kb.cool", pin=False)
+    return clr
+
+
+def build_windows(args, sizes, features, expected_df):
+    """Host side of the path through the product's own builder (PileUpper._prepare): per-chromosome window arrays
+    (reference emission order, seeded control shifts) with their dense accumulator slots."""
+    from functools import partial
+
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.coolio import ChromCooler
+
+    wl = WORKLOADS[args.workload]
+    kw = wl["kwargs"]
+    nbins = sum(-(-L // BINSIZE) for L in sizes.values())
+    clr = ChromCooler(sizes, BINSIZE, {}, {"weight": np.ones(nbins)}, filename="synthetic_3Gbp_10kb.cool")
+    np.random.seed(0)
+    cc = cp.CoordCreator(features, BINSIZE, features_format=kw["features_format"], flank=wl["flank"], nshifts=wl["nshifts"],
+                         mindist="auto", seed=0 if wl["nshifts"] else None)
+    pu = cp.PileUpper(clr, cc, clr_weight_name="weight", expected=expected_df if wl["expected"] else False, ooe=True,
+                      control=wl["nshifts"] > 0)
+    groupby, modify = [], None
+    if kw.get("by_strand"):
+        groupby += ["strand1", "strand2"]
+    if kw.get("by_distance"):
+        modify = partial(cp.bin_distance_intervals, band_edges=pu._distance_edges("default"))
+        groupby += ["distance_band"]
+    plan = pu._plan(groupby, False, modify, None)
+    plan["band_edges"] = pu._band_edges(plan)
+    job = pu._prepare(plan, None, None)
+    out = {c: dict(nb=-(-L // BINSIZE), r0=np.zeros(0, np.int32), c0=np.zeros(0, np.int32), slot=np.zeros(0, np.int32), n_roi=0)
+           for c, L in sizes.items()}
+    for b in job["built"]:
+        out[b["name"]].update(r0=b["w_r0"].astype(np.int32), c0=b["w_c0"].astype(np.int32), slot=b["slot"].astype(np.int32),
+                              n_roi=int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))))
+    return out, job["n_slots"], job["flags"]
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference" and rank != 0:
-        return 0
+    if args.impl == "reference":
+        return 0 if rank != 0 else run_reference(args)
 
     import torch
 
     from coolpuppy_b200 import _native
-    from coolpuppy_b200.synthetic import synthetic_region
+    from coolpuppy_b200.multigpu import lpt_assign, part_index, split_heavy
 
     _native.require_device()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
-    if world > 1 and args.impl == "b200":
+    if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group(backend="nccl", device_id=dev)
 
+    wl = WORKLOADS[args.workload]
+    W = 2 * (wl["flank"] // BINSIZE) + 1
     sizes = chromsizes(args)
     names = list(sizes)
+    features, n_pairs = make_features(args, sizes)
+    want_host = (not args.no_e2e) or (not args.no_api) or (rank == 0 and not args.no_cpu and world == 1)
+    # every rank generates every chromosome (seeded, identical): exact per-chromosome bytes need the matrices
+    dev_data, host_data = generate_genome(args, sizes, dev, keep_device=set(names), keep_host=set(names) if want_host else set(),
+                                          pin=world == 1)
+    expected_df = expected_table(dev_data) if wl["expected"] else None
     t_host0 = time.perf_counter()
-    windows, n_sites, n_pairs = build_windows(args, sizes)
+    windows, n_slots, flags = build_windows(args, sizes, features, expected_df)
     host_window_s = time.perf_counter() - t_host0
     n_windows_total = sum(len(w["r0"]) for w in windows.values())
-    config = {
-        "workload": "configs[3]: synthetic 3 Gbp @10 kb (hg38 lengths, Poisson(depth/sep)), all-vs-all cis pairs of "
-                    f"{n_sites} CTCF-like sites, pad=41 (W=83), nshifts={args.nshifts}, balanced (3% NaN bins), no expected",
-        "depth": args.depth, "roi_windows": int(n_pairs), "windows_per_step": int(n_windows_total),
-        "chromosomes": len(names), "binsize": BINSIZE, "flank": FLANK,
-        "l2": "inputs (region matrices, GBs) exceed the 126 MB L2; no flush between iterations",
-        "parallelism": f"chromosomes sharded over {world} GPU(s) by LPT, one all-reduce of the accumulators",
-        "host_window_generation_s": round(host_window_s, 3),
-    }
+    n_roi_total = sum(w["n_roi"] for w in windows.values())
+    region_flags = flags & _native.PUP_F_OOE
+    acc_flags = flags & (_native.PUP_F_EXPCTRL | _native.PUP_F_COVERAGE)
 
-    # which chromosomes are mine (the sharding unit of the reference: one view region per worker, coolpup.py:1502-1508)
-    cost = [len(windows[c]["r0"]) * (windows[c]["nb"] / 1e4) for c in names]
-    owner = lpt(cost, world if args.impl == "b200" else 1)
-    mine = [c for c, o in zip(names, owner) if o == (rank if args.impl == "b200" else 0)]
-    # Resident pass, N > 1: a chromosome heavier than half a rank's share is split by WINDOWS into equal parts that go
-    # to different ranks with the matrix replicated (windows are independent, the accumulators add up);
-    # otherwise chr1 alone (13 % of the work) caps 8 ranks at 7.6x.  The e2e pass keeps whole chromosomes per rank:
-    # there the matrix upload, not the pile-up, is the cost of a unit.
-    from coolpuppy_b200.multigpu import part_bounds, split_heavy
-
-    iunits, ucost, uowner = split_heavy(cost, world if args.impl == "b200" else 1)
-    units = [(names[i], part, parts) for i, part, parts in iunits]
-    my_units = [u for u, o in zip(units, uowner) if o == (rank if args.impl == "b200" else 0)]
-    split = sorted({c for c, _, n in units if n > 1}, key=names.index)
-    if split:
-        config["parallelism"] = (f"chromosomes sharded over {world} GPUs by LPT; {','.join(split)} split by windows into "
-                                 f"{sum(1 for c, _, n in units if n > 1)} parts (matrix replicated); one all-reduce of the "
-                                 "accumulators; e2e: whole chromosomes per GPU")
-
-    if args.impl == "reference":
-        return run_reference(args, names, sizes, windows, config, dev)
-
-    # ---- resident data
+    # ---- resident regions + exact algorithmic bytes of every chromosome's windows (identical on all ranks)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    regions, host, dwin = {}, {}, {}
-    nnz_total = 0
-    unit_chroms = {c for c, _, _ in my_units}
-    for ci, c in enumerate(names):
-        if c not in mine and c not in unit_chroms:
-            continue
-        t = synthetic_region(windows[c]["nb"], depth=args.depth, seed=1234 + ci, device=dev, nan_frac=0.03)
-        if c in unit_chroms:
-            nnz_total += int(t["col"].shape[0])
-            regions[c] = _native.Region(local_rank, t["nb"], t["indptr"], t["col"], t["count"], t["weight"], None, None,
-                                        ignore_diags=2, flags=0, stream=stream)
-        if c in mine and (not args.no_e2e or (rank == 0 and not args.no_cpu)):
-            host[c] = {k: t[k].cpu().pin_memory() for k in ("upper_indptr", "upper_col", "upper_count", "weight")}
-            if rank == 0 and not args.no_cpu and c in CPU_SAMPLE_REGIONS:
-                host[c].update({k: t[k].cpu() for k in ("indptr", "col", "count")})
-        del t
+    regions, cost, nnz_win = {}, [], []
+    for c in names:
+        d = dev_data[c]
+        regions[c] = _native.Region(local_rank, d["nb"], d["upper_indptr"], d["upper_col"], d["upper_count"], d["weight"],
+                                    d["expected"] if wl["expected"] else None, None, ignore_diags=2, flags=region_flags,
+                                    stream=stream, upper=True)
+        w = windows[c]
+        if len(w["r0"]):
+            b, z = regions[c].algorithmic_bytes(torch.from_numpy(w["r0"]).to(dev), torch.from_numpy(w["c0"]).to(dev), W, flags,
+                                                stream=stream)
+        else:
+            b, z = 0, 0
+        cost.append(b)
+        nnz_win.append(z)
+    iunits, ucost, uowner = split_heavy(cost, world, max_share=0.25)
+    my_units = [(names[i], part, parts) for (i, part, parts), o in zip(iunits, uowner) if o == rank]
+    load = np.bincount(uowner, weights=ucost, minlength=world)
+    predicted_imbalance = float(load.max() / load.mean()) if load.sum() > 0 else 1.0
+    for c in names:  # matrices of chromosomes this rank has no unit of are not needed any more
+        if c not in {u[0] for u in my_units}:
+            regions.pop(c).close()
+    split = sorted({c for c, _, n in my_units if n > 1} | {names[i] for (i, _, n) in iunits if n > 1}, key=names.index)
+    dwin = {}
+    alg_bytes = 0
     for c, part, parts in my_units:
         w = windows[c]
-        lo, hi = part_bounds(len(w["r0"]), part, parts)
-        dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][lo:hi])).to(dev) for k in ("r0", "c0", "slot"))
+        sel = part_index(len(w["r0"]), part, parts)
+        dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][sel])).to(dev) for k in ("r0", "c0", "slot"))
+        if parts == 1:
+            alg_bytes += cost[names.index(c)]
+        elif len(sel):
+            alg_bytes += regions[c].algorithmic_bytes(dwin[(c, part)][0], dwin[(c, part)][1], W, flags, stream=stream)[0]
+    if not want_host:
+        host_data = {}
+    del dev_data
     torch.cuda.synchronize(dev)
     torch.cuda.empty_cache()
 
-    n_slots = 2
+    config = {
+        "workload": workload_description(args, len(features), W),
+        "depth": args.depth, "roi_windows": int(n_pairs), "windows_per_step": int(n_windows_total),
+        "chromosomes": len(names), "binsize": BINSIZE, "flank": wl["flank"], "accumulator_slots": int(n_slots),
+        "l2": "inputs (region matrices, GBs) exceed the 126 MB L2; no flush between iterations",
+        "parallelism": (f"chromosomes sharded over {world} GPU(s) by LPT on exact algorithmic bytes; chromosomes above a quarter "
+                        "of a rank's share are cut into strided window parts (matrix replicated); one all-reduce of the "
+                        "accumulators; e2e: whole chromosomes per GPU"),
+    }
+
     stride = _native.acc_stride(W)
     acc = torch.zeros(n_slots * stride, dtype=torch.float64, device=dev)
-    flags = 0
-
-    # exact algorithmic bytes of my windows (untimed)
-    alg_bytes = 0
-    alg_nnz = 0
-    for c, part, _ in my_units:
-        b, z = regions[c].algorithmic_bytes(dwin[(c, part)][0], dwin[(c, part)][1], W, flags, stream=stream)
-        alg_bytes += b
-        alg_nnz += z
 
     def step():
         acc.zero_()
         launches = 1
         for c, part, _ in my_units:
             r0, c0, sl = dwin[(c, part)]
-            regions[c].accumulate(r0, c0, sl, W, n_slots, flags, acc, stream=stream)
+            if r0.shape[0] == 0:
+                continue
+            regions[c].accumulate(r0, c0, sl, W, n_slots, acc_flags, acc, stream=stream)
             launches += _native.lib().pup_last_launches()
         if dist is not None:
             dist.all_reduce(acc)
@@ -370,12 +481,28 @@ def main():
     phases = _native.timing_read(reset=True)
     _native.timing_enable(False)
     clocks = sampler.stop()
+    # all-reduce time alone (payload = the accumulators), N > 1
+    allreduce_ms = None
+    if dist is not None:
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(acc)
+        a1.record()
+        barrier()
+        allreduce_ms = a0.elapsed_time(a1) / 5
+        step()  # restore the accumulators of one clean step
+        barrier()
 
-    out = _native.acc_export(acc, W, n_slots, device=local_rank, stream=stream)
-    n_valid_total = int(out["n"].sum())  # after the all-reduce: whole job
+    n_all = _native.acc_counts(acc, W, n_slots)
+    n_valid_total = int(n_all.sum())  # after the all-reduce: whole job
+    sums = acc.view(n_slots, stride)[:, : W * W]
+    checksum = {"n": n_valid_total, "sum": float(f"{float(sums[torch.isfinite(sums)].sum().item()):.10e}"),
+                "slots_used": int((n_all > 0).sum())}
 
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    stats = torch.tensor([alg_bytes, alg_nnz, phases["main"][0], nnz_total, launches], dtype=torch.float64, device=dev)
+    stats = torch.tensor([alg_bytes, phases["main"][0], launches, phases["main"][1]], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         allstats = [torch.zeros_like(stats) for _ in range(world)]
@@ -385,59 +512,37 @@ def main():
     ms = float(t_ms.item())
     ms_per_step = ms / args.steps
     value = n_valid_total / (ms_per_step / 1e3)
+    roi_valid = n_roi_total  # ROI windows that lie inside their region (controls not counted)
 
-    # ---- e2e through the C ABI with host buffers
+    # ---- e2e through the C ABI with host buffers: the product's region pipeline
     e2e = None
+    cost_e2e = [c_ + 40.0 * (host_data[n]["upper_col"].numel() if n in host_data else 0) for n, c_ in zip(names, cost)]
+    owner_e2e = lpt_assign(cost_e2e, world)
+    mine = [c for c, o in zip(names, owner_e2e) if o == rank]
     if not args.no_e2e:
+        from coolpuppy_b200.pipeline import RegionPipeline
+
         hacc = torch.zeros(n_slots * stride, dtype=torch.float64).pin_memory()
         hwin = {c: tuple(torch.from_numpy(windows[c][k]).pin_memory() for k in ("r0", "c0", "slot")) for c in mine}
-        h2d = sum(sum(host[c][k].numel() * host[c][k].element_size()
-                      for k in ("upper_indptr", "upper_col", "upper_count", "weight")) for c in mine)
+        hk = ("upper_indptr", "upper_col", "upper_count", "weight") + (("expected",) if wl["expected"] else ())
+        h2d = sum(sum(host_data[c][k].numel() * host_data[c][k].element_size() for k in hk) for c in mine)
         h2d += sum(sum(t.numel() * t.element_size() for t in hwin[c]) for c in mine)
         d2h = acc.numel() * 8
-
-        s_copy, s_comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        ASYNC = _native.PUP_F_ASYNC
         # upload order: one small chromosome first (its upload is the only one nothing overlaps), then big to small
         e2e_order = sorted(mine, key=lambda c: -windows[c]["nb"])
         if len(e2e_order) > 2:
             e2e_order = [e2e_order[-1]] + e2e_order[:-1]
-        # persistent device landing buffers for the window arrays (filled from the pinned host arrays every step)
-        dwin_e2e = {c: tuple(torch.empty_like(t, device=dev) for t in hwin[c]) for c in mine}
 
         def e2e_step():
-            # every upload (matrices via pup_region_create_upper, window arrays via pup_upload) travels on the
-            # library's upload stream in consumption order and runs ahead of the kernels; chromosome k+1 is
-            # mirrored / normalised / indexed on s_copy while chromosome k piles up on s_comp
-            main_stream = torch.cuda.current_stream(dev)
-            s_comp.wait_stream(main_stream)
-            s_copy.wait_stream(main_stream)
-            with torch.cuda.stream(s_comp):
-                acc.zero_()
-
-            def upload(c):
-                h = host[c]
-                reg = _native.Region(local_rank, windows[c]["nb"], h["upper_indptr"], h["upper_col"], h["upper_count"],
-                                     h["weight"], None, None, ignore_diags=2, flags=ASYNC, stream=s_copy.cuda_stream,
-                                     upper=True)
-                for d, hsrc in zip(dwin_e2e[c], hwin[c]):
-                    _native.upload(local_rank, d, hsrc, stream=s_copy.cuda_stream)
-                ev = s_copy.record_event()  # matrix indexed and window arrays landed
-                return reg, ev
-
-            nxt = upload(e2e_order[0]) if e2e_order else None
-            for k, c in enumerate(e2e_order):
-                reg, ready = nxt
-                nxt = upload(e2e_order[k + 1]) if k + 1 < len(e2e_order) else None
-                s_comp.wait_event(ready)
-                r0, c0, sl = dwin_e2e[c]
-                reg.accumulate(r0, c0, sl, W, n_slots, flags | ASYNC, acc, stream=s_comp.cuda_stream)
-                done = s_comp.record_event()
-                s_copy.wait_event(done)
-                with torch.cuda.stream(s_copy):
-                    reg.close()
-            main_stream.wait_stream(s_comp)
-            main_stream.wait_stream(s_copy)
+            acc.zero_()
+            pipe = RegionPipeline(local_rank, W, n_slots, acc_flags)
+            for c in e2e_order:
+                h = host_data[c]
+                kw = dict(nb=h["nb"], indptr=h["upper_indptr"], col=h["upper_col"], count=h["upper_count"], weight=h["weight"],
+                          expected=h["expected"] if wl["expected"] else None, coverage=None, ignore_diags=2,
+                          flags=region_flags, upper=True)
+                pipe.submit(kw, tuple(t.numpy() for t in hwin[c]), acc)
+            pipe.finish()
             if dist is not None:
                 dist.all_reduce(acc)
             hacc.copy_(acc, non_blocking=True)
@@ -459,10 +564,53 @@ def main():
         e2e = {"value": n_valid_total / (float(ems.item()) / 1e3), "unit": "pile-ups/s", "ms_per_step": float(ems.item()),
                "h2d_bytes_per_step": int(bts[0].item()), "d2h_bytes_per_step": int(bts[1].item()),
                "steps": args.e2e_steps,
-               "what": "pup_region_create_upper + pup_accumulate per chromosome with pinned HOST buffers: the cooler-style "
-                       "upper-triangle pixels (indptr, col, count), weights and window arrays are uploaded, mirrored / "
-                       "normalised / indexed on the device and piled up; uploads run ahead on copy streams in consumption "
-                       "order, chromosome k+1 is indexed while chromosome k piles up; D2H of the accumulators at the end"}
+               "what": "coolpuppy_b200.pipeline.RegionPipeline (the product's own region loop) with pinned HOST buffers: per "
+                       "chromosome pup_region_create_upper(cooler-style upper-triangle pixels, weights[, expected]) + pup_upload"
+                       "(window arrays) on a prepare stream while the previous chromosome's pup_accumulate runs on a compute "
+                       "stream; D2H of the accumulators at the end"}
+
+    # ---- e2e through the public API: pileup(clr, features, ...) -> DataFrame
+    e2e_api = None
+    if not args.no_api:
+        from coolpuppy_b200 import coolpup as cp
+        from coolpuppy_b200.multigpu import RegionSharder
+
+        clr = host_cooler(sizes, host_data, pin=False)  # views of the (pinned, when N = 1) host arrays
+        sharder = RegionSharder() if dist is not None else None
+        kw = dict(wl["kwargs"], flank=wl["flank"], clr_weight_name="weight", device=local_rank, dist=sharder)
+        if wl["expected"]:
+            kw["expected_df"] = expected_df
+        import logging
+        import warnings
+
+        logging.getLogger("coolpuppy").setLevel(logging.WARNING)
+        times, stats_api, n_api = [], None, None
+        for i in range(args.api_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                pups = cp.pileup(clr, features, **kw)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if i > 0:  # the first call warms the allocator / module state
+                times.append(dt)
+            is_all = [isinstance(g, str) and g == "all" for g in pups["group"]]
+            n_api = int(pups.loc[is_all, "n"].iloc[0]) if any(is_all) else None
+            stats_api = dict(cp._LAST_STATS)
+        t_api = torch.tensor([float(np.median(times))], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_api, op=dist.ReduceOp.MAX)
+        sec = float(t_api.item())
+        api_windows = int(stats_api.get("windows", 0))
+        e2e_api = {"value": api_windows / sec, "unit": "pile-ups/s", "seconds_per_call": sec, "calls": len(times),
+                   "windows_per_call": api_windows, "rows": int(len(pups)), "n_all": n_api,
+                   "host_prepare_s": stats_api.get("host_prepare_s"), "gpu_phase_s": stats_api.get("gpu_phase_s"),
+                   "gpu_share": (stats_api.get("gpu_phase_s") or 0.0) / sec if sec > 0 else None,
+                   "device_windows": stats_api.get("device_windows"), "sharding_imbalance_predicted": stats_api.get("imbalance"),
+                   "what": "wall time of coolpuppy_b200.coolpup.pileup(clr, features, **kwargs) -> DataFrame: feature table in, "
+                           "window generation" + (" + MT19937 control shifts" if wl["nshifts"] else "") + " on the GPU when the "
+                           "workload allows, region pipeline from host memory, all-reduce, export, final normalisation"}
 
     if rank != 0:
         if dist is not None:
@@ -477,81 +625,104 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
-    # per rank: bytes of its windows / its main-kernel time; report the slowest rank's kernel (rank with max main ms)
-    per_rank = [(float(s[0]), float(s[2]) / args.steps) for s in allstats]
-    tot_bytes = sum(b for b, _ in per_rank)
-    slow_b, slow_ms = max(per_rank, key=lambda x: x[1])
+    per_rank = [(float(s[0]), float(s[1]) / args.steps, float(s[3]) / args.steps) for s in allstats]
+    tot_bytes = sum(b for b, _, _ in per_rank)
+    slow_b, slow_ms, slow_launches = max(per_rank, key=lambda x: x[1])
     achieved = (slow_b / 1e9) / (slow_ms / 1e3) if slow_ms > 0 else 0.0
-    n_main = max(1, phases["main"][1])
-    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/r1_k_pileup_main_ncu.md): the
-    # chr1 launch moved 4.82 GB (read+write) for 16.6 GB of algorithmic bytes; scaled to the average launch here
-    traffic = None
+    kernel_ms = [m_ for _, m_, _ in per_rank]
+    bytes_rank = [b for b, _, _ in per_rank]
+    # DRAM traffic of the dominant kernel: from the committed `ncu --set full` capture of this round (it cannot be
+    # measured outside a profiler); reported per launch, scaled by algorithmic bytes from the captured launch
+    traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        traffic = int(tr["dram_bytes"] / tr["algorithmic_bytes"] * (slow_b / max(1, len(my_units))))
+        tr = json.load(open(os.path.join(ROOT, "profiles", f"r2_traffic_{args.workload}.json")))
+        traffic = int(tr["dram_bytes"] / tr["algorithmic_bytes"] * (slow_b / max(1.0, slow_launches)))
+        traffic_src = tr.get("source")
     except Exception:
         pass
     roofline = {
         "kernel": "k_pileup_main", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "traffic_source": "ncu --set full capture of the chr1 launch (profiles/r1_k_pileup_main_ncu.md), scaled by "
-                          "algorithmic bytes to the average launch",
-        "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1, len(my_units))),
-        "kernel_ms_per_step": slow_ms, "launches_per_step": n_main // args.steps,
-        "avg_launch_ms": slow_ms / max(1, n_main // args.steps),
-        "stored_pixels_in_windows_per_step": int(sum(float(s[1]) for s in allstats)),
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
+        "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1.0, slow_launches)),
+        "kernel_ms_per_step": slow_ms, "launches_per_step": int(slow_launches),
+        "avg_launch_ms": slow_ms / max(1.0, slow_launches),
+        "stored_pixels_in_windows_per_step": int(sum(nnz_win)),
         "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
+        "kernel_ms_per_step_by_rank": kernel_ms,
     }
+    sharding = {"units": len(iunits), "split_chromosomes": split, "predicted_max_over_mean": predicted_imbalance,
+                "bytes_max_over_mean": float(max(bytes_rank) / (sum(bytes_rank) / len(bytes_rank))) if sum(bytes_rank) else 1.0,
+                "kernel_ms_max_over_mean": float(max(kernel_ms) / (sum(kernel_ms) / len(kernel_ms))) if sum(kernel_ms) else 1.0,
+                "allreduce_payload_bytes": int(acc.numel() * 8), "allreduce_ms": allreduce_ms}
 
     # ---- CPU baseline: restated reference path on a bounded sample, 1 core
     cpu = None
     if not args.no_cpu and world == 1:
-        sample_regions = [c for c in CPU_SAMPLE_REGIONS if c in mine and "col" in host[c]] or mine[:2]
-        per = max(1, args.cpu_sample // len(sample_regions))
-        rh = {c: dict(nb=windows[c]["nb"], **{k: host[c][k].numpy() for k in ("indptr", "col", "count", "weight")}) for c in sample_regions}
-        cpu_setup(rh, windows, per)
-        for c in sample_regions:
+        rh = {c: dict(nb=host_data[c]["nb"], **{k: host_data[c][k].numpy() for k in ("upper_indptr", "upper_col", "upper_count", "weight")},
+                      **({"expected": host_data[c]["expected"].numpy()} if wl["expected"] else {})) for c in names}
+        cpu_setup(rh, windows, args.cpu_sample, W)
+        used = [c for c in names if len(_CPU["regions"][c]["r0"])]
+        for c in used:
             _cpu_worker_prepare(c)
         t0 = time.perf_counter()
-        nwin = sum(_cpu_worker_step(c) for c in sample_regions)
+        nwin = sum(_cpu_worker_step(c) for c in used)
         dt = time.perf_counter() - t0
         cpu = {"value": nwin / dt, "unit": "pile-ups/s", "cores": 1, "kind": "port",
-               "sample": f"{nwin} windows drawn uniformly from {','.join(sample_regions)} of the same workload "
-                         f"({dt:.1f} s; matrix fetch+balancing untimed), oracle restatement of _stream_snips+_add_snip",
+               "sample": f"{nwin} windows drawn from all {len(used)} chromosomes in proportion to their share of the "
+                         f"workload's windows ({dt:.1f} s; matrix fetch+balancing untimed), oracle restatement of "
+                         "_stream_snips+_add_snip",
                "host_cpus": os.cpu_count()}
 
     line = {
         "metric": "pile-ups/sec (1e6 ROIs, 10kb bins, pad=41)", "value": value, "unit": "pile-ups/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(float(s[4]) for s in allstats)),
-        "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "e2e_api": e2e_api, "gpu_launches": int(sum(float(s[2]) for s in allstats)),
+        "roofline": roofline, "cpu_baseline": cpu, "sharding": sharding, "checksum": checksum,
         "windows_accumulated_per_step": n_valid_total,
+        "value_roi_only": roi_valid / (ms_per_step / 1e3),
+        "host_window_generation_s": {"host_builder_for_resident_arrays": round(host_window_s, 3),
+                                     "api_host_prepare": None if e2e_api is None else e2e_api["host_prepare_s"]},
     }
+    if args.workload != "configs3":
+        line["metric"] = f"pile-ups/sec ({args.workload} of BASELINE.json)"
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
-def run_reference(args, names, sizes, windows, config, dev):
-    """--impl reference: the restated reference CPU path on all usable host cores, bounded sample per step."""
+def run_reference(args):
+    """--impl reference: the restated reference CPU path on all usable host cores, bounded sample per step.
+
+    Nothing of the product runs here: libpileup_b200.so is not loaded, windows are enumerated with numpy, the timed
+    loop is numpy / scipy in forked worker processes.  The synthetic genome itself is generated with torch (on the GPU
+    when one is visible -- untimed input preparation, labelled in the output -- else on the CPU)."""
     import torch
 
-    from coolpuppy_b200.synthetic import synthetic_region
-
-    regions_host = {}
-    for ci, c in enumerate(names):
-        t = synthetic_region(windows[c]["nb"], depth=args.depth, seed=1234 + ci, device=dev, nan_frac=0.03)
-        regions_host[c] = dict(nb=t["nb"], **{k: t[k].cpu().numpy() for k in ("indptr", "col", "count", "weight")})
-        del t
-        torch.cuda.empty_cache()
-    cpu_setup(regions_host, windows, args.ref_sample)
+    wl = WORKLOADS[args.workload]
+    W = 2 * (wl["flank"] // BINSIZE) + 1
+    sizes = chromsizes(args)
+    names = list(sizes)
+    features, n_pairs = make_features(args, sizes)
+    gen_dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    _, host_data = generate_genome(args, sizes, gen_dev, keep_device=set(), keep_host=set(names), pin=False) \
+        if gen_dev.type == "cuda" else _generate_genome_cpu(args, sizes)
+    windows = reference_windows(features, sizes, wl, W)
+    n_windows_total = sum(len(w["r0"]) for w in windows.values())
+    rh = {c: dict(nb=host_data[c]["nb"], **{k: np.asarray(host_data[c][k]) for k in ("upper_indptr", "upper_col", "upper_count", "weight")},
+                  **({"expected": np.asarray(host_data[c]["expected"])} if wl["expected"] else {})) for c in names}
+    cpu_setup(rh, windows, args.ref_sample, W)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     value, sec_per_step, per_step, nproc = run_cpu_pool(names, cores, args.steps, args.warmup)
-    sample = (f"{per_step} windows per step ({args.ref_sample} drawn uniformly per chromosome), one process per "
-              f"chromosome task on {nproc} of {cores} cores like Pool.starmap over regions (coolpup.py:1502-1508); "
-              "matrix fetch+balancing untimed")
+    sample = (f"{per_step} windows per step drawn from all chromosomes in proportion to their share of the {n_windows_total} "
+              f"windows, one process per chromosome task on {nproc} of {cores} cores like Pool.starmap over regions "
+              "(coolpup.py:1502-1508); matrix fetch+balancing untimed")
+    config = {
+        "workload": workload_description(args, len(features), W),
+        "depth": args.depth, "roi_windows": int(n_pairs), "windows_per_step": int(n_windows_total),
+        "chromosomes": len(names), "binsize": BINSIZE, "flank": wl["flank"],
+    }
     line = {
         "impl": "reference", "metric": "pile-ups/sec (1e6 ROIs, 10kb bins, pad=41)", "value": value, "unit": "pile-ups/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
@@ -560,9 +731,51 @@ def run_reference(args, names, sizes, windows, config, dev):
         "cpu_baseline": {"value": value, "unit": "pile-ups/s", "cores": nproc, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pile-ups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "prep": f"synthetic genome generated with torch on {gen_dev.type} (untimed input preparation, not part of any arm); "
+                "windows enumerated with numpy; libpileup_b200.so not loaded; timed loop = numpy/scipy on host cores",
     }
+    if args.workload != "configs3":
+        line["metric"] = f"pile-ups/sec ({args.workload} of BASELINE.json)"
     print(json.dumps(line))
     return 0
+
+
+def _generate_genome_cpu(args, sizes):
+    return generate_genome(args, sizes, "cpu", keep_device=set(), keep_host=set(sizes), pin=False)
+
+
+def reference_windows(features, sizes, wl, W):
+    """numpy enumeration of the workload's windows for the CPU arm (no native code): ROI pairs / loops per chromosome and
+    their nshifts randomly shifted controls (coolpup.py:682-714, 387-453; same distribution as the product's seeded
+    stream, not the same draws -- the CPU arm times a sample of them)."""
+    res, flank, ns = BINSIZE, wl["flank"], wl["nshifts"]
+    mindist = 2 * flank + 2 * res
+    rng = np.random.default_rng(0)
+    out = {}
+    for c, L in sizes.items():
+        nb = -(-L // res)
+        if wl["features"] == "loops":
+            f = features[features["chrom1"] == c]
+            c1 = (f["start1"].values + f["end1"].values) / 2
+            c2 = (f["start2"].values + f["end2"].values) / 2
+            keep = np.abs(c2 - c1) >= mindist
+            a = np.floor(c1[keep] / res).astype(np.int64) - flank // res
+            b = np.floor(c2[keep] / res).astype(np.int64) - flank // res
+        else:
+            f = features[features["chrom"] == c].sort_values("start")
+            ctr = (f["start"].values + f["end"].values) / 2
+            st = np.floor(ctr / res).astype(np.int64) - flank // res
+            k, l = np.triu_indices(len(ctr), 1)
+            keep = np.abs(ctr[l] - ctr[k]) >= mindist
+            a, b = st[k[keep]], st[l[keep]]
+        slot = np.zeros(len(a), dtype=np.int32)
+        if ns > 0 and len(a):
+            sh = np.round(rng.integers(10**5, 10**6, len(a) * ns) * rng.choice([-1, 1], len(a) * ns) / res).astype(np.int64)
+            a = np.concatenate([a, np.tile(a, ns) + sh])
+            b = np.concatenate([b, np.tile(b, ns) + sh])
+            slot = np.concatenate([slot, np.ones(len(sh), dtype=np.int32)])
+        out[c] = dict(nb=nb, r0=a.astype(np.int32), c0=b.astype(np.int32), slot=slot)
+    return out
 
 
 if __name__ == "__main__":

@@ -32,7 +32,7 @@ import pandas as pd
 
 from . import hdf5lite
 
-__all__ = ["Cooler", "MemCooler", "parse_region", "is_cooler"]
+__all__ = ["Cooler", "MemCooler", "ChromCooler", "parse_region", "is_cooler"]
 
 
 def parse_region(region, chromsizes):
@@ -355,6 +355,117 @@ class MemCooler(_CoolerBase):
 
     def _bin_column(self, name):
         return self._cols[name]
+
+
+class ChromCooler(_CoolerBase):
+    """In-memory cooler that keeps every chromosome's cis pixels as the region-relative upper-triangle CSR the CUDA
+    path consumes (``int32 indptr[nb+1], col[nnz], count[nnz]``), so that ``region_upper_csr`` of a whole-chromosome
+    view is a zero-copy lookup -- with the arrays in pinned memory (``pin=True``) the host->device copies of the region
+    pipeline are truly asynchronous.  Trans pixels are not represented.  Sub-chromosome views and the cooler-style
+    ``matrix().fetch`` work too (they build global pixel ids on demand).
+    """
+
+    def __init__(self, chromsizes, binsize, regions, bin_columns=None, filename="<memory>.cool", pin=False):
+        self.filename = filename
+        self.binsize = int(binsize)
+        if isinstance(chromsizes, dict):
+            chromsizes = pd.Series(chromsizes)
+        self.chromnames = [str(c) for c in chromsizes.index]
+        self.chromsizes = pd.Series(
+            np.asarray(chromsizes.values, dtype=np.int64), index=pd.Index(self.chromnames, name="name"), name="length"
+        )
+        nb = -(-self.chromsizes.values // self.binsize)
+        self._chrom_offset = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+        nbins = int(self._chrom_offset[-1])
+        self._keep = []  # pinned torch tensors backing the numpy views
+
+        def hold(a, dtype):
+            a = np.ascontiguousarray(a, dtype=dtype)
+            if not pin:
+                return a
+            import torch
+
+            t = torch.from_numpy(a).pin_memory()
+            self._keep.append(t)
+            return t.numpy()
+
+        self._regions = {}
+        offs = np.zeros(nbins + 1, dtype=np.int64)
+        total = 0
+        for ci, c in enumerate(self.chromnames):
+            n = int(nb[ci])
+            if c in regions:
+                ip, col, cnt = regions[c]
+                ip = np.asarray(ip)
+                if ip.shape[0] != n + 1:
+                    raise ValueError(f"{c}: indptr has {ip.shape[0]} entries, expected {n + 1}")
+                self._regions[c] = (hold(ip, np.int32), hold(col, np.int32), hold(cnt, np.int32))
+            else:
+                self._regions[c] = (np.zeros(n + 1, dtype=np.int32), np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+            lo = int(self._chrom_offset[ci])
+            offs[lo : lo + n + 1] = total + self._regions[c][0].astype(np.int64)
+            total += int(self._regions[c][0][-1])
+        self._bin1_offset = offs
+        starts = np.concatenate([np.arange(n, dtype=np.int64) * self.binsize for n in nb])
+        chrom_col = np.repeat(np.asarray(self.chromnames, dtype=object), nb)
+        ends = np.minimum(starts + self.binsize, np.repeat(self.chromsizes.values, nb))
+        self._cols = {"chrom": chrom_col, "start": starts, "end": ends}
+        for k, v in (bin_columns or {}).items():
+            v = np.asarray(v)
+            if v.shape[0] != nbins:
+                raise ValueError(f"bin column {k!r} has {v.shape[0]} rows, expected {nbins}")
+            self._cols[k] = hold(v, v.dtype) if pin and v.dtype == np.float64 else v
+
+    def _bin_columns(self):
+        return list(self._cols)
+
+    def _bin_column(self, name):
+        return self._cols[name]
+
+    def _chrom_of(self, lo, hi):
+        ci = int(np.searchsorted(self._chrom_offset, lo, side="right") - 1)
+        if hi > int(self._chrom_offset[ci + 1]):
+            raise ValueError("bin range spans chromosomes")
+        return ci
+
+    def region_upper_csr(self, lo, hi):
+        ci = self._chrom_of(lo, hi)
+        off = int(self._chrom_offset[ci])
+        ip, col, cnt = self._regions[self.chromnames[ci]]
+        if lo == off and hi == int(self._chrom_offset[ci + 1]):
+            return ip, col, cnt  # the stored arrays themselves
+        a, b = lo - off, hi - off
+        p0, p1 = int(ip[a]), int(ip[b])
+        return (ip[a : b + 1] - p0).astype(np.int32), (col[p0:p1] - a).astype(np.int32), np.ascontiguousarray(cnt[p0:p1])
+
+    def _upper_pixels(self, lo, hi):
+        ci = self._chrom_of(lo, hi)
+        off = int(self._chrom_offset[ci])
+        ip, col, cnt = self._regions[self.chromnames[ci]]
+        a, b = lo - off, hi - off
+        p0, p1 = int(ip[a]), int(ip[b])
+        rows = np.repeat(np.arange(a, b, dtype=np.int64), np.diff(ip[a : b + 1].astype(np.int64)))
+        b2 = col[p0:p1].astype(np.int64)
+        keep = b2 < b
+        return rows[keep] + off, b2[keep] + off, cnt[p0:p1][keep]
+
+    def region_csr(self, lo, hi):
+        b1, b2, c = self._upper_pixels(lo, hi)
+        nb = hi - lo
+        offd = b1 != b2
+        row = np.concatenate([b1, b2[offd]]) - lo
+        col = np.concatenate([b2, b1[offd]]) - lo
+        val = np.concatenate([c, c[offd]])
+        order = np.lexsort((col, row))
+        indptr = np.zeros(nb + 1, dtype=np.int64)
+        np.cumsum(np.bincount(row, minlength=nb), out=indptr[1:])
+        return indptr.astype(np.int32), col[order].astype(np.int32), val[order].astype(np.int32)
+
+    @property
+    def _bin1(self):
+        raise NotImplementedError("ChromCooler keeps per-chromosome CSR arrays, not a global pixel table")
+
+    _bin2 = _count = _bin1
 
 
 def is_cooler(obj):

@@ -33,6 +33,7 @@ from ._coords import RegionWindows, build_region_windows, default_band_edges, na
 from .coolio import is_cooler
 
 logger = logging.getLogger("coolpuppy")
+_LAST_STATS = {}  # statistics of the most recent PileUpper run in this process (bench.py reads them after pileup())
 
 __all__ = [
     "CoordCreator", "PileUpper", "pileup", "bin_distance_intervals", "assign_groups", "expand", "expand2D",
@@ -919,7 +920,7 @@ class PileUpper:
         W, n_slots, flags, plan = job["W"], job["n_slots"], job["flags"], job["plan"]
         dev = torch.device("cuda", self._device)
         pipe = _native.make_pipeline(self._device, W, n_slots, flags)
-        s_rng = torch.cuda.Stream(dev)
+        s_rng = pipe.s_side
         s_rng.wait_stream(torch.cuda.current_stream(dev))
         need_rng = any(len(it["segs"]) for it in job["items"])
         rng = _native.DeviceRng(self._device, stream=s_rng.cuda_stream) if need_rng else None
@@ -1041,6 +1042,8 @@ class PileUpper:
         self._last_stats = {"windows": int(out["n"].sum()), "launches": pipe.launches, "regions": pipe.regions,
                             "imbalance": job["imbalance"], "n_slots": n_slots, "used_slots": int(len(used)),
                             "device_windows": bool(on_device), "host_prepare_s": t1 - t0, "gpu_phase_s": t2 - t1}
+        _LAST_STATS.clear()
+        _LAST_STATS.update(self._last_stats)
         grouped = bool(plan["groupby"]) or plan["by_window"]
         roi, ctrl = self._slots_to_pups(out, used, job, grouped)
         if exact:

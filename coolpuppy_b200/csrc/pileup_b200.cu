@@ -2449,6 +2449,7 @@ int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center,
 // ------------------------------------------------------------------------------------------ device-side windows
 struct pup_rng {
   int device;
+  cudaStream_t stream;  // the stream the state was allocated on
   pup_rng_state* st;
 };
 
@@ -2463,11 +2464,13 @@ int pup_rng_create(int device, const uint32_t* key, int pos, void* stream, pup_r
   h.pos = pos;
   pup_rng* r = new pup_rng();
   r->device = device;
-  cudaError_t e = cudaMalloc((void**)&r->st, sizeof(pup_rng_state));
+  r->stream = st;
+  // stream-ordered allocation (no device-wide synchronisation like cudaMalloc / cudaFree); the 2.5 KB pageable source
+  // on this frame is staged by the runtime before cudaMemcpyAsync returns
+  cudaError_t e = cudaMallocAsync((void**)&r->st, sizeof(pup_rng_state), st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(r->st, &h, sizeof h, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `h` lives on this stack frame
   if (e != cudaSuccess) {
-    if (r->st) cudaFree(r->st);
+    if (r->st) cudaFreeAsync(r->st, st);
     delete r;
     return fail(PUP_E_CUDA, "pup_rng_create", e);
   }
@@ -2491,7 +2494,7 @@ int pup_rng_read(pup_rng_t* r, uint32_t* key, int* pos, void* stream) {
 int pup_rng_destroy(pup_rng_t* r) {
   if (!r) return PUP_OK;
   DeviceGuard guard(r->device);
-  if (r->st) cudaFree(r->st);
+  if (r->st) cudaFreeAsync(r->st, r->stream);
   delete r;
   return PUP_OK;
 }

@@ -21,6 +21,20 @@ import numpy as np
 from . import _native
 
 
+_STREAMS = {}
+
+
+def device_streams(device):
+    """(prepare, compute, side) streams of ``device``, created once per process: torch's caching allocator keeps one
+    memory pool per stream, so fresh streams per run would turn every scratch allocation into a cudaMalloc."""
+    import torch
+
+    if device not in _STREAMS:
+        dev = torch.device("cuda", device)
+        _STREAMS[device] = tuple(torch.cuda.Stream(dev) for _ in range(3))
+    return _STREAMS[device]
+
+
 class RegionPipeline:
     def __init__(self, device, W, n_slots, flags):
         import torch
@@ -30,8 +44,8 @@ class RegionPipeline:
         self.dev = torch.device("cuda", self.device)
         self.W, self.n_slots, self.flags = int(W), int(n_slots), int(flags)
         self.main = torch.cuda.current_stream(self.dev)
-        self.s_prep = torch.cuda.Stream(self.dev)
-        self.s_comp = torch.cuda.Stream(self.dev)
+        self.s_prep, self.s_comp, self.s_side = device_streams(self.device)
+        self.s_side.wait_stream(self.main)
         self.s_prep.wait_stream(self.main)
         self.s_comp.wait_stream(self.main)
         self._pending = None
@@ -70,6 +84,14 @@ class RegionPipeline:
         """
         torch = self.torch
         self._reap()
+        # small per-bin host vectors go through pinned staging tensors: a pageable source would make the upload call
+        # wait until every copy queued before it (the region's pixels, 100s of MB) has drained
+        for k in ("weight", "expected", "coverage"):
+            v = region_kwargs.get(k)
+            if isinstance(v, np.ndarray):
+                t = torch.empty(v.shape[0], dtype=torch.float64, pin_memory=True)
+                t.numpy()[:] = v
+                region_kwargs[k] = t
         self._hold = [v for v in region_kwargs.values() if isinstance(v, np.ndarray) or hasattr(v, "data_ptr")]
         with torch.cuda.stream(self.s_prep):
             region = _native.Region(self.device, flags=region_kwargs.pop("flags", 0) | _native.PUP_F_ASYNC,
