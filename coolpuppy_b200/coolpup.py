@@ -930,14 +930,17 @@ class PileUpper:
         edges = plan["band_edges"]
         edges = None if edges is None else np.ascontiguousarray(edges, dtype=np.float64)
         stride = _native.acc_stride(W)
+        readies = []  # prepare-stream events of the regions submitted so far
         try:
             for it in job["items"]:
                 dbin, shifts_ready = None, None
                 if rng is not None and len(it["segs"]):
                     with torch.cuda.stream(s_rng):
                         if it["owned"]:
-                            dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)
-                            dbin.record_stream(pipe.s_prep)
+                            # the shift buffer of region k is reused by region k + 2: wait until region k's windows exist
+                            if len(readies) >= 2:
+                                s_rng.wait_event(readies[-2])
+                            (dbin,) = pipe.scratch_i32("dbin", int(it["total"]) * it["nctrl"], stream=s_rng)
                         rng.control_shifts(it["segs"], self.CC.minshift, self.CC.maxshift, self.resolution, dbin,
                                            stream=s_rng.cuda_stream)
                         shifts_ready = s_rng.record_event()
@@ -950,7 +953,7 @@ class PileUpper:
                 def generate(stream, it=it, dbin=dbin, shifts_ready=shifts_ready, n_mine=n_mine, targets=targets):
                     if shifts_ready is not None:
                         stream.wait_event(shifts_ready)
-                    outs = tuple(torch.empty(n_mine * targets, dtype=torch.int32, device=dev) for _ in range(3))
+                    outs = pipe.scratch_i32("windows", n_mine * targets, count=3)
                     _native.pair_windows_device(
                         self._device, it["stbin"], it["center"], self.CC.mindist, self.CC.maxdist, it["nctrl"],
                         it["per_offset"], dbin, it["nb"], W, it["key1"], it["key2"], edges, it["band_weight"],
@@ -963,7 +966,7 @@ class PileUpper:
                 target = acc
                 if exact:
                     target = region_acc[it["name"]] = _native.alloc_accumulator(n_slots * stride, self._device)
-                pipe.submit(self._region_kwargs(it["name"], flags), None, target, windows_on_device=generate)
+                readies.append(pipe.submit(self._region_kwargs(it["name"], flags), None, target, windows_on_device=generate))
             pipe.finish()
             s_rng.synchronize()
             if rng is not None:

@@ -1363,11 +1363,11 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_shifts(pup_rng_state* st, con
       int total;
       const int incl = mt_block_scan(acc, warp_sums, &total);
       const int64_t need = n - got;
-      if ((int64_t)total <= need) {
+      if ((int64_t)total < need) {  // every word of the block is consumed (trailing rejects too: the draw goes on)
         if (acc && dbin) dbin[outbase + got + incl - 1] = (int32_t)(low + (int64_t)v);
         got += total;
         pos = MT_N;
-      } else {  // the need-th accepted word ends this phase inside the block
+      } else {  // the need-th accepted word ends this phase inside the block; words after it belong to the signs
         if (acc && (int64_t)incl <= need && dbin) dbin[outbase + got + incl - 1] = (int32_t)(low + (int64_t)v);
         if (acc && (int64_t)incl == need) s_cut = t;
         __syncthreads();

@@ -22,6 +22,7 @@ from . import _native
 
 
 _STREAMS = {}
+_SCRATCH = {}  # (device, tag, parity) -> persistent int32 device tensor
 
 
 def device_streams(device):
@@ -49,11 +50,28 @@ class RegionPipeline:
         self.s_prep.wait_stream(self.main)
         self.s_comp.wait_stream(self.main)
         self._pending = None
+        self._submitted = 0
         self._keep = deque()  # (event, python objects whose memory an enqueued copy still reads)
         self.launches = 0
         self.regions = 0
 
     # -- helpers ----------------------------------------------------------------------------------
+    def scratch_i32(self, tag, n, count=1, stream=None):
+        """``count`` int32 device vectors of length ``n`` for the region being submitted, carved out of a persistent
+        buffer per (tag, region parity).  Region k's buffers are reused by region k + 2, whose prepare-stream work is
+        ordered after region k's pile-up (the ``wait_event(done)`` of :meth:`_compute`), so no allocator round trip
+        and no ``record_stream`` bookkeeping is needed per region."""
+        torch = self.torch
+        key = (self.device, tag, self._submitted & 1)
+        n = int(n)
+        step = (n + 63) // 64 * 64
+        buf = _SCRATCH.get(key)
+        if buf is None or buf.numel() < count * step:
+            with torch.cuda.stream(stream or self.s_prep):
+                buf = torch.empty(max(count * step, 1024) * 5 // 4, dtype=torch.int32, device=self.dev)
+            _SCRATCH[key] = buf
+        return tuple(buf[i * step : i * step + n] for i in range(count))
+
     def _reap(self, everything=False):
         while self._keep and (everything or self._keep[0][0].query()):
             self._keep.popleft()
@@ -61,17 +79,14 @@ class RegionPipeline:
     def upload_windows(self, arrays):
         """Host int32 arrays -> device tensors through the library's upload FIFO (ordered with the matrix copies)."""
         torch = self.torch
-        out = []
+        arrays = [np.ascontiguousarray(a, dtype=np.int32) for a in arrays]
+        out = self.scratch_i32("windows", arrays[0].shape[0], count=len(arrays))
         with torch.cuda.stream(self.s_prep):
-            for a in arrays:
-                a = np.ascontiguousarray(a, dtype=np.int32)
-                d = torch.empty(a.shape[0], dtype=torch.int32, device=self.dev)
-                d.record_stream(self.s_comp)
+            for a, d in zip(arrays, out):
                 if a.shape[0]:
                     _native.upload(self.device, d, a, stream=self.s_prep.cuda_stream)
-                out.append(d)
                 self._hold.append(a)
-        return tuple(out)
+        return out
 
     # -- the pipeline -----------------------------------------------------------------------------
     def submit(self, region_kwargs, windows, acc, after=None, windows_on_device=None):
@@ -101,14 +116,14 @@ class RegionPipeline:
                 wins = self.upload_windows(windows)
             else:
                 wins = windows_on_device(self.s_prep)
-                for t in wins:
-                    t.record_stream(self.s_comp)
             ready = self.s_prep.record_event()
         self._keep.append((ready, self._hold))
         self._hold = []
+        self._submitted += 1
         prev, self._pending = self._pending, (region, wins, ready, acc, after)
         if prev is not None:
             self._compute(prev)
+        return ready
 
     def _compute(self, item):
         region, wins, ready, acc, after = item

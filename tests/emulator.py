@@ -219,6 +219,7 @@ class SerialPipeline:
         if after is not None:
             after(region, 0)
         self.regions += 1
+        return None
 
     def finish(self):
         pass

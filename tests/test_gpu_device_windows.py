@@ -57,6 +57,34 @@ def test_control_shifts_replay_numpy_stream(seed, burn):
     assert np.array_equal(np.random.random(5), tail_host)
 
 
+def test_control_shifts_many_small_segments():
+    """Thousands of short segments: every alignment of a segment's end with the 624-word MT19937 blocks occurs,
+    including a segment whose last accepted word is followed by rejected words inside the same block (those words
+    belong to the sign draws -- a round-2 bug let them vanish)."""
+    nat = _cuda()
+    import torch
+
+    from coolpuppy_b200._coords import _draw_shifts
+
+    rs = np.random.RandomState(5)
+    segs = rs.randint(1, 700, 4000).astype(np.int64)
+    np.random.seed(11)
+    state0 = np.random.get_state()
+    want = np.concatenate([_draw_shifts(int(n), 100_000, 1_000_000, 10_000) for n in segs])
+    tail_host = np.random.random(4)
+    np.random.set_state(state0)
+    rng = nat.DeviceRng(0)
+    dbin = torch.empty(int(segs.sum()), dtype=torch.int32, device="cuda:0")
+    rng.control_shifts(segs, 100_000, 1_000_000, 10_000, dbin)
+    torch.cuda.synchronize()
+    got = dbin.cpu().numpy().astype(np.int64)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (len(bad), bad[:10])
+    rng.store()
+    rng.close()
+    assert np.array_equal(np.random.random(4), tail_host)
+
+
 def test_control_shifts_other_ranges():
     nat = _cuda()
     import torch
@@ -200,3 +228,52 @@ def test_golden_cases_on_both_window_paths(monkeypatch, name, device_windows):
             warnings.simplefilter("ignore")
             cp.pileup(clr, feats, **kw)
         assert np.array_equal(np.random.random(3), after)
+
+
+def test_device_windows_at_bench_scale():
+    """The whole configs[3] genome (6.4 k sites, 1.1e7 windows, 24 chromosomes, up to 510 sites per chromosome --
+    several thread tiles per pair offset, thousands of MT19937 segments): device windows == host windows."""
+    nat = _cuda()
+    import torch
+
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.coolio import ChromCooler
+    from coolpuppy_b200.synthetic import HG38, synthetic_sites
+
+    sizes = dict(HG38)
+    sites, n_pairs = synthetic_sites(1_000_000, chromsizes=sizes, binsize=10_000, flank=410_000, seed=1237)
+    nbins = sum(-(-L // 10_000) for L in sizes.values())
+    clr = ChromCooler(sizes, 10_000, {}, {"weight": np.ones(nbins)})
+    np.random.seed(0)
+    cc = cp.CoordCreator(sites, 10_000, features_format="bed", flank=410_000, nshifts=10, mindist="auto", seed=0)
+    pu = cp.PileUpper(clr, cc, clr_weight_name="weight", control=True)
+    plan = pu._plan([], False, None, None)
+    plan["band_edges"] = None
+    state0 = np.random.get_state()
+    host = pu._prepare(plan, None, None)
+    state_host = np.random.get_state()
+    np.random.set_state(state0)
+    job = pu._prepare_device(plan, None, None)
+    dev = torch.device("cuda", 0)
+    rng = nat.DeviceRng(0)
+    by_name = {b["name"]: b for b in host["built"]}
+    for it in job["items"]:
+        dbin = None
+        if len(it["segs"]):
+            dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)
+            rng.control_shifts(it["segs"], pu.CC.minshift, pu.CC.maxshift, pu.resolution, dbin)
+        if not it["owned"]:
+            continue
+        b = by_name[it["name"]]
+        n_all = int(it["total"]) * (1 + it["nctrl"])
+        outs = tuple(torch.full((n_all,), -7, dtype=torch.int32, device=dev) for _ in range(3))
+        nat.pair_windows_device(0, it["stbin"], it["center"], pu.CC.mindist, pu.CC.maxdist, it["nctrl"], it["per_offset"], dbin,
+                                it["nb"], job["W"], None, None, None, 0, 0, False, None, None, job["nk"], job["nf"], 0, 1,
+                                it["index"], outs[0], outs[1], outs[2])
+        torch.cuda.synchronize()
+        for got, want in zip(outs, (b["w_r0"], b["w_c0"], b["slot"])):
+            assert np.array_equal(got.cpu().numpy().astype(np.int64), np.asarray(want).astype(np.int64)), it["name"]
+    rng.store()
+    rng.close()
+    st = np.random.get_state()
+    assert st[2] == state_host[2] and np.array_equal(st[1], state_host[1])
