@@ -13,7 +13,7 @@ balanced with 3 % NaN bins):
 A step = one pass of the hot path over every window of every chromosome:
   value   : region matrices and window arrays resident in HBM; per sharding unit pup_accumulate() = device sort of the
             windows + count kernels + main pile-up kernel; N > 1: chromosomes sharded over ranks by LPT on their exact
-            algorithmic bytes, heavy chromosomes cut into strided window parts (matrix replicated), one NCCL
+            algorithmic bytes, heavy chromosomes cut into row-band window parts (matrix replicated), one NCCL
             all-reduce of the accumulators inside the timed region.
   e2e     : the same pass through the product's two-stream region pipeline (coolpuppy_b200.pipeline) with HOST (pinned)
             buffers: pup_region_create_upper() + pup_upload() + pup_accumulate() per chromosome, i.e. including the
@@ -313,11 +313,11 @@ def host_cooler(sizes, host_data, pin):
                         for k in ("upper_indptr", "upper_col", "upper_count")) for c, h in host_data.items()}
     nb = {c: -(-L // BINSIZE) for c, L in sizes.items()}
     weight = np.concatenate([(host_data[c]["weight"].numpy() if c in host_data else np.full(nb[c], np.nan)) for c in sizes])
-    clr = ChromCooler(sizes, BINSIZE, regions, {"weight": weight}, filename="synthetic_3Gbp_10kb.cool", pin=False)
+    clr = ChromCooler(sizes, BINSIZE, regions, {"weight": weight}, filename="synthetic_3Gbp_10kb.cool", pin=pin)
     return clr
 
 
-def build_windows(args, sizes, features, expected_df):
+def build_windows(args, sizes, features, expected_df, nnz_by_chrom=None):
     """Host side of the path through the product's own builder (PileUpper._prepare): per-chromosome window arrays
     (reference emission order, seeded control shifts) with their dense accumulator slots."""
     from functools import partial
@@ -329,6 +329,9 @@ def build_windows(args, sizes, features, expected_df):
     kw = wl["kwargs"]
     nbins = sum(-(-L // BINSIZE) for L in sizes.values())
     clr = ChromCooler(sizes, BINSIZE, {}, {"weight": np.ones(nbins)}, filename="synthetic_3Gbp_10kb.cool")
+    if nnz_by_chrom:  # stored pixels per chromosome: the density scale of the product's sharding cost model
+        edges = np.concatenate([[0.0], np.cumsum([float(nnz_by_chrom[c]) for c in sizes])])
+        clr._bin1_offset = np.interp(np.arange(nbins + 1), clr._chrom_offset, edges).astype(np.int64)
     np.random.seed(0)
     cc = cp.CoordCreator(features, BINSIZE, features_format=kw["features_format"], flank=wl["flank"], nshifts=wl["nshifts"],
                          mindist="auto", seed=0 if wl["nshifts"] else None)
@@ -343,12 +346,13 @@ def build_windows(args, sizes, features, expected_df):
     plan = pu._plan(groupby, False, modify, None)
     plan["band_edges"] = pu._band_edges(plan)
     job = pu._prepare(plan, None, None)
-    out = {c: dict(nb=-(-L // BINSIZE), r0=np.zeros(0, np.int32), c0=np.zeros(0, np.int32), slot=np.zeros(0, np.int32), n_roi=0)
-           for c, L in sizes.items()}
+    out = {c: dict(nb=-(-L // BINSIZE), r0=np.zeros(0, np.int32), c0=np.zeros(0, np.int32), slot=np.zeros(0, np.int32), n_roi=0,
+                   anchor=np.zeros(0, np.int64)) for c, L in sizes.items()}
     for b in job["built"]:
         out[b["name"]].update(r0=b["w_r0"].astype(np.int32), c0=b["w_c0"].astype(np.int32), slot=b["slot"].astype(np.int32),
-                              n_roi=int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))))
-    return out, job["n_slots"], job["flags"]
+                              n_roi=int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))),
+                              anchor=np.repeat(np.asarray(b["rw"].idx1), b["targets"]))
+    return out, job["n_slots"], job["flags"], pu
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -363,7 +367,7 @@ def main():
     import torch
 
     from coolpuppy_b200 import _native
-    from coolpuppy_b200.multigpu import lpt_assign, part_index, split_heavy
+    from coolpuppy_b200.multigpu import lpt_assign, split_heavy
 
     _native.require_device()
     torch.cuda.set_device(local_rank)
@@ -385,7 +389,8 @@ def main():
                                           pin=world == 1)
     expected_df = expected_table(dev_data) if wl["expected"] else None
     t_host0 = time.perf_counter()
-    windows, n_slots, flags = build_windows(args, sizes, features, expected_df)
+    nnz_by_chrom = {c: int(dev_data[c]["upper_col"].shape[0]) for c in names}
+    windows, n_slots, flags, pu_plan = build_windows(args, sizes, features, expected_df, nnz_by_chrom)
     host_window_s = time.perf_counter() - t_host0
     n_windows_total = sum(len(w["r0"]) for w in windows.values())
     n_roi_total = sum(w["n_roi"] for w in windows.values())
@@ -420,7 +425,13 @@ def main():
     alg_bytes = 0
     for c, part, parts in my_units:
         w = windows[c]
-        sel = part_index(len(w["r0"]), part, parts)
+        if parts == 1:
+            sel = np.arange(len(w["r0"]))
+        else:  # the product's row-band parts: windows whose row anchor lies in the part's feature range
+            mask = np.zeros(len(w["r0"]), dtype=bool)
+            for k_lo, k_hi in pu_plan._part_ranges(c, [part], parts):
+                mask |= (w["anchor"] >= k_lo) & (w["anchor"] < k_hi)
+            sel = np.nonzero(mask)[0]
         dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][sel])).to(dev) for k in ("r0", "c0", "slot"))
         if parts == 1:
             alg_bytes += cost[names.index(c)]
@@ -438,7 +449,7 @@ def main():
         "chromosomes": len(names), "binsize": BINSIZE, "flank": wl["flank"], "accumulator_slots": int(n_slots),
         "l2": "inputs (region matrices, GBs) exceed the 126 MB L2; no flush between iterations",
         "parallelism": (f"chromosomes sharded over {world} GPU(s) by LPT on exact algorithmic bytes; chromosomes above a quarter "
-                        "of a rank's share are cut into strided window parts (matrix replicated); one all-reduce of the "
+                        "of a rank's share are cut into row-band window parts (matrix replicated); one all-reduce of the "
                         "accumulators; e2e: whole chromosomes per GPU"),
     }
 
@@ -523,6 +534,9 @@ def main():
         from coolpuppy_b200.pipeline import RegionPipeline
 
         hacc = torch.zeros(n_slots * stride, dtype=torch.float64).pin_memory()
+        if world > 1:  # this rank's chromosomes into pinned memory (N = 1: the whole genome already is)
+            for c in mine:
+                host_data[c] = {k: (v.pin_memory() if hasattr(v, "pin_memory") else v) for k, v in host_data[c].items()}
         hwin = {c: tuple(torch.from_numpy(windows[c][k]).pin_memory() for k in ("r0", "c0", "slot")) for c in mine}
         hk = ("upper_indptr", "upper_col", "upper_count", "weight") + (("expected",) if wl["expected"] else ())
         h2d = sum(sum(host_data[c][k].numel() * host_data[c][k].element_size() for k in hk) for c in mine)
@@ -575,7 +589,9 @@ def main():
         from coolpuppy_b200 import coolpup as cp
         from coolpuppy_b200.multigpu import RegionSharder
 
-        clr = host_cooler(sizes, host_data, pin=False)  # views of the (pinned, when N = 1) host arrays
+        # N = 1: views of the pinned host arrays; N > 1: every rank pins the chromosomes it reads on first use (the
+        # untimed first call), not the whole genome
+        clr = host_cooler(sizes, host_data, pin=False if world == 1 else "lazy")
         sharder = RegionSharder() if dist is not None else None
         kw = dict(wl["kwargs"], flank=wl["flank"], clr_weight_name="weight", device=local_rank, dist=sharder)
         if wl["expected"]:

@@ -24,7 +24,7 @@ SYMBOLS = [
     "pup_region_destroy", "pup_upload", "pup_expected_cis", "pup_pair_windows_count", "pup_pair_windows_fill",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
-    "pup_rng_create", "pup_rng_read", "pup_rng_destroy", "pup_control_shifts", "pup_pair_windows_device",
+    "pup_pair_windows_count_range", "pup_rng_create", "pup_rng_read", "pup_rng_destroy", "pup_control_shifts", "pup_pair_windows_device",
 ]
 
 
@@ -54,6 +54,8 @@ def lib():
     L.pup_expected_cis.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.pup_pair_windows_count.argtypes = [i32, vp, C.c_double, C.c_double, vp]
     L.pup_pair_windows_count.restype = i64
+    L.pup_pair_windows_count_range.argtypes = [i32, vp, C.c_double, C.c_double, i32, i32, vp]
+    L.pup_pair_windows_count_range.restype = i64
     L.pup_pair_windows_fill.argtypes = [i32, vp, vp, C.c_double, C.c_double, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pup_region_device_bytes.argtypes = [vp]
     L.pup_region_device_bytes.restype = i64
@@ -70,7 +72,7 @@ def lib():
     L.pup_rng_destroy.argtypes = [vp]
     L.pup_control_shifts.argtypes = [vp, i64, vp, i64, i64, C.c_double, vp, vp]
     L.pup_pair_windows_device.argtypes = [C.c_int, i32, vp, vp, C.c_double, C.c_double, i32, vp, vp, i32, C.c_int, vp,
-                                          vp, vp, i32, i64, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, i32, i32, i32,
+                                          vp, vp, i32, i64, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, i32, i32, vp, i32,
                                           vp, vp, vp, vp, vp, vp]
     L.pup_timing_enable.argtypes = [C.c_int]
     L.pup_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
@@ -225,11 +227,14 @@ def upload(device, dst, src, stream=0):
     check(lib().pup_upload(device, ptr(dst), ptr(src), int(nbytes), stream))
 
 
-def pair_windows_count(center, mindist, maxdist):
-    """``pup_pair_windows_count`` (host code): kept all-vs-all pairs per offset, int64[m]."""
+def pair_windows_count(center, mindist, maxdist, k_lo=0, k_hi=None):
+    """``pup_pair_windows_count[_range]`` (host code): kept all-vs-all pairs per offset, int64[m] (only the pairs
+    whose first feature lies in ``[k_lo, k_hi)`` when given)."""
     center = np.ascontiguousarray(center, dtype=np.float64)
     q = np.zeros(max(1, center.shape[0]), dtype=np.int64)
-    total = lib().pup_pair_windows_count(int(center.shape[0]), ptr(center), float(mindist), float(maxdist), ptr(q))
+    m = int(center.shape[0])
+    total = lib().pup_pair_windows_count_range(m, ptr(center), float(mindist), float(maxdist), int(k_lo),
+                                               m if k_hi is None else int(k_hi), ptr(q))
     if total < 0:
         raise NativeError(f"libpileup_b200: {lib().pup_last_error().decode()}")
     return q[: center.shape[0]], int(total)
@@ -295,19 +300,19 @@ class DeviceRng:
 
 
 def pair_windows_device(device, stbin, center, mindist, maxdist, nctrl, per_offset, dbin, nb, W, key1, key2, band_edges,
-                        band_weight, flip_mode, swap_on_flip, flipval, ident, nk, nf, part, parts, region_index, r0, c0,
-                        slot, first_seen=None, n_roi=None, stream=0):
+                        band_weight, flip_mode, swap_on_flip, flipval, ident, nk, nf, k_lo, k_hi, per_offset_part,
+                        region_index, r0, c0, slot, first_seen=None, n_roi=None, stream=0):
     """``pup_pair_windows_device``: all-vs-all windows + slots of one region written into the device tensors
     ``r0 / c0 / slot`` in the reference's emission order."""
     m = int(center.shape[0])
-    if int(r0.shape[0]) == 0:  # this strided share holds no window
+    if int(r0.shape[0]) == 0:  # this part holds no window
         return
     check(lib().pup_pair_windows_device(
         int(device), m, ptr(stbin, np.int32), ptr(center, np.float64), float(mindist), float(maxdist),
         int(nctrl), ptr(per_offset, np.int64), ptr(dbin), int(nb), int(W), ptr(key1), ptr(key2), ptr(band_edges),
         0 if band_edges is None else int(band_edges.shape[0]), int(band_weight), int(flip_mode), int(bool(swap_on_flip)),
-        ptr(flipval), ptr(ident), int(nk), int(nf), int(part), int(parts), int(region_index), ptr(r0), ptr(c0),
-        ptr(slot), ptr(first_seen), ptr(n_roi), stream))
+        ptr(flipval), ptr(ident), int(nk), int(nf), int(k_lo), int(k_hi), ptr(per_offset_part, np.int64),
+        int(region_index), ptr(r0), ptr(c0), ptr(slot), ptr(first_seen), ptr(n_roi), stream))
 
 
 def expected_cis_sums(device, nb, indptr_upper, col_upper, count_upper, weight=None, stream=0):

@@ -360,13 +360,16 @@ class MemCooler(_CoolerBase):
 class ChromCooler(_CoolerBase):
     """In-memory cooler that keeps every chromosome's cis pixels as the region-relative upper-triangle CSR the CUDA
     path consumes (``int32 indptr[nb+1], col[nnz], count[nnz]``), so that ``region_upper_csr`` of a whole-chromosome
-    view is a zero-copy lookup -- with the arrays in pinned memory (``pin=True``) the host->device copies of the region
-    pipeline are truly asynchronous.  Trans pixels are not represented.  Sub-chromosome views and the cooler-style
+    view is a zero-copy lookup -- with the arrays in pinned memory (``pin=True``, or ``pin="lazy"``: a chromosome is
+    pinned the first time it is read) the host->device copies of the region pipeline are truly asynchronous.  Trans pixels are not represented.  Sub-chromosome views and the cooler-style
     ``matrix().fetch`` work too (they build global pixel ids on demand).
     """
 
     def __init__(self, chromsizes, binsize, regions, bin_columns=None, filename="<memory>.cool", pin=False):
         self.filename = filename
+        self._lazy_pin = pin == "lazy"
+        self._pinned = set()
+        pin = pin is True
         self.binsize = int(binsize)
         if isinstance(chromsizes, dict):
             chromsizes = pd.Series(chromsizes)
@@ -431,8 +434,17 @@ class ChromCooler(_CoolerBase):
     def region_upper_csr(self, lo, hi):
         ci = self._chrom_of(lo, hi)
         off = int(self._chrom_offset[ci])
-        ip, col, cnt = self._regions[self.chromnames[ci]]
+        name = self.chromnames[ci]
+        ip, col, cnt = self._regions[name]
         if lo == off and hi == int(self._chrom_offset[ci + 1]):
+            if self._lazy_pin and name not in self._pinned:
+                # pin on first use: a rank of a multi-GPU job only pays for the chromosomes it actually reads
+                import torch
+
+                ts = [torch.from_numpy(a).pin_memory() for a in (ip, col, cnt)]
+                self._keep.extend(ts)
+                ip, col, cnt = self._regions[name] = tuple(t.numpy() for t in ts)
+                self._pinned.add(name)
             return ip, col, cnt  # the stored arrays themselves
         a, b = lo - off, hi - off
         p0, p1 = int(ip[a]), int(ip[b])

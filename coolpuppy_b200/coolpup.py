@@ -500,6 +500,7 @@ class PileUpper:
         if self.coverage_norm and self.clr_weight_name:
             raise ValueError("Can't do coverage normalization when clr_weight_name is provided")
         self.empty_outmap = self.make_outmap()
+        self._cost_cache = {}
 
     # -- small reference-compatible helpers -------------------------------------------------------
     def make_outmap(self):
@@ -630,10 +631,14 @@ class PileUpper:
         lo, hi = self.clr.extent((r["chrom"], r["start"], r["end"]))
         return int(off[hi] - off[lo])
 
-    def _region_cost(self, name):
-        """Predicted algorithmic bytes of a view region (per window 16 + 4(W+1) [+16W balanced] + 8 per
-        stored pixel), for the LPT sharding.  Stored pixels per window are modelled as W^2 * min(1, A / separation)
-        with A fitted to the region's pixel count (contact density falls like 1 / separation)."""
+    def _feature_costs(self, name):
+        """Predicted algorithmic bytes (per window 16 + 4(W+1) [+16W balanced] + 8 per stored pixel) of the
+        windows anchored at every feature of a view region, in the order of the region's feature table: for bed pairs
+        the pairs (k, l > k) count for their row anchor k.  Stored pixels per window are modelled as
+        W^2 * min(1, A / separation) with A fitted to the region's pixel count (contact density ~ 1 / separation).
+        The sum is the region's cost for the LPT sharding; its running sum gives the cut points of window parts."""
+        if name in self._cost_cache:
+            return self._cost_cache[name]
         r = self.view_df.loc[name]
         df = self.CC.intervals
         W = 2 * self.pad_bins + 1
@@ -643,24 +648,75 @@ class PileUpper:
         A = 1.0 if nnz is None else max(1e-3, nnz / (nb * max(1.0, np.log(nb) - 1.0)))
         fixed = 16 + 4 * (W + 1) + (16 * W if self.clr_weight_name else 0)
         reps = 1 + (self.CC.nshifts if self.control else 0)
+        res = float(self.resolution)
 
         def cost_of(sep_bins):
-            px = W * W * np.minimum(1.0, A / np.maximum(np.abs(sep_bins), 1.0))
-            return float(np.sum(fixed + 8.0 * px)) * reps
+            return (fixed + 8.0 * W * W * np.minimum(1.0, A / np.maximum(np.abs(sep_bins), 1.0))) * reps
 
         if self.CC.kind == "bedpe":
-            m = ((df["chrom1"].values == r["chrom"]) & (df["start1"].values >= r["start"]) & (df["end1"].values < r["end"]))
-            return cost_of(df["distance"].values[m] / self.resolution)
-        m = (df["chrom"].values == r["chrom"]) & (df["start"].values >= r["start"]) & (df["end"].values < r["end"])
-        c = np.sort(df["center"].values[m]) / self.resolution
-        if self.local:
-            return cost_of(np.zeros(len(c)))
-        if len(c) > 3000:  # quadratic: sample the sites, scale to all pairs
-            sub = c[:: len(c) // 1500]
-            d = (sub[None, :] - sub[:, None])[np.triu_indices(len(sub), 1)]
-            return cost_of(d[np.abs(d) * self.resolution >= self.mindist]) * (len(c) / len(sub)) ** 2
-        d = (c[None, :] - c[:, None])[np.triu_indices(len(c), 1)]
-        return cost_of(d[(np.abs(d) * self.resolution >= self.mindist) & (np.abs(d) * self.resolution <= self.maxdist)])
+            m = ((df["chrom1"].values == r["chrom"]) & (df["chrom2"].values == r["chrom"])
+                 & (df["start1"].values >= r["start"]) & (df["end1"].values < r["end"])
+                 & (df["start2"].values >= r["start"]) & (df["end2"].values < r["end"]))
+            out = cost_of(df["distance"].values[m] / res)
+        else:
+            m = (df["chrom"].values == r["chrom"]) & (df["start"].values >= r["start"]) & (df["end"].values < r["end"])
+            c = df["center"].values[m] / res
+            n = len(c)
+            if self.local:
+                out = cost_of(np.zeros(n))
+            else:
+                out = np.zeros(n)
+                lo_d, hi_d = self.mindist / res, self.maxdist / res
+                step = max(1, n // 2000)  # quadratic in the sites: evaluate every step-th anchor, interpolate
+                ks = np.arange(0, n, step)
+                for a in range(0, len(ks), 256):
+                    kk = ks[a : a + 256]
+                    d = np.abs(c[None, :] - c[kk, None])
+                    keep = (np.arange(n)[None, :] > kk[:, None]) & (d >= lo_d) & (d <= hi_d)
+                    out[kk] = np.where(keep, cost_of(d), 0.0).sum(axis=1)
+                if step > 1:
+                    out = np.interp(np.arange(n), ks, out[ks])
+        self._cost_cache[name] = np.asarray(out, dtype=np.float64)
+        return self._cost_cache[name]
+
+    def _region_cost(self, name):
+        return float(self._feature_costs(name).sum())
+
+    def _part_ranges(self, name, my_parts, parts):
+        """Feature-index ranges ``[(k_lo, k_hi)]`` (merged when adjacent) of window parts ``my_parts`` out of ``parts``:
+        the region's features are cut at equal predicted cost.  A part holds the windows whose ROW anchor lies in its
+        range (controls stay with their ROI pair), i.e. a band of matrix rows -- every rank streams only its band
+        from HBM, unlike a strided split whose parts each read the whole matrix."""
+        cost = self._feature_costs(name)
+        n = len(cost)
+        if parts <= 1 or n == 0:
+            return [(0, n)]
+        cum = np.concatenate([[0.0], np.cumsum(cost)])
+        cuts = np.searchsorted(cum, cum[-1] * np.arange(1, parts) / parts, side="left")
+        cuts = np.concatenate([[0], np.clip(cuts, 0, n), [n]])
+        cuts = np.maximum.accumulate(cuts)
+        ranges = []
+        for p_ in sorted(my_parts):
+            a, b = int(cuts[p_]), int(cuts[p_ + 1])
+            if b <= a:
+                continue
+            if ranges and ranges[-1][1] == a:
+                ranges[-1] = (ranges[-1][0], b)
+            else:
+                ranges.append((a, b))
+        return ranges
+
+    def _my_units(self, region_names, dist, splittable=True):
+        """{region: [feature-index ranges]} of this rank + the predicted max / mean load over the ranks."""
+        self._cost_cache = {}
+        if dist is None or dist.world_size == 1:
+            return {name: None for name in region_names}, 1.0
+        costs = [self._region_cost(n) for n in region_names]
+        units, imbalance = dist.my_units(region_names, costs, max_share=0.25 if splittable else 1e9)
+        mine = {}
+        for name, part, parts in units:
+            mine.setdefault(name, (set(), parts))[0].add(part)
+        return {name: (None if parts == 1 else self._part_ranges(name, ps, parts)) for name, (ps, parts) in mine.items()}, imbalance
 
     def _needs_exact_merge(self):
         """True when a pixel can become +inf (x / 0 with ooe): the reference's region / group merge then turns it
@@ -679,13 +735,7 @@ class PileUpper:
         do_control = bool(self.control)
         expctrl = bool(self.expected is True and not self.ooe)
         splittable = not (self.store_stripes or (modify_2Dintervals_func is not None and plan["band_edges"] is None))
-        imbalance = 1.0
-        if dist is None or dist.world_size == 1:
-            my_units = {name: (0, 1) for name in region_names}
-        else:
-            costs = [self._region_cost(n) for n in region_names]
-            units, imbalance = dist.my_units(region_names, costs, max_share=0.25 if splittable else 1e9)
-            my_units = {name: (part, parts) for name, part, parts in units}
+        my_units, imbalance = self._my_units(region_names, dist, splittable)
         built = []
         for ri, name in enumerate(region_names):
             r = self.view_df.loc[name]
@@ -699,19 +749,22 @@ class PileUpper:
             rw = self.CC.region_windows(region, control=do_control)
             if len(rw) == 0:
                 continue
-            part, parts = my_units[name]
             pos0 = np.arange(len(rw), dtype=np.int64)
-            if parts > 1:  # my strided share of the region's windows (matrix replicated on the other owners)
-                pos0 = pos0[part::parts]
+            if my_units[name] is not None:  # my row bands of the region's windows (matrix replicated on the other owners)
+                mask = np.zeros(len(rw), dtype=bool)
+                for k_lo, k_hi in my_units[name]:
+                    mask |= (rw.idx1 >= k_lo) & (rw.idx1 < k_hi)
+                pos0 = pos0[mask]
                 rw = rw.take(pos0)
+                if len(rw) == 0:
+                    continue
             flipf, cols = self._region_group_codes(rw, plan, table)
             lo_rel, hi_rel = self.view_df_extents[name]
             nb = hi_rel - lo_rel
             r0 = rw.st1 - lo_rel
             c0 = rw.st2 - lo_rel
             valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
-            built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, cols=cols, pos0=pos0,
-                              part=part, parts=parts))
+            built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, cols=cols, pos0=pos0))
         # dense group keys: mixed radix over the group columns (identical on every rank), or the feature id (by-window)
         table.finalize(dist)
         if plan["by_window"]:
@@ -831,13 +884,7 @@ class PileUpper:
         region_names = list(self.view_df.index) if regions is None else list(regions)
         do_control = bool(self.control) and self.CC.nshifts > 0
         expctrl = bool(self.expected is True and not self.ooe)
-        imbalance = 1.0
-        if dist is None or dist.world_size == 1:
-            my_units = {name: (0, 1) for name in region_names}
-        else:
-            costs = [self._region_cost(n) for n in region_names]
-            units, imbalance = dist.my_units(region_names, costs, max_share=0.25)
-            my_units = {name: (part, parts) for name, part, parts in units}
+        my_units, imbalance = self._my_units(region_names, dist)
         # dense key space (static columns only on this path)
         if plan["by_window"]:
             self._feature_ident(None)
@@ -873,8 +920,7 @@ class PileUpper:
                       owned=name in my_units and total > 0)
             if it["owned"]:
                 lo_rel, hi_rel = self.view_df_extents[name]
-                part, parts = my_units[name]
-                it.update(nb=hi_rel - lo_rel, part=part, parts=parts, center=center, per_offset=q,
+                it.update(nb=hi_rel - lo_rel, ranges=my_units[name] or [(0, len(center))], center=center, per_offset=q,
                           stbin=np.ascontiguousarray(sel["stBin"].values - lo_rel, dtype=np.int32),
                           key1=None, key2=None, flipval=None, ident=None, band_weight=0)
                 if plan["by_window"]:
@@ -947,20 +993,35 @@ class PileUpper:
                 if not it["owned"]:
                     continue
                 targets = 2 if it["ident"] is not None else 1
-                n_all = int(it["total"]) * (1 + it["nctrl"])
-                n_mine = (n_all - it["part"] + it["parts"] - 1) // it["parts"]
+                # kept pairs per offset inside each of my row bands (anchor k in [k_lo, k_hi))
+                bands = []
+                for k_lo, k_hi in it["ranges"]:
+                    if (k_lo, k_hi) == (0, len(it["center"])):
+                        q_part = it["per_offset"]
+                    else:
+                        q_part, _ = _native.pair_windows_count(it["center"], self.CC.mindist, self.CC.maxdist, k_lo, k_hi)
+                    bands.append((k_lo, k_hi, q_part, int(q_part.sum()) * (1 + it["nctrl"])))
+                n_mine = sum(b[3] for b in bands)
+                if n_mine == 0:
+                    continue
 
-                def generate(stream, it=it, dbin=dbin, shifts_ready=shifts_ready, n_mine=n_mine, targets=targets):
+                def generate(stream, it=it, dbin=dbin, shifts_ready=shifts_ready, n_mine=n_mine, targets=targets, bands=bands):
                     if shifts_ready is not None:
                         stream.wait_event(shifts_ready)
                     outs = pipe.scratch_i32("windows", n_mine * targets, count=3)
-                    _native.pair_windows_device(
-                        self._device, it["stbin"], it["center"], self.CC.mindist, self.CC.maxdist, it["nctrl"],
-                        it["per_offset"], dbin, it["nb"], W, it["key1"], it["key2"], edges, it["band_weight"],
-                        0 if it["flipval"] is None else (1 if self.flip_negative_strand else 2),
-                        bool(plan["flip"] and plan["ignore_group_order"]), it["flipval"], it["ident"], job["nk"], job["nf"],
-                        it["part"], it["parts"], it["index"], outs[0], outs[1], outs[2], first_seen=first,
-                        n_roi=n_roi[it["index"] : it["index"] + 1], stream=stream.cuda_stream)
+                    at = 0
+                    for k_lo, k_hi, q_part, n_band in bands:
+                        if n_band == 0:
+                            continue
+                        sub = tuple(o[at * targets : (at + n_band) * targets] for o in outs)
+                        _native.pair_windows_device(
+                            self._device, it["stbin"], it["center"], self.CC.mindist, self.CC.maxdist, it["nctrl"],
+                            it["per_offset"], dbin, it["nb"], W, it["key1"], it["key2"], edges, it["band_weight"],
+                            0 if it["flipval"] is None else (1 if self.flip_negative_strand else 2),
+                            bool(plan["flip"] and plan["ignore_group_order"]), it["flipval"], it["ident"], job["nk"],
+                            job["nf"], k_lo, k_hi, q_part, it["index"], sub[0], sub[1], sub[2], first_seen=first,
+                            n_roi=n_roi[it["index"] : it["index"] + 1], stream=stream.cuda_stream)
+                        at += n_band
                     return outs
 
                 target = acc

@@ -1404,12 +1404,14 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_shifts(pup_rng_state* st, con
 // get_combinations, coolpup.py:682-714: pairs (k, k + i) by offset i then k, distance-filtered; per offset block the
 // ROI rows, then the nctrl shifted replicas, _control_regions 387-453) together with their accumulator slots.
 struct PairGen {
-  int m, nctrl, W, nb, nk, nf, targets, part, parts, region_index;
+  int m, nctrl, W, nb, nk, nf, targets, k_lo, k_hi, region_index;
   const int32_t* stbin;       // [m] region-relative first bin of every feature's window
   const double* center;       // [m]
   double mindist, maxdist;
   const int64_t* base;        // [m] kept pairs of all smaller offsets (exclusive prefix of per_offset)
   const int64_t* per_offset;  // [m]
+  const int64_t* base_part;   // [m] the same two for the pairs whose row anchor k lies in [k_lo, k_hi) (the part written)
+  const int64_t* per_offset_part;
   const int32_t* dbin;        // control shifts in draw order (k_mt_shifts) or null
   const int64_t* key1;        // [m] group-key part of a feature on side 1 / side 2 (null: 0)
   const int64_t* key2;
@@ -1420,24 +1422,27 @@ struct PairGen {
   int swap_on_flip;           // ignore_group_order: a flipped window swaps the sides of its group key
   const int32_t* flipval;
   const int32_t* ident;       // by-window: feature identity (the window goes to both anchors' groups)
-  int32_t *r0, *c0, *slot;    // outputs, [ceil((n - part) / parts) * targets]
+  int32_t *r0, *c0, *slot;    // outputs, [sum(per_offset_part) * (1 + nctrl) * targets]
   unsigned long long* first;  // [n_keys] atomicMin of (control?, region, emission position) over valid windows; null: off
   unsigned long long* n_roi;  // [1] valid ROI windows (x targets) of this call; null: off
 };
 
 __global__ void __launch_bounds__(256) k_pair_windows(const PairGen p) {
-  __shared__ int warp_sums[8];
-  __shared__ int s_base;
+  __shared__ int warp_sums[2][8];
+  __shared__ int s_base[2];
   const int i = blockIdx.x + 1;  // pair offset
   if (i >= p.m) return;
   const long long q = p.per_offset[i];
-  if (q == 0) return;
-  const long long blk = p.base[i] * (1 + p.nctrl);  // emission index of the block's first row
-  const long long dr0 = p.base[i] * p.nctrl;        // first draw of the block
+  const long long qp = p.per_offset_part[i];
+  if (qp == 0) return;
+  const long long blk = p.base[i] * (1 + p.nctrl);        // emission index of the block's first row
+  const long long dr0 = p.base[i] * p.nctrl;              // first draw of the block
+  const long long oblk = p.base_part[i] * (1 + p.nctrl);  // output index of the part's first row of this block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_base = 0;
+  if (threadIdx.x < 2) s_base[threadIdx.x] = 0;
   __syncthreads();
-  for (int k0 = 0; k0 + i < p.m; k0 += blockDim.x) {
+  const int k_end = min(p.k_hi, p.m - i);  // anchors beyond the part contribute nothing (ranks only look backwards)
+  for (int k0 = 0; k0 < k_end; k0 += blockDim.x) {
     const int k = k0 + threadIdx.x, l = k + i;
     bool keep = false;
     double dist = 0.0;
@@ -1446,22 +1451,35 @@ __global__ void __launch_bounds__(256) k_pair_windows(const PairGen p) {
       const double ad = fabs(dist);
       keep = p.mindist <= ad && ad <= p.maxdist;
     }
-    // rank of this pair among the kept pairs of the offset
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    int x = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_sums[warp] = __popc(bal);
-    __syncthreads();
-    int before = s_base;
-    for (int w = 0; w < warp; ++w) before += warp_sums[w];
-    const long long j = before + x;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w = 0; w < 8; ++w) tot += warp_sums[w];
-      s_base += tot;
+    const bool mine = keep && k >= p.k_lo && k < p.k_hi;
+    // rank of this pair among the kept pairs of the offset (all anchors: emission position and draw index) and
+    // among the kept pairs of the part (output index)
+    const unsigned bal = __ballot_sync(0xffffffffu, keep), balp = __ballot_sync(0xffffffffu, mine);
+    const unsigned below = (1u << lane) - 1u;
+    if (lane == 0) {
+      warp_sums[0][warp] = __popc(bal);
+      warp_sums[1][warp] = __popc(balp);
     }
     __syncthreads();
-    if (!keep) continue;
+    int before = s_base[0], beforep = s_base[1];
+    for (int w = 0; w < warp; ++w) {
+      before += warp_sums[0][w];
+      beforep += warp_sums[1][w];
+    }
+    const long long j = before + __popc(bal & below);
+    const long long jp = beforep + __popc(balp & below);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0, totp = 0;
+      for (int w = 0; w < 8; ++w) {
+        tot += warp_sums[0][w];
+        totp += warp_sums[1][w];
+      }
+      s_base[0] += tot;
+      s_base[1] += totp;
+    }
+    __syncthreads();
+    if (!mine) continue;
     // group key and flip flag are properties of the pair; the controls inherit them (coolpup.py:436-450)
     bool flip = false;
     if (p.flip_mode == 1) flip = p.flipval[k] != 0;
@@ -1485,12 +1503,11 @@ __global__ void __launch_bounds__(256) k_pair_windows(const PairGen p) {
     }
     for (int rep = 0; rep <= p.nctrl; ++rep) {
       const long long pos = blk + (long long)rep * q + j;
-      if (pos % p.parts != p.part) continue;  // another rank's strided share
       const int sh = rep == 0 ? 0 : p.dbin[dr0 + (long long)(rep - 1) * q + j];
       const int a = p.stbin[k] + sh, b = p.stbin[l] + sh;
       const bool valid = a >= 0 && b >= 0 && a + p.W <= p.nb && b + p.W <= p.nb;
       const int kind = rep == 0 ? 0 : 1;
-      const long long o = (pos / p.parts) * p.targets;
+      const long long o = (oblk + (long long)rep * qp + jp) * p.targets;
       for (int tg = 0; tg < p.targets; ++tg) {
         const long long kk = p.ident ? (long long)(tg == 0 ? p.ident[k] : p.ident[l]) : key;
         p.r0[o + tg] = a;
@@ -2394,7 +2411,12 @@ int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* i
 // ------------------------------------------------------------------------------------------ host-side window layout
 // (plain host code: no device involved)
 int64_t pup_pair_windows_count(int32_t m, const double* center, double mindist, double maxdist, int64_t* per_offset) {
-  if (m < 0 || (m > 0 && (!center || !per_offset))) {
+  return pup_pair_windows_count_range(m, center, mindist, maxdist, 0, m, per_offset);
+}
+
+int64_t pup_pair_windows_count_range(int32_t m, const double* center, double mindist, double maxdist, int32_t k_lo,
+                                     int32_t k_hi, int64_t* per_offset) {
+  if (m < 0 || (m > 0 && (!center || !per_offset)) || k_lo < 0 || k_hi < k_lo || k_hi > m) {
     fail(PUP_E_ARG, "pup_pair_windows_count: bad arguments");
     return -1;
   }
@@ -2402,7 +2424,7 @@ int64_t pup_pair_windows_count(int32_t m, const double* center, double mindist, 
   if (m > 0) per_offset[0] = 0;
   for (int32_t i = 1; i < m; ++i) {
     int64_t q = 0;
-    for (int32_t k = 0; k + i < m; ++k) {
+    for (int32_t k = k_lo; k < k_hi && k + i < m; ++k) {
       const double d = std::fabs(center[k + i] - center[k]);
       q += (mindist <= d && d <= maxdist) ? 1 : 0;
     }
@@ -2532,10 +2554,10 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
                             double maxdist, int32_t nctrl, const int64_t* per_offset, const int32_t* dbin, int32_t nb,
                             int W, const int64_t* key1, const int64_t* key2, const double* band_edges, int32_t n_edges,
                             int64_t band_weight, int flip_mode, int swap_on_flip, const int32_t* flipval,
-                            const int32_t* ident, int nk, int nf, int32_t part, int32_t parts, int32_t region_index,
-                            int32_t* r0, int32_t* c0, int32_t* slot, uint64_t* first_seen, uint64_t* n_roi,
-                            void* stream) {
-  if (m < 0 || nctrl < 0 || W <= 0 || nb <= 0 || nk <= 0 || nf <= 0 || parts <= 0 || part < 0 || part >= parts ||
+                            const int32_t* ident, int nk, int nf, int32_t k_lo, int32_t k_hi,
+                            const int64_t* per_offset_part, int32_t region_index, int32_t* r0, int32_t* c0,
+                            int32_t* slot, uint64_t* first_seen, uint64_t* n_roi, void* stream) {
+  if (m < 0 || nctrl < 0 || W <= 0 || nb <= 0 || nk <= 0 || nf <= 0 || k_lo < 0 || k_hi < k_lo || k_hi > m ||
       region_index < 0 || region_index >= (1 << 20))
     return fail(PUP_E_ARG, "pup_pair_windows_device: bad sizes");
   if (m < 2) return PUP_OK;
@@ -2546,13 +2568,17 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
   if (!is_device_ptr(r0) || !is_device_ptr(c0) || !is_device_ptr(slot) || (dbin && !is_device_ptr(dbin)) ||
       (first_seen && !is_device_ptr(first_seen)) || (n_roi && !is_device_ptr(n_roi)))
     return fail(PUP_E_ARG, "pup_pair_windows_device: outputs and dbin must be device memory");
-  int64_t total = 0;
-  std::vector<int64_t> base((size_t)m);
+  if (!per_offset_part) per_offset_part = per_offset;  // the whole region
+  int64_t total = 0, total_part = 0;
+  std::vector<int64_t> base((size_t)m), base_part((size_t)m);
   for (int32_t i = 0; i < m; ++i) {
     base[(size_t)i] = total;
+    base_part[(size_t)i] = total_part;
     total += per_offset[i];
+    total_part += per_offset_part[i];
+    if (per_offset_part[i] > per_offset[i]) return fail(PUP_E_ARG, "pup_pair_windows_device: part counts exceed the region's");
   }
-  if (total == 0) return PUP_OK;
+  if (total == 0 || total_part == 0) return PUP_OK;
   if (nctrl > 0 && !dbin) return fail(PUP_E_ARG, "pup_pair_windows_device: control shifts missing");
   if (total * (1 + (int64_t)nctrl) >= (1ll << 40)) return fail(PUP_E_ARG, "pup_pair_windows_device: too many windows");
   DeviceGuard guard(device);
@@ -2569,12 +2595,14 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
     *dst = t;
     return PUP_OK;
   };
-  const void *d_st, *d_ce, *d_po, *d_base, *d_k1, *d_k2, *d_ed, *d_fv, *d_id;
+  const void *d_st, *d_ce, *d_po, *d_base, *d_pop, *d_basep, *d_k1, *d_k2, *d_ed, *d_fv, *d_id;
   int rc;
   if ((rc = stage(stbin, (size_t)m * 4, &d_st)) != PUP_OK) return rc;
   if ((rc = stage(center, (size_t)m * 8, &d_ce)) != PUP_OK) return rc;
   if ((rc = stage(per_offset, (size_t)m * 8, &d_po)) != PUP_OK) return rc;
   if ((rc = stage(base.data(), (size_t)m * 8, &d_base)) != PUP_OK) return rc;
+  if ((rc = stage(per_offset_part, (size_t)m * 8, &d_pop)) != PUP_OK) return rc;
+  if ((rc = stage(base_part.data(), (size_t)m * 8, &d_basep)) != PUP_OK) return rc;
   if ((rc = stage(key1, (size_t)m * 8, &d_k1)) != PUP_OK) return rc;
   if ((rc = stage(key2, (size_t)m * 8, &d_k2)) != PUP_OK) return rc;
   if ((rc = stage(band_edges, (size_t)n_edges * 8, &d_ed)) != PUP_OK) return rc;
@@ -2588,8 +2616,8 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
   g.nk = nk;
   g.nf = nf;
   g.targets = ident ? 2 : 1;
-  g.part = part;
-  g.parts = parts;
+  g.k_lo = k_lo;
+  g.k_hi = k_hi;
   g.region_index = region_index;
   g.stbin = (const int32_t*)d_st;
   g.center = (const double*)d_ce;
@@ -2597,6 +2625,8 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
   g.maxdist = maxdist;
   g.base = (const int64_t*)d_base;
   g.per_offset = (const int64_t*)d_po;
+  g.base_part = (const int64_t*)d_basep;
+  g.per_offset_part = (const int64_t*)d_pop;
   g.dbin = dbin;
   g.key1 = (const int64_t*)d_k1;
   g.key2 = (const int64_t*)d_k2;

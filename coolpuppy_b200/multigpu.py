@@ -30,10 +30,11 @@ def split_heavy(costs, n_ranks, max_share=0.25):
     windows are independent and the accumulators add up).  Returns ``(units, unit_costs, owners)`` with
     ``units[j] = (item, part, parts)`` and ``owners[j]`` the LPT rank of unit ``j``.
 
-    Parts are STRIDED: part ``p`` of an item takes windows ``p, p + parts, p + 2 * parts, ...`` (:func:`part_index`).
-    A region's windows come in emission order (pair offset = separation ascending) and pixel density falls like
-    1 / separation, so contiguous equal-count parts differ several-fold in bytes (round 1: slowest rank 1.48x the mean
-    at 8 GPUs); strided parts are statistically identical, which also makes ``cost / parts`` the right unit cost."""
+    What a part is, is the caller's business.  ``PileUpper`` cuts a region's features at equal predicted cost and gives
+    part ``p`` the windows whose ROW anchor lies in the p-th feature range (``PileUpper._part_ranges``): a band of matrix
+    rows, so that every rank streams only its band from HBM.  (Round 1 cut the emission-ordered window list into
+    contiguous equal-count parts -- separation ascending, density ~ 1 / separation, parts several-fold unequal, slowest
+    rank 1.48x the mean at 8 GPUs; strided parts balance but make every part read the whole matrix.)"""
     units, ucost = [], []
     share = float(sum(costs)) / max(n_ranks, 1)
     for i, k in enumerate(costs):
@@ -47,7 +48,7 @@ def split_heavy(costs, n_ranks, max_share=0.25):
 
 
 def part_index(n, part, parts):
-    """Indices (into a list of ``n`` windows in emission order) of strided part ``part`` of ``parts``."""
+    """Indices (into a list of ``n`` items) of strided part ``part`` of ``parts`` (generic helper)."""
     return np.arange(part, n, parts, dtype=np.int64)
 
 

@@ -190,6 +190,9 @@ int pup_expected_cis(int device, int32_t nb, int64_t nnz_upper, const int32_t* i
  *       idx1 / idx2 = feature indices k, l, distance = center[l] - center[k].
  */
 int64_t pup_pair_windows_count(int32_t m, const double* center, double mindist, double maxdist, int64_t* per_offset);
+/* the same, counting only the pairs whose first feature (the window's row anchor) k lies in [k_lo, k_hi) */
+int64_t pup_pair_windows_count_range(int32_t m, const double* center, double mindist, double maxdist, int32_t k_lo,
+                                     int32_t k_hi, int64_t* per_offset);
 int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center, double mindist, double maxdist,
                           int32_t nctrl, const int64_t* dbin, int64_t* st1, int64_t* st2, int8_t* kind, int64_t* idx1,
                           int64_t* idx2, double* distance);
@@ -213,8 +216,9 @@ int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center,
  * (387-453) for the m features of one view region (sorted like the reference sorts them), written in the
  * reference's emission order: pairs (k, k + i) by offset i then k, kept when mindist <= |center[k+i] - center[k]|
  * <= maxdist; per offset block the ROI rows, then nctrl replicas shifted by dbin (block order, replica-major:
- * draw = nctrl * base[i] + (rep - 1) * per_offset[i] + j).  Window `pos` (emission index) is written at
- * (pos / parts) * targets when pos % parts == part (strided sharding of a region's windows over ranks).
+ * draw = nctrl * base[i] + (rep - 1) * per_offset[i] + j).  Only the windows whose row anchor k lies in
+ * [k_lo, k_hi) are written (a band of matrix rows: how a heavy region's windows are split over ranks), packed in
+ * emission order; per_offset_part = pup_pair_windows_count_range(.., k_lo, k_hi, ..) (NULL: the whole region).
  *   stbin[m]        region-relative first bin of every feature's window; center[m] in bp; per_offset[m] from
  *                   pup_pair_windows_count (host memory; the others host or device)
  *   slot            = ((key * nk + kind) * nf + flip); key = key1[k] + key2[l] (swapped to key1[l] + key2[k] for a
@@ -241,9 +245,9 @@ int pup_pair_windows_device(int device, int32_t m, const int32_t* stbin, const d
                             double maxdist, int32_t nctrl, const int64_t* per_offset, const int32_t* dbin, int32_t nb,
                             int W, const int64_t* key1, const int64_t* key2, const double* band_edges, int32_t n_edges,
                             int64_t band_weight, int flip_mode, int swap_on_flip, const int32_t* flipval,
-                            const int32_t* ident, int nk, int nf, int32_t part, int32_t parts, int32_t region_index,
-                            int32_t* r0, int32_t* c0, int32_t* slot, uint64_t* first_seen, uint64_t* n_roi,
-                            void* stream);
+                            const int32_t* ident, int nk, int nf, int32_t k_lo, int32_t k_hi,
+                            const int64_t* per_offset_part, int32_t region_index, int32_t* r0, int32_t* c0,
+                            int32_t* slot, uint64_t* first_seen, uint64_t* n_roi, void* stream);
 
 /* Statistics of the last pup_accumulate() on this thread (for bench.py): kernels launched by the call and
  * the exact algorithmic bytes of SURVEY.md section 8(d) -- filled only when n_valid_out was requested. */

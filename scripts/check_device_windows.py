@@ -41,8 +41,8 @@ for it in job["items"]:
     n_all = int(it["total"]) * (1 + it["nctrl"])
     outs = tuple(torch.full((n_all,), -7, dtype=torch.int32, device=dev) for _ in range(3))
     nat.pair_windows_device(0, it["stbin"], it["center"], pu.CC.mindist, pu.CC.maxdist, it["nctrl"], it["per_offset"], dbin,
-                            it["nb"], job["W"], None, None, None, 0, 0, False, None, None, job["nk"], job["nf"], 0, 1, it["index"],
-                            outs[0], outs[1], outs[2])
+                            it["nb"], job["W"], None, None, None, 0, 0, False, None, None, job["nk"], job["nf"], 0, len(it["center"]),
+                            None, it["index"], outs[0], outs[1], outs[2])
     torch.cuda.synchronize()
     for nm, got, want in zip(("r0", "c0", "slot"), outs, (b["w_r0"], b["w_c0"], b["slot"])):
         g = got.cpu().numpy().astype(np.int64)

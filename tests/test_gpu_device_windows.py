@@ -144,8 +144,8 @@ def _pileupper(name):
 @pytest.mark.parametrize("parts", [1, 3])
 def test_device_windows_equal_host_windows(name, parts):
     """r0 / c0 / slot arrays generated on the GPU == the host builder's arrays, element by element, in emission
-    order (incl. the seeded control shifts), for whole regions and for a strided share of them; the first-appearance
-    table gives the same group order."""
+    order (incl. the seeded control shifts), for whole regions and for row-anchor ranges of them (how a region's
+    windows are split over ranks); the first-appearance table gives the same group order."""
     nat = _cuda()
     import torch
 
@@ -180,18 +180,23 @@ def test_device_windows_equal_host_windows(name, parts):
         b = by_name[it["name"]]
         targets = 2 if it["ident"] is not None else 1
         n_all = int(it["total"]) * (1 + it["nctrl"])
+        m = len(it["center"])
+        cuts = np.linspace(0, m, parts + 1).astype(int)  # row-anchor ranges [k_lo, k_hi)
+        idx1 = np.repeat(np.asarray(b["rw"].idx1), targets)
         for part in range(parts):
-            n_mine = (n_all - part + parts - 1) // parts
+            k_lo, k_hi = int(cuts[part]), int(cuts[part + 1])
+            q_part, tot_part = nat.pair_windows_count(it["center"], pu.CC.mindist, pu.CC.maxdist, k_lo, k_hi)
+            n_mine = tot_part * (1 + it["nctrl"])
+            idx = np.nonzero((idx1 >= k_lo) & (idx1 < k_hi))[0]
+            assert len(idx) == n_mine * targets
             outs = tuple(torch.full((n_mine * targets,), -7, dtype=torch.int32, device=dev) for _ in range(3))
             nat.pair_windows_device(0, it["stbin"], it["center"], pu.CC.mindist, pu.CC.maxdist, it["nctrl"], it["per_offset"], dbin,
                                     it["nb"], job["W"], it["key1"], it["key2"], edges, it["band_weight"],
                                     0 if it["flipval"] is None else (1 if pu.flip_negative_strand else 2),
                                     bool(plan["flip"] and plan["ignore_group_order"]), it["flipval"], it["ident"], job["nk"],
-                                    job["nf"], part, parts, it["index"], outs[0], outs[1], outs[2],
-                                    first_seen=first if part == 0 and parts == 1 else None)
+                                    job["nf"], k_lo, k_hi, q_part, it["index"], outs[0], outs[1], outs[2],
+                                    first_seen=first if parts == 1 else None)
             torch.cuda.synchronize()
-            sel = np.arange(part, n_all, parts)
-            idx = (sel[:, None] * targets + np.arange(targets)[None, :]).reshape(-1)
             for got, want in zip(outs, (b["w_r0"], b["w_c0"], b["slot"])):
                 assert np.array_equal(got.cpu().numpy().astype(np.int64), np.asarray(want)[idx].astype(np.int64))
     rng.store()
@@ -268,8 +273,8 @@ def test_device_windows_at_bench_scale():
         n_all = int(it["total"]) * (1 + it["nctrl"])
         outs = tuple(torch.full((n_all,), -7, dtype=torch.int32, device=dev) for _ in range(3))
         nat.pair_windows_device(0, it["stbin"], it["center"], pu.CC.mindist, pu.CC.maxdist, it["nctrl"], it["per_offset"], dbin,
-                                it["nb"], job["W"], None, None, None, 0, 0, False, None, None, job["nk"], job["nf"], 0, 1,
-                                it["index"], outs[0], outs[1], outs[2])
+                                it["nb"], job["W"], None, None, None, 0, 0, False, None, None, job["nk"], job["nf"], 0,
+                                len(it["center"]), None, it["index"], outs[0], outs[1], outs[2])
         torch.cuda.synchronize()
         for got, want in zip(outs, (b["w_r0"], b["w_c0"], b["slot"])):
             assert np.array_equal(got.cpu().numpy().astype(np.int64), np.asarray(want).astype(np.int64)), it["name"]

@@ -168,3 +168,72 @@ def test_dynamic_group_dictionaries_are_merged_over_ranks():
     v1 = [t1.value("cls", k) for k in t1.remap("cls", c1)]
     assert v0 == ["b", "a", "b", None] and v1 == ["c", "a"]
     assert [t0.value("cls", k) for k in range(4)] == [t1.value("cls", k) for k in range(4)] == ["a", "b", "c", None]
+
+
+class _AllPartsDist:
+    """A fake sharder that hands THIS rank every part of every region as separate units (collectives are identities):
+    a rank can own several parts of one region (round-2 bug: the later part used to replace the earlier one)."""
+
+    world_size = 2
+    rank = 0
+
+    def my_units(self, items, costs, max_share=0.25):
+        units = []
+        for j, it in enumerate(items):
+            parts = 3 if j % 2 == 0 else 2
+            units += [(it, p, parts) for p in range(parts)]
+        return units, 1.0
+
+    def all_reduce(self, t):
+        return t
+
+    def all_reduce_min(self, t):
+        return t
+
+    def merge_min(self, m):
+        return m
+
+    def all_gather_object(self, o):
+        return [o]
+
+
+@pytest.mark.parametrize("name", ["toy_strand_dist_ctrl", "toy_bywindow", "scc1_ctcf_pairs_arms", "scc1_loops_ctrl",
+                                  "toy_local_raw", "toy_zero_expected_strand"])
+def test_several_parts_of_one_region_on_one_rank(emu, name):
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, feats, dist=_AllPartsDist(), **kw)
+    z, _ = gu.load_golden(name)
+    for i in range(len(pups)):
+        g = {f.split(".", 1)[1]: z[f] for f in z.files if f.startswith(f"row{i}.")}
+        a, b = np.asarray(pups["data"].iloc[i], dtype=float), g["data"]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        m = np.isfinite(b)
+        np.testing.assert_allclose(a[m], b[m], rtol=1e-9)
+        assert int(pups["n"].iloc[i]) == int(g["n"]) and np.array_equal(np.asarray(pups["num"].iloc[i]), g["num"])
+
+
+def test_part_ranges_cover_features_once():
+    from coolpuppy_b200 import coolpup as cp
+
+    clr, feats, kw = gu.case_inputs("scc1_ctcf_pairs_arms")
+    view = kw["view_df"]
+    cc = cp.CoordCreator(feats, clr.binsize, features_format="bed", flank=50_000, mindist=0, maxdist=2_000_000,
+                         chroms=list(view["chrom"].unique()))
+    pu = cp.PileUpper(clr, cc, view_df=view, clr_weight_name=None)
+    for name in pu.view_df.index:
+        n = len(pu._feature_costs(name))
+        for parts in (2, 5):
+            got = []
+            for p in range(parts):
+                got += [k for lo, hi in pu._part_ranges(name, [p], parts) for k in range(lo, hi)]
+            assert sorted(got) == list(range(n))
+            merged = pu._part_ranges(name, range(parts), parts)
+            assert merged == [(0, n)]
+        c = pu._feature_costs(name)
+        cuts = [pu._part_ranges(name, [p], 4) for p in range(4)]
+        loads = [sum(c[lo:hi].sum() for lo, hi in r) for r in cuts]
+        assert max(loads) <= 0.5 * c.sum()  # equal-cost cut points, up to one feature's cost
