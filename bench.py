@@ -12,9 +12,9 @@ balanced with 3 % NaN bins):
 
 A step = one pass of the hot path over every window of every chromosome:
   value   : region matrices and window arrays resident in HBM; per sharding unit pup_accumulate() = device sort of the
-            windows + count kernels + main pile-up kernel; N > 1: chromosomes sharded over ranks by LPT on their exact
-            algorithmic bytes, heavy chromosomes cut into row-band window parts (matrix replicated), one NCCL
-            all-reduce of the accumulators inside the timed region.
+            windows + count kernels + main pile-up kernel; N > 1: the (chromosome, row anchor) sequence is cut into N
+            contiguous pieces of equal exact algorithmic bytes (a chromosome on a cut is piled up as row bands on two
+            ranks, matrix replicated), one NCCL all-reduce of the accumulators inside the timed region.
   e2e     : the same pass through the product's two-stream region pipeline (coolpuppy_b200.pipeline) with HOST (pinned)
             buffers: pup_region_create_upper() + pup_upload() + pup_accumulate() per chromosome, i.e. including the
             H2D upload and device-side indexing of every chromosome and the D2H read of the accumulators.
@@ -367,7 +367,7 @@ def main():
     import torch
 
     from coolpuppy_b200 import _native
-    from coolpuppy_b200.multigpu import lpt_assign, split_heavy
+    from coolpuppy_b200.multigpu import contiguous_partition, lpt_assign
 
     _native.require_device()
     torch.cuda.set_device(local_rank)
@@ -413,30 +413,30 @@ def main():
             b, z = 0, 0
         cost.append(b)
         nnz_win.append(z)
-    iunits, ucost, uowner = split_heavy(cost, world, max_share=0.25)
-    my_units = [(names[i], part, parts) for (i, part, parts), o in zip(iunits, uowner) if o == rank]
-    load = np.bincount(uowner, weights=ucost, minlength=world)
-    predicted_imbalance = float(load.max() / load.mean()) if load.sum() > 0 else 1.0
-    for c in names:  # matrices of chromosomes this rank has no unit of are not needed any more
+    # one contiguous, equal-cost piece of the (chromosome, row anchor) sequence per rank (the product's sharding,
+    # multigpu.contiguous_partition); the per-anchor cost model is rescaled to every chromosome's exact bytes
+    arrs = []
+    for c, b in zip(names, cost):
+        a = np.array(pu_plan._feature_costs(c) if len(windows[c]["r0"]) else np.zeros(0), dtype=np.float64)
+        arrs.append(a * (b / a.sum()) if a.sum() > 0 else a)
+    pieces, loads = contiguous_partition(arrs, world)
+    my_units = [(names[i], lo, hi, lo == 0 and hi == len(arrs[i])) for i, lo, hi in pieces[rank]]
+    predicted_imbalance = float(max(loads) / (sum(loads) / len(loads))) if sum(loads) > 0 else 1.0
+    for c in names:  # matrices of chromosomes this rank has no piece of are not needed any more
         if c not in {u[0] for u in my_units}:
             regions.pop(c).close()
-    split = sorted({c for c, _, n in my_units if n > 1} | {names[i] for (i, _, n) in iunits if n > 1}, key=names.index)
+    split = [names[i] for i in sorted({i for p_ in pieces for i, lo, hi in p_ if not (lo == 0 and hi == len(arrs[i]))})]
+    n_units = sum(len(p_) for p_ in pieces)
     dwin = {}
     alg_bytes = 0
-    for c, part, parts in my_units:
+    for c, lo, hi, whole in my_units:
         w = windows[c]
-        if parts == 1:
-            sel = np.arange(len(w["r0"]))
-        else:  # the product's row-band parts: windows whose row anchor lies in the part's feature range
-            mask = np.zeros(len(w["r0"]), dtype=bool)
-            for k_lo, k_hi in pu_plan._part_ranges(c, [part], parts):
-                mask |= (w["anchor"] >= k_lo) & (w["anchor"] < k_hi)
-            sel = np.nonzero(mask)[0]
-        dwin[(c, part)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][sel])).to(dev) for k in ("r0", "c0", "slot"))
-        if parts == 1:
+        sel = np.arange(len(w["r0"])) if whole else np.nonzero((w["anchor"] >= lo) & (w["anchor"] < hi))[0]
+        dwin[(c, lo)] = tuple(torch.from_numpy(np.ascontiguousarray(w[k][sel])).to(dev) for k in ("r0", "c0", "slot"))
+        if whole:
             alg_bytes += cost[names.index(c)]
         elif len(sel):
-            alg_bytes += regions[c].algorithmic_bytes(dwin[(c, part)][0], dwin[(c, part)][1], W, flags, stream=stream)[0]
+            alg_bytes += regions[c].algorithmic_bytes(dwin[(c, lo)][0], dwin[(c, lo)][1], W, flags, stream=stream)[0]
     if not want_host:
         host_data = {}
     del dev_data
@@ -448,9 +448,9 @@ def main():
         "depth": args.depth, "roi_windows": int(n_pairs), "windows_per_step": int(n_windows_total),
         "chromosomes": len(names), "binsize": BINSIZE, "flank": wl["flank"], "accumulator_slots": int(n_slots),
         "l2": "inputs (region matrices, GBs) exceed the 126 MB L2; no flush between iterations",
-        "parallelism": (f"chromosomes sharded over {world} GPU(s) by LPT on exact algorithmic bytes; chromosomes above a quarter "
-                        "of a rank's share are cut into row-band window parts (matrix replicated); one all-reduce of the "
-                        "accumulators; e2e: whole chromosomes per GPU"),
+        "parallelism": (f"the (chromosome, row anchor) sequence is cut into {world} contiguous pieces of equal algorithmic bytes, one "
+                        "per GPU (a chromosome that straddles a cut is piled up as row bands on two GPUs, its matrix "
+                        "replicated); one all-reduce of the accumulators; e2e: whole chromosomes per GPU by LPT"),
     }
 
     stride = _native.acc_stride(W)
@@ -459,8 +459,8 @@ def main():
     def step():
         acc.zero_()
         launches = 1
-        for c, part, _ in my_units:
-            r0, c0, sl = dwin[(c, part)]
+        for c, lo, _, _ in my_units:
+            r0, c0, sl = dwin[(c, lo)]
             if r0.shape[0] == 0:
                 continue
             regions[c].accumulate(r0, c0, sl, W, n_slots, acc_flags, acc, stream=stream)
@@ -666,7 +666,7 @@ def main():
         "phase_ms_per_step": {k: v[0] / args.steps for k, v in phases.items()},
         "kernel_ms_per_step_by_rank": kernel_ms,
     }
-    sharding = {"units": len(iunits), "split_chromosomes": split, "predicted_max_over_mean": predicted_imbalance,
+    sharding = {"units": n_units, "split_chromosomes": split, "predicted_max_over_mean": predicted_imbalance,
                 "bytes_max_over_mean": float(max(bytes_rank) / (sum(bytes_rank) / len(bytes_rank))) if sum(bytes_rank) else 1.0,
                 "kernel_ms_max_over_mean": float(max(kernel_ms) / (sum(kernel_ms) / len(kernel_ms))) if sum(kernel_ms) else 1.0,
                 "allreduce_payload_bytes": int(acc.numel() * 8), "allreduce_ms": allreduce_ms}

@@ -711,6 +711,9 @@ class PileUpper:
         self._cost_cache = {}
         if dist is None or dist.world_size == 1:
             return {name: None for name in region_names}, 1.0
+        if splittable and hasattr(dist, "my_ranges"):
+            # one contiguous, equal-cost piece of the (region, row anchor) sequence per rank
+            return dist.my_ranges(region_names, [self._feature_costs(n) for n in region_names])
         costs = [self._region_cost(n) for n in region_names]
         units, imbalance = dist.my_units(region_names, costs, max_share=0.25 if splittable else 1e9)
         mine = {}

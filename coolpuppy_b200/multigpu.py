@@ -47,6 +47,50 @@ def split_heavy(costs, n_ranks, max_share=0.25):
     return units, ucost, lpt_assign(ucost, n_ranks)
 
 
+def contiguous_partition(cost_arrays, n_ranks):
+    """Cut the concatenation of the items' per-element costs into ``n_ranks`` contiguous pieces of (nearly) equal cost.
+
+    ``cost_arrays[i][k]`` is the cost of element ``k`` of item ``i`` (for the pile-up: the predicted bytes of the windows
+    whose row anchor is feature ``k`` of view region ``i``).  Returns ``(pieces, loads)``: ``pieces[r]`` is the list of
+    ``(item, lo, hi)`` element ranges of rank ``r`` (in item order, at most the first and the last one partial) and
+    ``loads[r]`` their cost.  At most ``n_ranks - 1`` items are split, every rank runs few large launches, and the
+    balance is as good as the cost model -- LPT over whole items plus a fixed number of parts is not (round 2: 1.04
+    predicted, 1.06 measured at 8 GPUs)."""
+    sizes = [len(c) for c in cost_arrays]
+    flat = np.concatenate([np.asarray(c, dtype=np.float64) for c in cost_arrays]) if cost_arrays else np.zeros(0)
+    cum = np.concatenate([[0.0], np.cumsum(flat)])
+    total = cum[-1]
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    if total <= 0 or n_ranks <= 1:
+        pieces = [[(i, 0, sizes[i]) for i in range(len(sizes)) if sizes[i]]] + [[] for _ in range(max(0, n_ranks - 1))]
+        return pieces, [float(total)] + [0.0] * max(0, n_ranks - 1)
+    # cut at the element boundary nearest to r / n_ranks of the total
+    cuts = [0]
+    for r in range(1, n_ranks):
+        t = total * r / n_ranks
+        j = int(np.searchsorted(cum, t, side="left"))
+        if j > 0 and t - cum[j - 1] < cum[min(j, len(flat))] - t:  # the nearer element boundary
+            j -= 1
+        cuts.append(j)
+    cuts.append(len(flat))
+    cuts = np.maximum.accumulate(np.asarray(cuts, dtype=np.int64))
+    pieces, loads = [], []
+    for r in range(n_ranks):
+        a, b = int(cuts[r]), int(cuts[r + 1])
+        mine = []
+        i = int(np.searchsorted(starts, a, side="right") - 1)
+        while a < b and i < len(sizes):
+            lo = a - int(starts[i])
+            hi = min(b, int(starts[i + 1])) - int(starts[i])
+            if hi > lo:
+                mine.append((i, lo, hi))
+            a = int(starts[i + 1])
+            i += 1
+        pieces.append(mine)
+        loads.append(float(cum[cuts[r + 1]] - cum[cuts[r]]))
+    return pieces, loads
+
+
 def part_index(n, part, parts):
     """Indices (into a list of ``n`` items) of strided part ``part`` of ``parts`` (generic helper)."""
     return np.arange(part, n, parts, dtype=np.int64)
@@ -81,6 +125,17 @@ class RegionSharder:
         imbalance = float(load.max() / load.mean()) if load.sum() > 0 else 1.0
         mine = [(items[i], part, parts) for (i, part, parts), o in zip(units, owner) if o == self.rank]
         return mine, imbalance
+
+    def my_ranges(self, items, cost_arrays):
+        """``{item: [(lo, hi)] or None (the whole item)}`` of this rank from :func:`contiguous_partition`, plus the
+        predicted max / mean load over the ranks."""
+        pieces, loads = contiguous_partition(cost_arrays, self.world_size)
+        mean = sum(loads) / max(1, len(loads))
+        mine = {}
+        for i, lo, hi in pieces[self.rank]:
+            whole = lo == 0 and hi == len(cost_arrays[i])
+            mine[items[i]] = None if whole else [(lo, hi)]
+        return mine, (max(loads) / mean if mean > 0 else 1.0)
 
     def all_gather_object(self, obj):
         if self.world_size == 1:
