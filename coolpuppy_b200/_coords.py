@@ -41,11 +41,12 @@ class RegionWindows:
     on side 1 / side 2; ``distance``: centre2 - centre1 in bp (None for local).
     """
 
-    __slots__ = ("region", "sel", "st1", "st2", "kind", "idx1", "idx2", "distance", "paired", "frame")
+    __slots__ = ("region", "sel", "sel2", "st1", "st2", "kind", "idx1", "idx2", "distance", "paired", "frame")
 
-    def __init__(self, region, sel, st1, st2, kind, idx1, idx2, distance, paired):
+    def __init__(self, region, sel, st1, st2, kind, idx1, idx2, distance, paired, sel2=None):
         self.region = region
         self.sel = sel
+        self.sel2 = sel if sel2 is None else sel2  # feature table of side 2 (differs from side 1 for trans pairs)
         self.st1 = st1
         self.st2 = st2
         self.kind = kind
@@ -63,7 +64,8 @@ class RegionWindows:
         if self.frame is not None:
             raise NotImplementedError("cannot subset windows after a user callback has materialised the frame")
         return RegionWindows(self.region, self.sel, self.st1[sel], self.st2[sel], self.kind[sel], self.idx1[sel],
-                             self.idx2[sel], None if self.distance is None else self.distance[sel], self.paired)
+                             self.idx2[sel], None if self.distance is None else self.distance[sel], self.paired,
+                             sel2=self.sel2)
 
     def column(self, name, swap=None):
         """Values of 2-D interval column ``name`` for every window.
@@ -83,11 +85,11 @@ class RegionWindows:
         if self.paired:
             if name[-1] not in "12" or name[:-1] not in self.sel.columns:
                 raise KeyError(f"no 2-D interval column {name!r}")
-            base = self.sel[name[:-1]].to_numpy()
-            a, b = (self.idx1, self.idx2) if name[-1] == "1" else (self.idx2, self.idx1)
+            own = self.sel[name[:-1]].to_numpy()[self.idx1] if name[-1] == "1" else self.sel2[name[:-1]].to_numpy()[self.idx2]
             if swap is not None and swap.any():
-                return base[np.where(swap, b, a)]
-            return base[a]
+                other = self.sel2[name[:-1]].to_numpy()[self.idx2] if name[-1] == "1" else self.sel[name[:-1]].to_numpy()[self.idx1]
+                return np.where(swap, other, own)
+            return own
         if name not in self.sel.columns:
             raise KeyError(f"no 2-D interval column {name!r}")
         vals = self.sel[name].to_numpy()[self.idx1]
@@ -112,7 +114,7 @@ class RegionWindows:
             return self.frame
         if self.paired:
             left = self.sel.iloc[self.idx1].reset_index(drop=True).rename(columns=lambda c: c + "1")
-            right = self.sel.iloc[self.idx2].reset_index(drop=True).rename(columns=lambda c: c + "2")
+            right = self.sel2.iloc[self.idx2].reset_index(drop=True).rename(columns=lambda c: c + "2")
             fr = pd.concat([left, right], axis=1)
             if self.distance is not None:
                 fr["distance"] = self.distance
@@ -217,3 +219,70 @@ def build_region_windows(cc, region, control, draw_only=False):
         nctrl = 0
     st1, st2, kind, kk, ll, dist_all = _native.pair_windows_fill(stbin, center, cc.mindist, cc.maxdist, nctrl, dbin, total)
     return RegionWindows(region, sel, st1, st2, kind, kk, ll, dist_all, paired=True)
+
+
+def _draw_shifts_trans(n, minshift, maxshift, resolution):
+    """Control-shift draw of a TRANS block (coolpup.py:392-407): a second (shift2, sign2) pair is drawn for side 2, but
+    the bin columns of BOTH sides move by the first shift (430-433) -- the second draw only advances the stream."""
+    dbin = _draw_shifts(n, minshift, maxshift, resolution)
+    np.random.randint(minshift, maxshift, n)
+    np.random.choice([-1, 1], n)
+    return dbin
+
+
+def build_trans_windows(cc, region1, region2, control, draw_only=False):
+    """Windows between two view regions on different chromosomes (reference: coolpup.py:565-590, 652-680, 1330-1348).
+
+    bed: every feature of region1 with every feature of region2 (``itertools.product``), one ``_control_regions`` call
+    PER PAIR (ROI row, then its nshifts controls); bedpe: the rows joining the two regions in either orientation -- the
+    rows stored the other way round are taken as they are, their side-1 bins applied to region1 (a quirk of
+    ``_filter_func_trans_pairs``, reproduced) -- and one ``_control_regions`` call for the region pair."""
+    df = cc.intervals
+    nctrl = cc.nshifts if control else 0
+    res = cc.resolution
+    (ch1, s1, e1), (ch2, s2, e2) = region1, region2
+    if cc.kind == "bedpe":
+        a = ((df["chrom1"].values == ch1) & (df["chrom2"].values == ch2) & (df["start1"].values >= s1) & (df["end1"].values < e1)
+             & (df["start2"].values >= s2) & (df["end2"].values < e2))
+        b = ((df["chrom2"].values == ch1) & (df["chrom1"].values == ch2) & (df["start2"].values >= s1) & (df["end2"].values < e1)
+             & (df["start1"].values >= s2) & (df["end1"].values < e2))
+        sel = pd.concat([df[a], df[b]]).reset_index(drop=True)
+        q = len(sel)
+        idx = np.arange(q, dtype=np.int64)
+        st1 = sel["stBin1"].values.astype(np.int64)
+        st2 = sel["stBin2"].values.astype(np.int64)
+        dist = sel["distance"].values.astype(np.float64)
+        kind = np.zeros(q, dtype=np.int8)
+        if nctrl > 0 and q > 0:
+            dbin = _draw_shifts_trans(q * nctrl, cc.minshift, cc.maxshift, res)
+            if draw_only:
+                return None
+            cidx = np.tile(idx, nctrl)
+            st1 = np.concatenate([st1, st1[cidx] + dbin])
+            st2 = np.concatenate([st2, st2[cidx] + dbin])
+            dist = np.concatenate([dist, dist[cidx]])
+            kind = np.concatenate([kind, np.ones(q * nctrl, dtype=np.int8)])
+            idx = np.concatenate([idx, cidx])
+        return RegionWindows((region1, region2), sel, st1, st2, kind, idx, idx, dist, paired=False)
+    left = df[(df["chrom"].values == ch1) & (df["start"].values >= s1) & (df["end"].values < e1)].reset_index(drop=True)
+    right = df[(df["chrom"].values == ch2) & (df["start"].values >= s2) & (df["end"].values < e2)].reset_index(drop=True)
+    n1, n2 = len(left), len(right)
+    x = np.repeat(np.arange(n1, dtype=np.int64), n2)
+    y = np.tile(np.arange(n2, dtype=np.int64), n1)
+    lb = left["stBin"].values.astype(np.int64)
+    rb = right["stBin"].values.astype(np.int64)
+    if nctrl == 0 or n1 * n2 == 0:
+        return RegionWindows((region1, region2), left, lb[x], rb[y], np.zeros(n1 * n2, dtype=np.int8), x, y, None,
+                             paired=True, sel2=right)
+    shifts = np.empty((n1 * n2, nctrl), dtype=np.int64)
+    for p in range(n1 * n2):  # one draw per pair: that is the reference's stream
+        shifts[p] = _draw_shifts_trans(nctrl, cc.minshift, cc.maxshift, res)
+    if draw_only:
+        return None
+    block = 1 + nctrl  # per pair: the ROI row, then its controls
+    st1 = np.repeat(lb[x], block)
+    st2 = np.repeat(rb[y], block)
+    add = np.concatenate([np.zeros((n1 * n2, 1), dtype=np.int64), shifts], axis=1).reshape(-1)
+    kind = np.tile(np.concatenate([[0], np.ones(nctrl, dtype=np.int8)]).astype(np.int8), n1 * n2)
+    return RegionWindows((region1, region2), left, st1 + add, st2 + add, kind, np.repeat(x, block), np.repeat(y, block),
+                         None, paired=True, sel2=right)

@@ -15,8 +15,8 @@ the result unchanged.  What differs is how the work is done:
   and the per-GPU accumulators are merged with a single all-reduce.
 
 There is no CPU fallback.  Not supported (raises ``NotImplementedError``):
-``trans``, ``rescale``, arbitrary ``postprocess_func`` / ``extra_sum_funcs``
-callbacks ("out of scope").
+``rescale``, arbitrary ``postprocess_func`` / ``extra_sum_funcs`` callbacks
+("out of scope").
 """
 from __future__ import annotations
 
@@ -29,7 +29,7 @@ import numpy as np
 import pandas as pd
 
 from . import _native
-from ._coords import RegionWindows, build_region_windows, default_band_edges, natsorted
+from ._coords import RegionWindows, build_region_windows, build_trans_windows, default_band_edges, natsorted
 from .coolio import is_cooler
 
 logger = logging.getLogger("coolpuppy")
@@ -146,12 +146,22 @@ class CoordCreator:
         self.maxshift = maxshift
         self.nshifts = nshifts
         self.trans = trans
-        if trans:
-            raise NotImplementedError("trans pile-ups are not supported by the B200 path")
         if rescale_flank is not None:
             raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
-        self.mindist = 2 * self.flank + 2 * self.resolution if mindist == "auto" else mindist
-        self.maxdist = np.inf if maxdist is None else maxdist
+        if isinstance(mindist, str) and mindist == "auto":
+            self.mindist = 2 * self.flank + 2 * self.resolution
+        else:
+            self.mindist = mindist
+            if self.trans:  # coolpup.py:243-246
+                warnings.warn("Ignoring mindist when using trans", stacklevel=2)
+                self.mindist = 0
+        if maxdist is None:
+            self.maxdist = np.inf
+        else:
+            self.maxdist = maxdist
+            if self.trans:  # coolpup.py:250-253
+                warnings.warn("Ignoring maxdist when using trans", stacklevel=2)
+                self.maxdist = np.inf
         self.local = local
         self.subset = subset
         self.seed = seed
@@ -207,7 +217,10 @@ class CoordCreator:
         else:
             if self.local:
                 raise ValueError("Can't make local with both sides of loops defined")
-            basechroms = set(df["chrom1"]).intersection(set(df["chrom2"]))
+            if self.trans:  # coolpup.py:341-345
+                basechroms = set(df["chrom1"].unique().tolist() + df["chrom2"].unique().tolist())
+            else:
+                basechroms = set(df["chrom1"]).intersection(set(df["chrom2"]))
         self.basechroms = natsorted(list(basechroms))
         if isinstance(self.chroms, str) and self.chroms == "all":
             self.final_chroms = natsorted(list(basechroms))
@@ -219,6 +232,8 @@ class CoordCreator:
                 'Are they in the same format, e.g. starting with "chr"?'
             )
         self.intervals = self._binnify(df)
+        if self.trans and self.local:
+            raise ValueError("Cannot do local with trans=True")
         self.pos_stream = self.get_combinations if self.kind == "bed" else self.get_intervals_stream
 
     def _subset(self, df):
@@ -248,6 +263,10 @@ class CoordCreator:
     def region_windows(self, region, control=False) -> RegionWindows:
         """All windows of view region ``(chrom, start, end)`` as arrays, in the reference's emission order."""
         return build_region_windows(self, region, control)
+
+    def region_windows_trans(self, region1, region2, control=False) -> RegionWindows:
+        """Windows between two view regions on different chromosomes (trans pile-ups)."""
+        return build_trans_windows(self, region1, region2, control)
 
     # -- reference-compatible generators (slow; for callers that iterate the stream themselves) ----
     def _stream(self, region_filter, control, groupby, modify_2Dintervals_func):
@@ -452,22 +471,31 @@ class PileUpper:
             if self.control:
                 warnings.warn("Can't do both expected and control shifts; defaulting to expected", stacklevel=2)
                 self.control = False
-            exp = exp[exp["region1"] == exp["region2"]].reset_index(drop=True)
-            for c in ("region1", "region2", "dist", self.expected_value_col):
-                if c not in exp.columns:
-                    raise ValueError("provided expected is not valid")
-            for name in self.view_df["name"]:
-                vals = exp.loc[(exp["region1"] == name), self.expected_value_col].values.astype(np.float64)
-                self._expected_values[name] = vals  # E[d] in table row order (ExpectedSnipper.select, 907-916)
-            self.expected_df = exp
-            self.expected = True
+            if self.trans:  # one scalar per region pair (get_expected_trans, coolpup.py:999-1005)
+                for c in ("region1", "region2", self.expected_value_col):
+                    if c not in exp.columns:
+                        raise ValueError("provided expected is not valid")
+                self.expected_df = exp.reset_index(drop=True)
+                self.expected = True
+            else:
+                exp = exp[exp["region1"] == exp["region2"]].reset_index(drop=True)
+                for c in ("region1", "region2", "dist", self.expected_value_col):
+                    if c not in exp.columns:
+                        raise ValueError("provided expected is not valid")
+                by_region = {k: v.values.astype(np.float64)
+                             for k, v in exp.groupby("region1", sort=False)[self.expected_value_col]}
+                for name in self.view_df["name"]:
+                    # E[d] in table row order (ExpectedSnipper.select, 907-916)
+                    self._expected_values[name] = by_region.get(name, np.zeros(0))
+                self.expected_df = exp
+                self.expected = True
         self.view_df = self.view_df.set_index("name")
         self.view_df_extents = {}
         for region_name, region in self.view_df.iterrows():
             lo, hi = self.clr.extent((region["chrom"], region["start"], region["end"]))
             chroffset = self.clr.offset(region["chrom"])
             self.view_df_extents[region_name] = lo - chroffset, hi - chroffset
-        if self.expected is True:
+        if self.expected is True and not self.trans:
             # cooltools.lib.checks.is_valid_expected(..., verify_cooler=clr) at coolpup.py:875-906: every view region
             # needs one expected row per diagonal; a missing region would silently give an all-NaN pile-up here
             for region_name, (lo_rel, hi_rel) in self.view_df_extents.items():
@@ -484,6 +512,8 @@ class PileUpper:
                 "No chromosomes are in common between the coordinate file and the cooler file. "
                 'Are they in the same format, e.g. starting with "chr"?'
             )
+        if self.trans and self.view_df["chrom"].unique().shape[0] < 2:
+            raise ValueError("Trying to do trans with fewer than two chromosomes")
         if self.coverage_norm is True:
             self.coverage_norm = "cov_tot_raw"
         elif self.coverage_norm == "cis":
@@ -682,6 +712,20 @@ class PileUpper:
     def _region_cost(self, name):
         return float(self._feature_costs(name).sum())
 
+    def _pair_cost(self, name1, name2):
+        """Relative cost of a trans region pair: the number of windows between the two regions."""
+        df = self.CC.intervals
+
+        def inside(name, side):
+            r = self.view_df.loc[name]
+            return ((df["chrom" + side].values == r["chrom"]) & (df["start" + side].values >= r["start"])
+                    & (df["end" + side].values < r["end"]))
+
+        if self.CC.kind == "bedpe":
+            return float(np.count_nonzero(inside(name1, "1") & inside(name2, "2"))
+                         + np.count_nonzero(inside(name1, "2") & inside(name2, "1"))) + 1e-3
+        return float(np.count_nonzero(inside(name1, "")) * np.count_nonzero(inside(name2, ""))) + 1e-3
+
     def _part_ranges(self, name, my_parts, parts):
         """Feature-index ranges ``[(k_lo, k_hi)]`` (merged when adjacent) of window parts ``my_parts`` out of ``parts``:
         the region's features are cut at equal predicted cost.  A part holds the windows whose ROW anchor lies in its
@@ -711,6 +755,9 @@ class PileUpper:
         self._cost_cache = {}
         if dist is None or dist.world_size == 1:
             return {name: None for name in region_names}, 1.0
+        if self.trans:
+            units, imbalance = dist.my_units(region_names, [self._pair_cost(*n) for n in region_names], max_share=1e9)
+            return {name: None for name, _, _ in units}, imbalance
         if splittable and hasattr(dist, "my_ranges"):
             # one contiguous, equal-cost piece of the (region, row anchor) sequence per rank
             return dist.my_ranges(region_names, [self._feature_costs(n) for n in region_names])
@@ -727,6 +774,8 @@ class PileUpper:
         pile-ups were grouped -- reproduced by :meth:`_exact_merge` from per-region accumulators."""
         if not (self.expected is True and self.ooe):
             return False
+        if self.trans:
+            return bool(np.any(self.expected_df[self.expected_value_col].values == 0))
         return any(np.any(v == 0) for v in self._expected_values.values())
 
     def _prepare(self, plan, regions=None, dist=None):
@@ -734,22 +783,29 @@ class PileUpper:
         modify_2Dintervals_func = plan["modify"]
         W = 2 * self.pad_bins + 1
         table = _GroupTable(self.CC)
-        region_names = list(self.view_df.index) if regions is None else list(regions)
+        region_names = self._unit_keys() if regions is None else list(regions)
         do_control = bool(self.control)
         expctrl = bool(self.expected is True and not self.ooe)
-        splittable = not (self.store_stripes or (modify_2Dintervals_func is not None and plan["band_edges"] is None))
+        splittable = not (self.trans or self.store_stripes
+                          or (modify_2Dintervals_func is not None and plan["band_edges"] is None))
         my_units, imbalance = self._my_units(region_names, dist, splittable)
         built = []
         for ri, name in enumerate(region_names):
-            r = self.view_df.loc[name]
-            region = (r["chrom"], r["start"], r["end"])
+            if self.trans:
+                ra, rb = self.view_df.loc[name[0]], self.view_df.loc[name[1]]
+                region = ((ra["chrom"], ra["start"], ra["end"]), (rb["chrom"], rb["start"], rb["end"]))
+                make = lambda draw_only=False: build_trans_windows(self.CC, region[0], region[1], do_control, draw_only=draw_only)
+            else:
+                r = self.view_df.loc[name]
+                region = (r["chrom"], r["start"], r["end"])
+                make = lambda draw_only=False: build_region_windows(self.CC, region, do_control, draw_only=draw_only)
             if name not in my_units:
                 if do_control and self.CC.nshifts > 0:
                     # another rank's region: make its np.random draws (no window layout) so that every rank consumes
                     # the random stream exactly like the reference's serial (nproc=1) run
-                    build_region_windows(self.CC, region, True, draw_only=True)
+                    make(draw_only=True)
                 continue
-            rw = self.CC.region_windows(region, control=do_control)
+            rw = make()
             if len(rw) == 0:
                 continue
             pos0 = np.arange(len(rw), dtype=np.int64)
@@ -762,11 +818,20 @@ class PileUpper:
                 if len(rw) == 0:
                     continue
             flipf, cols = self._region_group_codes(rw, plan, table)
-            lo_rel, hi_rel = self.view_df_extents[name]
-            nb = hi_rel - lo_rel
-            r0 = rw.st1 - lo_rel
-            c0 = rw.st2 - lo_rel
-            valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
+            if self.trans:
+                # the rectangular region1 x region2 matrix is embedded in a square one of nb1 + nb2 bins (rows: region1,
+                # columns: region2 behind an offset of nb1); a window must lie inside both regions (coolpup.py:1111-1114)
+                (lo1, hi1), (lo2, hi2) = self.view_df_extents[name[0]], self.view_df_extents[name[1]]
+                a, b = rw.st1 - lo1, rw.st2 - lo2
+                valid = (a >= 0) & (a + W <= hi1 - lo1) & (b >= 0) & (b + W <= hi2 - lo2)
+                r0 = np.where(valid, a, -1)  # the kernel drops windows with a negative corner
+                c0 = b + (hi1 - lo1)
+            else:
+                lo_rel, hi_rel = self.view_df_extents[name]
+                nb = hi_rel - lo_rel
+                r0 = rw.st1 - lo_rel
+                c0 = rw.st2 - lo_rel
+                valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
             built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, cols=cols, pos0=pos0))
         # dense group keys: mixed radix over the group columns (identical on every rank), or the feature id (by-window)
         table.finalize(dist)
@@ -794,8 +859,8 @@ class PileUpper:
             n = len(rw)
             if plan["by_window"]:
                 # every window goes to the groups of both anchors (group_by_region, lib/puputils.py:218-223)
-                ident = self._feature_ident(rw)
-                key = np.stack([ident[rw.idx1], ident[rw.idx2]], axis=1).reshape(-1)  # [n * 2]
+                ident1, ident2 = self._feature_ident(rw)
+                key = np.stack([ident1[rw.idx1], ident2[rw.idx2]], axis=1).reshape(-1)  # [n * 2]
                 ntarget = 2
             else:
                 key = np.zeros(n, dtype=np.int64)
@@ -825,6 +890,8 @@ class PileUpper:
             flags |= _native.PUP_F_EXPCTRL
         if self.coverage_norm:
             flags |= _native.PUP_F_COVERAGE
+        if self.trans:
+            flags |= _native.PUP_F_NODIAG  # no diagonal mask between chromosomes (coolpup.py:1141)
         return dict(plan=plan, W=W, built=built, colspec=colspec, table=table, first=first, nk=nk, nf=nf, n_keys=n_keys,
                     n_slots=n_keys * nk * nf, flags=flags, do_control=do_control, expctrl=expctrl,
                     region_names=region_names, imbalance=imbalance)
@@ -846,7 +913,53 @@ class PileUpper:
                 vals.append(job["table"].value(g, code))
         return tuple(reversed(vals))
 
+    def _unit_keys(self):
+        """What pileup_region is mapped over (coolpup.py:1419-1429): the view regions, or for trans every pair of view
+        regions on different chromosomes."""
+        names = list(self.view_df.index)
+        if not self.trans:
+            return names
+        import itertools
+
+        return [(a, b) for a, b in itertools.combinations(names, 2)
+                if self.view_df.loc[a, "chrom"] != self.view_df.loc[b, "chrom"]]
+
+    def _expected_trans(self, region1, region2):
+        """get_expected_trans (coolpup.py:999-1005): the one expected value of a region pair."""
+        e = self.expected_df
+        vals = e.loc[(e["region1"] == region1) & (e["region2"] == region2), self.expected_value_col]
+        return float(vals.item())
+
+    def _trans_arrays(self, name1, name2):
+        """Host arrays of a trans region pair: the region1 x region2 block as the upper-right block of a square CSR of
+        nb1 + nb2 bins, per-bin vectors concatenated, the scalar expected as a constant vector."""
+        ra, rb = self.view_df.loc[name1], self.view_df.loc[name2]
+        reg1, reg2 = (ra["chrom"], ra["start"], ra["end"]), (rb["chrom"], rb["start"], rb["end"])
+        m = self.clr.matrix(sparse=True, balance=False).fetch(reg1, reg2).tocsr()
+        m.sort_indices()
+        nb1, nb2 = m.shape
+        nb = nb1 + nb2
+        indptr = np.concatenate([m.indptr, np.full(nb2, m.indptr[-1])]).astype(np.int32)
+        col = (m.indices.astype(np.int64) + nb1).astype(np.int32)
+        cnt = m.data
+        if not np.issubdtype(cnt.dtype, np.integer):
+            raise NotImplementedError("floating-point pixel counts are not supported by the CUDA path")
+        cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+
+        def both(colname):
+            f = self.clr.bins()[colname].fetch
+            return np.ascontiguousarray(np.concatenate([f(reg1).values, f(reg2).values]), dtype=np.float64)
+
+        weight = both(self.clr_weight_name) if self.clr_weight_name else None
+        cov = both(self.coverage_norm) if self.coverage_norm else None
+        exp = np.full(nb, self._expected_trans(name1, name2)) if self.expected is True else None
+        return nb, indptr, col, cnt, weight, exp, cov, False
+
     def _region_kwargs(self, name, flags):
+        if self.trans:
+            nb, indptr, col, cnt, weight, exp, cov, upper = self._trans_arrays(*name)
+            return dict(nb=nb, indptr=indptr, col=col, count=cnt, weight=weight, expected=exp, coverage=cov, ignore_diags=0,
+                        flags=flags & (_native.PUP_F_OOE | _native.PUP_F_NODIAG), upper=False)
         nb, indptr, col, cnt, weight, exp, cov, upper = self._region_arrays(name)
         return dict(nb=nb, indptr=indptr, col=col, count=cnt, weight=weight, expected=exp, coverage=cov,
                     ignore_diags=self.ignore_diags, flags=flags & (_native.PUP_F_OOE | _native.PUP_F_NODIAG), upper=upper)
@@ -857,7 +970,7 @@ class PileUpper:
         user callbacks and per-ROI stripes keep the host window builder."""
         if os.environ.get("PUP_DEVICE_WINDOWS", "1") == "0" or not _native.device_windows_supported():
             return False
-        if self.CC.kind != "bed" or self.local or self.store_stripes:
+        if self.CC.kind != "bed" or self.local or self.store_stripes or self.trans:
             return False
         if plan["modify"] is not None and plan["band_edges"] is None:
             return False
@@ -1070,7 +1183,7 @@ class PileUpper:
             pipe.submit(self._region_kwargs(b["name"], flags), (b["w_r0"], b["w_c0"], b["slot"]), target, after=after)
             n_roi = int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))) * b["targets"]
             if n_roi > 0:
-                logger.info(f"{(b['name'], b['name'])}: {n_roi}")
+                logger.info(f"{b['name'] if self.trans else (b['name'], b['name'])}: {n_roi}")
         pipe.finish()
         return pipe
 
@@ -1333,19 +1446,22 @@ class PileUpper:
             self._ident_index = pd.Series(np.arange(len(uniq), dtype=np.int64), index=uniq)
         if rw is None:
             return None
-        s = rw.sel
-        mi = pd.MultiIndex.from_arrays([s["chrom"].values, s["start"].values, s["end"].values])
-        return self._ident_index.reindex(mi).values.astype(np.int64)
+
+        def of(tab):
+            mi = pd.MultiIndex.from_arrays([tab["chrom"].values, tab["start"].values, tab["end"].values])
+            return self._ident_index.reindex(mi).values.astype(np.int64)
+
+        return of(rw.sel), (of(rw.sel2) if rw.sel2 is not rw.sel else of(rw.sel))
 
     def pileup_region(self, region1, region2=None, groupby=[], modify_2Dintervals_func=None, postprocess_func=None,
                       extra_sum_funcs=None):
         """Accumulated pile-ups of one view region: ``{"ROI": {group: pup}, "control": {...}}`` (coolpup.py:1285-1358)."""
-        if region2 is not None and region2 != region1:
-            raise NotImplementedError("trans pile-ups are not supported by the B200 path")
         if extra_sum_funcs:
             raise NotImplementedError("extra_sum_funcs callbacks are not supported by the B200 path")
+        if self.trans != (region2 is not None and region2 != region1):
+            raise ValueError("pileup_region: two different regions are needed exactly when trans=True")
         roi, ctrl = self._run(groupby, self.ignore_group_order, modify_2Dintervals_func, postprocess_func,
-                              regions=[region1])
+                              regions=[(region1, region2) if self.trans else region1])
         return {"ROI": roi, "control": ctrl}
 
     def pileupsWithControl(self, nproc=None, groupby=[], ignore_group_order=False, modify_2Dintervals_func=None,
@@ -1492,6 +1608,8 @@ class PileUpper:
     def pileupsByDistanceWithControl(self, nproc=None, distance_edges="default", groupby=[], ignore_group_order=False,
                                      dist=None):
         """By-distance wrapper (coolpup.py:1757-1833)."""
+        if self.trans:
+            raise ValueError("Cannot do by-distance pileups for trans")
         if self.local:
             raise ValueError("Cannot do by-distance pileups for local")
         bin_func = partial(bin_distance_intervals, band_edges=self._distance_edges(distance_edges))
@@ -1508,6 +1626,8 @@ class PileUpper:
     def pileupsByStrandByDistanceWithControl(self, nproc=None, distance_edges="default", groupby=[],
                                              ignore_group_order=False, dist=None):
         """By-strand-by-distance wrapper (coolpup.py:1835-1919)."""
+        if self.trans:
+            raise ValueError("Cannot do by-distance pileups for trans")
         bin_func = partial(bin_distance_intervals, band_edges=self._distance_edges(distance_edges))
         pups = self.pileupsWithControl(nproc=nproc, modify_2Dintervals_func=bin_func,
                                        groupby=["strand1", "strand2", "distance_band"] + groupby,
@@ -1595,7 +1715,7 @@ def pileup(clr, features, features_format="bed", view_df=None, expected_df=None,
     if expected_df is None:
         expected_value_col = None
     else:
-        need = ["region1", "region2", "dist", expected_value_col]
+        need = ["region1", "region2"] + ([] if trans else ["dist"]) + [expected_value_col]
         if not all(c in expected_df.columns for c in need):
             raise ValueError("provided expected is not valid")
     if mindist is None:

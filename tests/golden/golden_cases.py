@@ -90,6 +90,21 @@ CASES = {
                                                "flip_negative_strand": True}},
     "toy_zero_expected_one_region": {**TOY, "expected": "CN.mm9.toy_expected.tsv", "expected_zero": {"foo": [3]},
                                      "view_rows": [0], "kwargs": {**TOYKW, "ooe": True}},
+    # ---- trans (inter-chromosomal) pile-ups: rectangular region1 x region2 matrices, scalar expected, no diagonal
+    # mask (coolpup.py:652-680, 999-1005, 1126-1128, 1419-1426)
+    "toy_trans_raw": {**TOY, "kwargs": {"features_format": "bed", "flank": 2_000_000, "trans": True, "clr_weight_name": None}},
+    "toy_trans_strand": {**TOY, "kwargs": {"features_format": "bed", "flank": 2_000_000, "trans": True, "by_strand": True}},
+    "toy_trans_ctrl": {**TOY, "kwargs": {"features_format": "bed", "flank": 2_000_000, "trans": True, "nshifts": 2, "seed": 4}},
+    "toy_trans_expected_ooe": {**TOY, "expected": "toy_trans_expected.tsv",
+                               "kwargs": {"features_format": "bed", "flank": 3_000_000, "trans": True, "ooe": True}},
+    "toy_trans_notooe_flip": {**TOY, "expected": "toy_trans_expected.tsv",
+                              "kwargs": {"features_format": "bed", "flank": 2_000_000, "trans": True, "ooe": False,
+                                         "by_strand": True, "flip_negative_strand": True}},
+    "toy_trans_bywindow_rawcov": {**{k: v for k, v in TOY.items() if k != "view"},
+                                  "kwargs": {"features_format": "bed", "flank": 2_000_000, "trans": True, "by_window": True,
+                                             "clr_weight_name": None, "coverage_norm": True}},
+    "toy_trans_bedpe_ctrl": {**TOY, "features": "toy_trans.bedpe", "features_schema": "bedpe6",
+                             "kwargs": {"features_format": "bedpe", "flank": 1_000_000, "trans": True, "nshifts": 2, "seed": 12}},
     "scc1_ctcf_pairs_arms": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "view": "scc1_arms_view.bed",
                              "kwargs": dict(features_format="bed", clr_weight_name=None, flank=50_000, mindist=0, maxdist=2_000_000,
                                             nshifts=1, seed=4)},

@@ -79,8 +79,10 @@ def test_unsupported_features_raise():
     from coolpuppy_b200 import coolpup as cp
 
     clr, feats, kw = gu.case_inputs("toy_strand_balanced")
-    with pytest.raises(NotImplementedError):
-        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True)
+    with pytest.raises(ValueError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True, by_distance=True, view_df=kw["view_df"])
+    with pytest.raises(ValueError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True, local=True, view_df=kw["view_df"])
     with pytest.raises(NotImplementedError):
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1)
     with pytest.raises(ValueError):
