@@ -146,6 +146,14 @@ def device_windows_supported():
     return True
 
 
+def acc_has_inf(acc, W, n_slots):
+    """True when some pile-up sum of a torch accumulator is infinite (x / 0 pixels poison their cell)."""
+    import torch
+
+    stride = acc_stride(W)
+    return bool(torch.isinf(acc.view(int(n_slots), stride)[:, : int(W) * int(W)]).any().item())
+
+
 def make_pipeline(device, W, n_slots, flags):
     """The two-stream region pipeline (:mod:`coolpuppy_b200.pipeline`) on ``device``."""
     from .pipeline import RegionPipeline

@@ -296,7 +296,15 @@ class Cooler(_CoolerBase):
         return self._load_pixels()[2]
 
     def _bin_columns(self):
-        return self._root["bins"].keys()
+        stored = list(self._root["bins"].keys())
+        return stored + [k for k in self._cols if k not in stored]
+
+    def add_bin_column(self, name, values):
+        """Attach an in-memory bin column (e.g. computed coverage); the file is not modified."""
+        values = np.asarray(values)
+        if values.shape[0] != int(self._chrom_offset[-1]):
+            raise ValueError(f"bin column {name!r} has {values.shape[0]} rows, expected {int(self._chrom_offset[-1])}")
+        self._cols[name] = values
 
     def _bin_column(self, name):
         if name not in self._cols:
@@ -355,6 +363,9 @@ class MemCooler(_CoolerBase):
 
     def _bin_column(self, name):
         return self._cols[name]
+
+    def add_bin_column(self, name, values):
+        self._cols[name] = np.asarray(values)
 
 
 class ChromCooler(_CoolerBase):
@@ -424,6 +435,9 @@ class ChromCooler(_CoolerBase):
 
     def _bin_column(self, name):
         return self._cols[name]
+
+    def add_bin_column(self, name, values):
+        self._cols[name] = np.asarray(values)
 
     def _chrom_of(self, lo, hi):
         ci = int(np.searchsorted(self._chrom_offset, lo, side="right") - 1)

@@ -213,14 +213,14 @@ class CoordCreator:
         if self.kind == "bedpe" and self.nshifts > 0:
             df["kind"] = "ROI"
         if self.kind == "bed":
-            basechroms = set(df["chrom"])
+            basechroms = set(df["chrom"].unique().tolist())
         else:
             if self.local:
                 raise ValueError("Can't make local with both sides of loops defined")
             if self.trans:  # coolpup.py:341-345
                 basechroms = set(df["chrom1"].unique().tolist() + df["chrom2"].unique().tolist())
             else:
-                basechroms = set(df["chrom1"]).intersection(set(df["chrom2"]))
+                basechroms = set(df["chrom1"].unique().tolist()).intersection(set(df["chrom2"].unique().tolist()))
         self.basechroms = natsorted(list(basechroms))
         if isinstance(self.chroms, str) and self.chroms == "all":
             self.final_chroms = natsorted(list(basechroms))
@@ -520,11 +520,24 @@ class PileUpper:
             self.coverage_norm = "cov_cis_raw"
         elif self.coverage_norm == "total":
             self.coverage_norm = "cov_tot_raw"
+        if (self.coverage_norm in ("cov_cis_raw", "cov_tot_raw") and self.coverage_norm not in self.clr.bins().columns
+                and hasattr(self.clr, "add_bin_column")):
+            # the reference computes the coverage with cooltools and STORES it in the cooler (coolpup.py:955-963);
+            # here it is computed the same way (expected.coverage, pinned against cooltools-made columns) and kept in
+            # memory
+            from .expected import coverage as _coverage
+
+            try:
+                cis, tot = _coverage(self.clr, ignore_diags=self.ignore_diags)
+                self.clr.add_bin_column("cov_cis_raw", cis)
+                self.clr.add_bin_column("cov_tot_raw", tot)
+            except NotImplementedError:
+                pass
         if self.coverage_norm and self.coverage_norm not in self.clr.bins().columns:
             if self.coverage_norm in ("cov_cis_raw", "cov_tot_raw"):
                 raise NotImplementedError(
-                    f"{self.coverage_norm} is not stored in the cooler; computing and storing coverage "
-                    "(cooltools.coverage) is outside the B200 path -- run `cooltools coverage --store` first"
+                    f"{self.coverage_norm} is not stored in the cooler and this cooler object cannot take an in-memory "
+                    "column -- run `cooltools coverage --store` first"
                 )
             raise ValueError(f"coverage_norm {self.coverage_norm} not found in cooler bins")
         if self.coverage_norm and self.clr_weight_name:
@@ -1204,18 +1217,24 @@ class PileUpper:
         t1 = time.perf_counter()
         W, n_slots = job["W"], job["n_slots"]
         stride = _native.acc_stride(W)
-        exact = self._needs_exact_merge()
         acc = _native.alloc_accumulator(n_slots * stride, self._device)
         region_acc = {}
-        if on_device:
-            pipe = self._execute_device(job, acc, region_acc, exact, dist)
-        else:
-            pipe = self._execute_host(job, acc, region_acc, exact)
-        if exact:
-            for a in region_acc.values():
-                acc += a
+        execute = (lambda exact: self._execute_device(job, acc, region_acc, exact, dist)) if on_device else \
+                  (lambda exact: self._execute_host(job, acc, region_acc, exact))
+        pipe = execute(False)
         if dist is not None:
             dist.all_reduce(acc)
+        # x / 0 = +inf can only arise with ooe and a zero expected value; when one really occurred (it poisons the sum),
+        # the reference's merge quirk matters and the run is repeated with one accumulator per region (expected runs
+        # draw no random numbers, so the repetition sees the same windows)
+        exact = self._needs_exact_merge() and bool(_native.acc_has_inf(acc, W, n_slots))
+        if exact:
+            acc.zero_()
+            pipe = execute(True)
+            for a in region_acc.values():
+                acc += a
+            if dist is not None:
+                dist.all_reduce(acc)
         stream = _native.current_stream(self._device)
         out, used = self._export_used(acc, job, stream)
         t2 = time.perf_counter()

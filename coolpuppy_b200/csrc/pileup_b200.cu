@@ -2181,7 +2181,9 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     const int R = m->R, S = m->S;
     // one lane group per strip of the window; a band = the groups whose R x W fp64 tile rows fit PUP_TILE_KB
     const int n_groups = (W + 2 * R - 2) / R;  // ceil((W + R - 1) / R): a window touches at most that many strips
-    const int tile_kb = env_int("PUP_TILE_KB", 72);
+    // tile budget per CTA: 112 KB leaves two CTAs per SM; W = 203 then takes 3 row bands of 34 strips (measured on
+    // configs[4]: 12.4 ms per step against 18.1 ms with 72 KB / 5 bands and 20.9 ms with 96 KB)
+    const int tile_kb = env_int("PUP_TILE_KB", 112);
     // tile row stride: W plus PUP_TILE_PAD doubles (bank mapping of the rows a half-warp works on)
     const int TW = W + std::max(0, env_int("PUP_TILE_PAD", 0));
     int Gb = (int)std::min<int64_t>(n_groups, ((int64_t)tile_kb * 1024) / (8ll * TW * R));

@@ -102,3 +102,25 @@ def expected_cis_gpu(clr, view_df=None, clr_weight_name=None, ignore_diags=2, de
                 tab["balanced.avg"] = bs / nv
         rows.append(pd.DataFrame(tab))
     return pd.concat(rows, ignore_index=True)
+
+
+def coverage(clr, ignore_diags=2):
+    """Per-bin raw coverage ``(cov_cis_raw, cov_tot_raw)`` of a cooler (int64 arrays over all bins).
+
+    Restates ``cooltools.api.coverage.coverage(clr, ignore_diags=..., store=True)``, which the reference runs when
+    ``coverage_norm`` is requested and the columns are missing (``coolpup.py:955-963``): pixels closer to the diagonal
+    than ``ignore_diags`` bins are zeroed; every remaining pixel adds its count to both of its bins (``cov_tot_raw``),
+    cis pixels also to ``cov_cis_raw``.  (Here the columns are kept in memory instead of being written into the file.)
+    """
+    b1 = np.asarray(clr._bin1, dtype=np.int64)
+    b2 = np.asarray(clr._bin2, dtype=np.int64)
+    w = np.asarray(clr._count, dtype=np.float64).copy()
+    nbins = int(clr._chrom_offset[-1])
+    if ignore_diags:
+        w[np.abs(b1 - b2) < ignore_diags] = 0
+    chrom_of = np.searchsorted(clr._chrom_offset, np.arange(nbins), side="right") - 1
+    cis = chrom_of[b1] == chrom_of[b2]
+    tot = np.bincount(b1, weights=w, minlength=nbins) + np.bincount(b2, weights=w, minlength=nbins)
+    cisw = w * cis
+    cisc = np.bincount(b1, weights=cisw, minlength=nbins) + np.bincount(b2, weights=cisw, minlength=nbins)
+    return cisc[:nbins].astype(np.int64), tot[:nbins].astype(np.int64)

@@ -85,13 +85,17 @@ class Coords:
 
     def __init__(self, features, resolution, *, features_format="auto", flank=100000, chroms="all",
                  minshift=10**5, maxshift=10**6, nshifts=10, mindist="auto", maxdist=None, local=False,
-                 subset=0, seed=None):
+                 subset=0, seed=None, trans=False):
         df = features.copy()
         self.resolution = resolution
         self.flank = flank
         self.minshift, self.maxshift, self.nshifts = minshift, maxshift, nshifts
-        self.mindist = 2 * flank + 2 * resolution if mindist == "auto" else mindist  # 240-243
-        self.maxdist = np.inf if maxdist is None else maxdist  # 247-250
+        self.trans = trans
+        if isinstance(mindist, str) and mindist == "auto":  # 240-253: explicit distances are ignored for trans
+            self.mindist = 2 * flank + 2 * resolution
+        else:
+            self.mindist = 0 if trans else mindist
+        self.maxdist = np.inf if (maxdist is None or trans) else maxdist
         self.local = local
         if features_format in (None, "auto"):  # 260-277
             if all(c in df.columns for c in ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]):
@@ -130,7 +134,10 @@ class Coords:
         else:
             if local:
                 raise ValueError("Can't make local with both sides of loops defined")
-            base = set(df["chrom1"]).intersection(set(df["chrom2"]))
+            if trans:  # 341-345
+                base = set(df["chrom1"].unique().tolist() + df["chrom2"].unique().tolist())
+            else:
+                base = set(df["chrom1"]).intersection(set(df["chrom2"]))
         self.final_chroms = natsorted(base) if chroms == "all" else natsorted(set(chroms) & base)
         if not self.final_chroms:
             raise ValueError("No chromosomes are in common between the coordinate file and the cooler file")
@@ -161,6 +168,9 @@ class Coords:
         shift = np.random.randint(self.minshift, self.maxshift, ctrl.shape[0])
         sign = np.random.choice([-1, 1], ctrl.shape[0])
         shift = shift * sign
+        if self.trans:  # 397-407: a second shift is drawn for side 2, but the BIN columns all move by the first one (430-433)
+            np.random.randint(self.minshift, self.maxshift, ctrl.shape[0])
+            np.random.choice([-1, 1], ctrl.shape[0])
         dbin = np.round(shift / self.resolution).astype(int)
         for c in ("stBin1", "endBin1", "stBin2", "endBin2"):
             ctrl[c] = ctrl[c].values + dbin
@@ -211,6 +221,34 @@ class Coords:
                 fr = modify(fr)
             if len(fr):
                 yield fr
+
+
+def trans_frames(cc, region1, region2, control, modify=None):
+    """Frames of the 2-D intervals between two view regions on different chromosomes (coolpup.py:565-590, 652-680,
+    1330-1348): bedpe -- rows joining the regions in either stored orientation, concatenated, one control draw; bed --
+    ``itertools.product`` of the two feature lists, one single-row frame (and control draw) per pair."""
+    (c1, s1, e1), (c2, s2, e2) = region1, region2
+    df = cc.intervals
+    if cc.kind == "bedpe":
+        a = df[(df["chrom1"] == c1) & (df["chrom2"] == c2) & (df["start1"] >= s1) & (df["end1"] < e1)
+               & (df["start2"] >= s2) & (df["end2"] < e2)].reset_index(drop=True)
+        b = df[(df["chrom2"] == c1) & (df["chrom1"] == c2) & (df["start2"] >= s1) & (df["end2"] < e1)
+               & (df["start1"] >= s2) & (df["end1"] < e2)].reset_index(drop=True)
+        fr = cc.control_shifts(pd.concat([a, b]), cc.nshifts * control)
+        if modify is not None:
+            fr = modify(fr)
+        if len(fr):
+            yield fr
+        return
+    left = df[(df["chrom"] == c1) & (df["start"] >= s1) & (df["end"] < e1)].reset_index(drop=True).rename(columns=lambda c: c + "1")
+    right = df[(df["chrom"] == c2) & (df["start"] >= s2) & (df["end"] < e2)].reset_index(drop=True).rename(columns=lambda c: c + "2")
+    for x in range(len(left)):
+        for y in range(len(right)):
+            comb = pd.concat([left.iloc[[x]].reset_index(drop=True), right.iloc[[y]].reset_index(drop=True)], axis=1)
+            fr = cc.control_shifts(comb, cc.nshifts * control)
+            if modify is not None:
+                fr = modify(fr)
+            yield fr
 
 
 def band_annotator(edges):
@@ -296,7 +334,7 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
                   maxshift=10**6, nshifts=0, ooe=True, mindist="auto", maxdist=None, min_diag=2, subset=0,
                   by_window=False, by_strand=False, by_distance=False, groupby=[], ignore_group_order=False,
                   flip_negative_strand=False, local=False, coverage_norm=False, store_stripes=False, seed=None,
-                  max_windows_per_region=None):
+                  max_windows_per_region=None, trans=False):
     """Restatement of ``pileup()`` -> ``PileUpper.pileupsWith*Control`` (coolpup.py:1922-2279, 1360-1919).
 
     ``max_windows_per_region`` is NOT a reference feature: it truncates every
@@ -332,7 +370,11 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
 
     cc = Coords(features, resolution, features_format=features_format, flank=flank, chroms=chroms, minshift=minshift,
                 maxshift=maxshift, nshifts=nshifts, mindist=mindist, maxdist=maxdist, local=local, subset=subset,
-                seed=seed)
+                seed=seed, trans=trans)
+    if trans and by_distance:
+        raise ValueError("Cannot do by-distance pileups for trans")
+    if trans and local:
+        raise ValueError("Cannot do local with trans=True")
 
     # ---- PileUpper.__init__ (837-997)
     pad = flank // resolution
@@ -341,11 +383,15 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
     E = {}
     if expected:
         ex = expected_df[expected_df["region1"].isin(view["name"]) & expected_df["region2"].isin(view["name"])]
-        ex = ex[ex["region1"] == ex["region2"]].reset_index(drop=True)
         if control:  # 867-872
             control = False
-        for name in view["name"]:  # ExpectedSnipper.select: table row order (907-916)
-            E[name] = ex.loc[(ex["region1"] == name) & (ex["region2"] == name), expected_value_col].values.astype(float)
+        if trans:  # get_expected_trans (999-1005): one scalar per region pair
+            for _, row in ex.iterrows():
+                E[(row["region1"], row["region2"])] = float(row[expected_value_col])
+        else:
+            ex = ex[ex["region1"] == ex["region2"]].reset_index(drop=True)
+            for name in view["name"]:  # ExpectedSnipper.select: table row order (907-916)
+                E[name] = ex.loc[(ex["region1"] == name) & (ex["region2"] == name), expected_value_col].values.astype(float)
     extents = {}
     for _, r in view.iterrows():  # 922-925
         lo, hi = clr.extent((r["chrom"], r["start"], r["end"]))
@@ -426,7 +472,19 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
         return OracleResult([], {}, {}, {"W": W})
     region_out = {}
     window_log = {}
-    for rname, r in view.iterrows():
+    if trans:  # every pair of view regions on different chromosomes (1419-1426)
+        import itertools
+
+        for n1, n2 in itertools.combinations(view.index, 2):
+            ra, rb = view.loc[n1], view.loc[n2]
+            if ra["chrom"] == rb["chrom"]:
+                continue
+            region_out[(n1, n2)], window_log[(n1, n2)] = _pileup_region(
+                clr, cc, (n1, n2), ((ra["chrom"], ra["start"], ra["end"]), (rb["chrom"], rb["start"], rb["end"])),
+                (extents[n1], extents[n2]), control, modify_final, groupby, do_flip, ignore_group_order, dup_by_region,
+                E.get((n1, n2)) if expected else None, ooe, clr_weight_name, coverage_norm, min_diag, W, store_stripes,
+                max_windows_per_region, trans=True)
+    for rname, r in ([] if trans else view.iterrows()):
         region_out[rname], window_log[rname] = _pileup_region(
             clr, cc, rname, (r["chrom"], r["start"], r["end"]), extents[rname], control, modify_final, groupby,
             do_flip, ignore_group_order, dup_by_region, E.get(rname) if expected else None, ooe, clr_weight_name,
@@ -495,9 +553,20 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
 
 
 def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_flip, ignore_group_order,
-                   dup_by_region, E, ooe, weight_name, coverage_norm, ignore_diags, W, store_stripes, max_windows):
-    """``pileup_region`` = ``pos_stream`` -> ``_stream_snips`` -> ``accumulate_stream`` (coolpup.py:1285-1358)."""
-    lo_rel, hi_rel = extent
+                   dup_by_region, E, ooe, weight_name, coverage_norm, ignore_diags, W, store_stripes, max_windows,
+                   trans=False):
+    """``pileup_region`` = ``pos_stream`` -> ``_stream_snips`` -> ``accumulate_stream`` (coolpup.py:1285-1358).
+
+    ``trans``: ``region`` / ``extent`` are pairs (region1, region2); the matrix is the rectangular region1 x region2
+    block, ``E`` a scalar (1126-1128) and the diagonal mask is not applied (1141)."""
+    if trans:
+        (lo_rel, hi_rel), (lo_rel2, hi_rel2) = extent
+        region, region2 = region
+        nb2 = hi_rel2 - lo_rel2
+    else:
+        lo_rel, hi_rel = extent
+        lo_rel2, region2 = lo_rel, region
+        nb2 = hi_rel - lo_rel
     nb = hi_rel - lo_rel
     out = {"ROI": {}, "control": {}}
     log = {"st1": [], "st2": [], "kind": [], "flip": [], "group": []}
@@ -505,7 +574,8 @@ def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_
     empty = np.zeros((W, W))
     n_seen = 0
     stop = False
-    for fr in cc.region_frames(region, control, modify):
+    frames = trans_frames(cc, region, region2, control, modify) if trans else cc.region_frames(region, control, modify)
+    for fr in frames:
         cols = {c: fr[c].tolist() for c in fr.columns}  # to_dict(records) gives native python scalars
         nrow = len(fr)
         for i in range(nrow):
@@ -522,32 +592,37 @@ def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_
             log["flip"].append(int(flip))
             log["group"].append(key_repr(group))
             if bigdata is None:  # get_data (1024-1057) + NaN-weight masks (1081-1098)
-                chrom, start, end = region
-                bigdata = clr.matrix(sparse=True, balance=weight_name).fetch((chrom, start, end)).tocsr()
+                bigdata = clr.matrix(sparse=True, balance=weight_name).fetch(tuple(region), tuple(region2)).tocsr()
                 if weight_name:
-                    isnan = np.isnan(clr.bins()[weight_name].fetch((chrom, start, end)).values)
+                    isnan = np.isnan(clr.bins()[weight_name].fetch(tuple(region)).values)
+                    isnan2 = np.isnan(clr.bins()[weight_name].fetch(tuple(region2)).values)
                 else:
                     isnan = np.zeros(nb, dtype=bool)
-                cov = clr.bins()[coverage_norm].fetch((chrom, start, end)).values if coverage_norm else None
+                    isnan2 = np.zeros(nb2, dtype=bool)
+                cov = clr.bins()[coverage_norm].fetch(tuple(region)).values if coverage_norm else None
+                cov2 = clr.bins()[coverage_norm].fetch(tuple(region2)).values if coverage_norm else None
             # region-relative bins and bounds test (1105-1114)
             s1, e1 = rec["stBin1"] - lo_rel, rec["endBin1"] - lo_rel
-            s2, e2 = rec["stBin2"] - lo_rel, rec["endBin2"] - lo_rel
-            if s1 < 0 or e1 > nb or s2 < 0 or e2 > nb:
+            s2, e2 = rec["stBin2"] - lo_rel2, rec["endBin2"] - lo_rel2
+            if s1 < 0 or e1 > nb or s2 < 0 or e2 > nb2:
                 continue
             data = bigdata[s1:e1, s2:e2].toarray().astype(float)  # 1115-1121
             data[isnan[s1:e1], :] = np.nan  # 1122-1123
-            data[:, isnan[s2:e2]] = np.nan
+            data[:, isnan2[s2:e2]] = np.nan
             ii = np.arange(s1, e1)[:, None]
             jj = np.arange(s2, e2)[None, :]
             exp_data = None
-            if E is not None:  # expected_selections[region][s1:e1, s2:e2] = E[|i-j|] (1130-1133)
+            if E is not None and trans:  # np.full(data.shape, exp_value) (1126-1128)
+                exp_data = np.full(data.shape, E)
+            elif E is not None:  # expected_selections[region][s1:e1, s2:e2] = E[|i-j|] (1130-1133)
                 exp_data = E[np.abs(jj - ii)]
-            data[(jj - ii) < ignore_diags] = np.nan  # signed diagonal mask (1141-1149)
+            if not trans:
+                data[(jj - ii) < ignore_diags] = np.nan  # signed diagonal mask (1141-1149)
             snip = {"kind": rec["kind"], "group": group, "coordinates": [], "horizontal_stripe": [],
                     "vertical_stripe": [], "cov_start": np.zeros(W), "cov_end": np.zeros(W)}
             if coverage_norm:  # 1151-1153
                 snip["cov_start"] = cov[s1:e1]
-                snip["cov_end"] = cov[s2:e2]
+                snip["cov_end"] = cov2[s2:e2]
             if E is not None and ooe:  # 1154-1156
                 with np.errstate(divide="ignore", invalid="ignore"):
                     data = data / exp_data

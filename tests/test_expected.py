@@ -64,3 +64,14 @@ def test_expected_cis_gpu_matches_cooltools_table(fixtures_dir):
 
     clr, view, table = _inputs(fixtures_dir)
     _check(expected_cis_gpu(clr, view_df=view, clr_weight_name="weight", ignore_diags=2), table)
+
+
+def test_coverage_matches_cooltools_columns(fixtures_dir):
+    """expected.coverage (what the reference gets from cooltools.coverage when coverage_norm is requested,
+    coolpup.py:955-963) == the cov_cis_raw / cov_tot_raw columns cooltools stored in the reference's own fixture."""
+    from coolpuppy_b200.expected import coverage
+
+    clr = Cooler(os.path.join(fixtures_dir, "CN.mm9.1000kb.cool"))
+    cis, tot = coverage(clr, ignore_diags=2)
+    assert np.array_equal(cis, clr._bin_column("cov_cis_raw"))
+    assert np.array_equal(tot, clr._bin_column("cov_tot_raw"))

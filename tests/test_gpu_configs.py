@@ -129,3 +129,44 @@ def test_expected_cis_gpu_on_synthetic_genome(genome):
     assert np.array_equal(a["n_valid"].values, b["n_valid"].values)
     np.testing.assert_allclose(b["balanced.avg"].values, a["balanced.avg"].values, rtol=1e-10, equal_nan=True)
     np.testing.assert_allclose(b["count.sum"].values, a["count.sum"].values, rtol=1e-10, equal_nan=True)
+
+
+def test_by_window_with_thousands_of_features(genome):
+    """By-window pile-up (one group per feature, every window goes to both anchors' groups) with > 2000 features --
+    thousands of accumulator slots, most of them sparse -- against the oracle, on both window paths."""
+    import os
+
+    from coolpuppy_b200 import coolpup as cp
+    from oracle.pileup_oracle import key_repr, oracle_pileup
+    import pandas as pd
+
+    (clr, exp), sizes = genome
+    rng = np.random.default_rng(21)
+    rows = []
+    for c, L in sizes.items():
+        n = int(2300 * L / sum(sizes.values()))
+        pos = np.sort(rng.choice(np.arange(60_000, L - 70_000, 10_000), size=n, replace=False)) + rng.integers(0, 9_000, n)
+        rows.append(pd.DataFrame({"chrom": c, "start": pos, "end": pos + 500}))
+    feats = pd.concat(rows, ignore_index=True)
+    assert len(feats) > 2000
+    kw = dict(features_format="bed", flank=20_000, by_window=True, mindist=60_000, maxdist=130_000, clr_weight_name="weight")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = oracle_pileup(clr, feats, **kw).by_key()
+        for mode in ("1", "0"):
+            os.environ["PUP_DEVICE_WINDOWS"] = mode
+            try:
+                pups = cp.pileup(clr, feats, **kw)
+            finally:
+                os.environ.pop("PUP_DEVICE_WINDOWS", None)
+            assert cp._LAST_STATS["device_windows"] == (mode == "1")
+            keys = [repr((r.chrom, int(r.start), int(r.end))) if r.chrom != "all" else "all" for r in pups.itertuples()]
+            assert len(keys) > 2000 and set(keys) == set(ref)
+            for k, (_, row) in zip(keys, pups.iterrows()):
+                o = ref[k]
+                assert int(row["n"]) == int(o["n"])
+                assert np.array_equal(np.asarray(row["num"]), np.asarray(o["num"]))
+                a, b = np.asarray(row["data"], dtype=float), np.asarray(o["data"], dtype=float)
+                assert np.array_equal(np.isnan(a), np.isnan(b))
+                m = np.isfinite(b)
+                np.testing.assert_allclose(a[m], b[m], rtol=RTOL)

@@ -428,3 +428,51 @@ def test_async_upload_pipeline_matches_oracle():
         m = np.isfinite(ref_sum)
         assert np.array_equal(np.isinf(out["sum"]), np.isinf(ref_sum))
         np.testing.assert_allclose(out["sum"][m], ref_sum[m], rtol=RTOL, atol=1e-300)
+
+
+def test_legacy_goldens_statistically(fixtures_dir):
+    """BASELINE.json north_star names tests/loop_ref.np.txt and tests/bed2_ref.np.txt.  Both are Monte-Carlo outputs
+    of a pre-1.0 CLI (random control shifts; `bed2` and `subset` options that no longer exist), so the
+    GPU path with the options of their headers is compared statistically: loop_ref -- coverage_norm, nshifts 10,
+    unbalanced, mindist 0, pad 100 kb; bed2_ref -- CTCF+ sites (baselist) against CTCF- sites (bed2), both ordered:
+    the (+, -) orientation of an all-vs-all pile-up of the stranded union, a subset of the sites."""
+    _cuda()
+    import os
+
+    import pandas as pd
+
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.coolio import Cooler
+
+    clr = Cooler(os.path.join(fixtures_dir, "Scc1-control.10000.cool"))
+    loops = pd.read_csv(os.path.join(fixtures_dir, "CH12_loops_Rao.bed"), sep="\t", header=None).iloc[:, :6]
+    loops.columns = ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]
+    ref = np.loadtxt(os.path.join(fixtures_dir, "loop_ref.np.txt"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, loops, features_format="bedpe", clr_weight_name=None, flank=100_000, mindist=0, nshifts=10,
+                         seed=0, coverage_norm=True)  # the coverage columns are computed in memory (expected.coverage)
+    mine = np.asarray(pups["data"].iloc[0], dtype=float)
+    assert np.corrcoef(mine.ravel(), ref.ravel())[0, 1] > 0.9
+    assert abs(mine[10, 10] / ref[10, 10] - 1) < 0.15
+    assert np.median(np.abs(mine - ref) / ref) < 0.06
+
+    plus = pd.read_csv(os.path.join(fixtures_dir, "Bonev_CTCF+.bed"), sep="\t", header=None).iloc[:, :3]
+    minus = pd.read_csv(os.path.join(fixtures_dir, "Bonev_CTCF-.bed"), sep="\t", header=None).iloc[:, :3]
+    plus.columns = minus.columns = ["chrom", "start", "end"]
+    rng = np.random.default_rng(0)
+    plus = plus.iloc[np.sort(rng.choice(len(plus), 4000, replace=False))].assign(strand="+")
+    minus = minus.iloc[np.sort(rng.choice(len(minus), 4000, replace=False))].assign(strand="-")
+    both = pd.concat([plus, minus], ignore_index=True)
+    both = both[~both["chrom"].isin(["chrY", "chrM"])]
+    ref2 = np.loadtxt(os.path.join(fixtures_dir, "bed2_ref.np.txt"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, both, features_format="bed", clr_weight_name=None, flank=100_000, mindist=0, nshifts=10, seed=0,
+                         coverage_norm=True, by_strand=True)
+    row = pups[pups["orientation"] == "+-"].iloc[0]
+    mine2 = np.asarray(row["data"], dtype=float)
+    m = np.isfinite(mine2) & np.isfinite(ref2)
+    r2 = np.corrcoef(mine2[m], ref2[m])[0, 1]
+    print("bed2_ref: pearson", r2, "n", int(row["n"]), "centre", mine2[10, 10], ref2[10, 10])
+    assert r2 > 0.6  # a few thousand pairs of another random subset: the corner-stripe pattern, not the values
