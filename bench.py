@@ -413,6 +413,9 @@ def main():
             b, z = 0, 0
         cost.append(b)
         nnz_win.append(z)
+    if os.environ.get("PUP_BENCH_VERBOSE") and rank == 0:
+        sys.stderr.write(json.dumps({"algorithmic_bytes_by_chromosome": dict(zip(names, [int(c) for c in cost])),
+                                     "windows_by_chromosome": {c: len(windows[c]["r0"]) for c in names}}) + "\n")
     # one contiguous, equal-cost piece of the (chromosome, row anchor) sequence per rank (the product's sharding,
     # multigpu.contiguous_partition); the per-anchor cost model is rescaled to every chromosome's exact bytes
     arrs = []

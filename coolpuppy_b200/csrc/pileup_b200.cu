@@ -2094,7 +2094,13 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
 
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
-  const int ch = std::max(1, env_int("PUP_CHUNK", 32));
+  // windows per work item: 32, fewer when the call is small (at least ~4 items per resident CTA, so that a launch of
+  // a few thousand dense windows -- BASELINE configs[2] -- still keeps every SM busy)
+  int ch = std::max(1, env_int("PUP_CHUNK", 32));
+  if (env_int("PUP_CHUNK", 0) == 0) {
+    const int64_t per_item = n_win / (int64_t)(n_sm * 2 * 4);
+    ch = (int)std::max<int64_t>(4, std::min<int64_t>(32, per_item));
+  }
   uint64_t *keys_a, *keys_b;
   int32_t *slot_start, *nchunks, *chunk_start;
   int* counters;  // [0] main work counter, [1] dense-num work counter, [2] slow windows of this call
