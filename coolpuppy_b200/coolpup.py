@@ -1038,8 +1038,13 @@ class PileUpper:
         nf = 2 if plan["flip"] else 1
         nctrl = self.CC.nshifts if do_control else 0
         chrom_v, start_v, end_v = df["chrom"].values, df["start"].values, df["end"].values
-        items = []
-        for ri, name in enumerate(region_names):
+
+        def items():
+            """One item per view region, made while the GPU works on the previous ones."""
+            for ri, name in enumerate(region_names):
+                yield make_item(ri, name)
+
+        def make_item(ri, name):
             r = self.view_df.loc[name]
             m_ = (chrom_v == r["chrom"]) & (start_v >= r["start"]) & (end_v < r["end"])
             sel = df[m_]
@@ -1075,7 +1080,7 @@ class PileUpper:
                         fb = plan["flipby"]
                         table.is_dynamic(fb + "1")
                         it["flipval"] = np.ascontiguousarray(table.codes(fb + "1", sel[fb].to_numpy()), dtype=np.int32)
-            items.append(it)
+            return it
         flags = 0
         if self.expected is True and self.ooe:
             flags |= _native.PUP_F_OOE
@@ -1083,7 +1088,7 @@ class PileUpper:
             flags |= _native.PUP_F_EXPCTRL
         if self.coverage_norm:
             flags |= _native.PUP_F_COVERAGE
-        return dict(plan=plan, W=W, built=[], items=items, colspec=colspec, table=table, first={}, nk=nk, nf=nf,
+        return dict(plan=plan, W=W, built=[], items=items, need_rng=bool(nctrl), colspec=colspec, table=table, first={}, nk=nk, nf=nf,
                     n_keys=n_keys, n_slots=n_keys * nk * nf, flags=flags, do_control=bool(self.control), expctrl=expctrl,
                     region_names=region_names, imbalance=imbalance)
 
@@ -1097,17 +1102,16 @@ class PileUpper:
         pipe = _native.make_pipeline(self._device, W, n_slots, flags)
         s_rng = pipe.s_side
         s_rng.wait_stream(torch.cuda.current_stream(dev))
-        need_rng = any(len(it["segs"]) for it in job["items"])
-        rng = _native.DeviceRng(self._device, stream=s_rng.cuda_stream) if need_rng else None
+        rng = _native.DeviceRng(self._device, stream=s_rng.cuda_stream) if job["need_rng"] else None
         first = torch.full((job["n_keys"],), torch.iinfo(torch.int64).max, dtype=torch.int64, device=dev)
-        n_roi = torch.zeros(max(1, len(job["items"])), dtype=torch.int64, device=dev)
+        n_roi = torch.zeros(max(1, len(job["region_names"])), dtype=torch.int64, device=dev)
         pipe.s_prep.wait_stream(torch.cuda.current_stream(dev))
         edges = plan["band_edges"]
         edges = None if edges is None else np.ascontiguousarray(edges, dtype=np.float64)
         stride = _native.acc_stride(W)
         readies = []  # prepare-stream events of the regions submitted so far
         try:
-            for it in job["items"]:
+            for it in job["items"]():
                 dbin, shifts_ready = None, None
                 if rng is not None and len(it["segs"]):
                     with torch.cuda.stream(s_rng):
@@ -1171,9 +1175,9 @@ class PileUpper:
         job["first"] = {int(k): (int(fv[k] >> 62), int((fv[k] >> 40) & 0xFFFFF), int(fv[k] & ((1 << 40) - 1)))
                         for k in np.nonzero(fv != np.iinfo(np.int64).max)[0]}
         counts = n_roi.cpu().numpy()
-        for it in job["items"]:
-            if counts[it["index"]] > 0:
-                logger.info(f"{(it['name'], it['name'])}: {int(counts[it['index']])}")
+        for ri, name in enumerate(job["region_names"]):
+            if counts[ri] > 0:
+                logger.info(f"{(name, name)}: {int(counts[ri])}")
         return pipe
 
     def _execute_host(self, job, acc, region_acc, exact):

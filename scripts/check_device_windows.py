@@ -30,7 +30,7 @@ dev = torch.device("cuda", 0)
 rng = nat.DeviceRng(0)
 by_name = {b["name"]: b for b in host["built"]}
 bad = 0
-for it in job["items"]:
+for it in job["items"]():
     dbin = None
     if len(it["segs"]):
         dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)

@@ -169,7 +169,7 @@ def test_device_windows_equal_host_windows(name, parts):
     by_name = {b["name"]: b for b in host["built"]}
     edges = plan["band_edges"]
     edges = None if edges is None else np.ascontiguousarray(edges, dtype=np.float64)
-    for it in job["items"]:
+    for it in job["items"]():
         dbin = None
         if len(it["segs"]):
             dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)
@@ -262,7 +262,7 @@ def test_device_windows_at_bench_scale():
     dev = torch.device("cuda", 0)
     rng = nat.DeviceRng(0)
     by_name = {b["name"]: b for b in host["built"]}
-    for it in job["items"]:
+    for it in job["items"]():
         dbin = None
         if len(it["segs"]):
             dbin = torch.empty(int(it["total"]) * it["nctrl"], dtype=torch.int32, device=dev)
