@@ -67,6 +67,17 @@ class RegionWindows:
                              self.idx2[sel], None if self.distance is None else self.distance[sel], self.paired,
                              sel2=self.sel2)
 
+    def sizes(self):
+        """(rows, columns) of every window in bins: 2 * pad + 1 everywhere, or the features' own expanded sizes for
+        rescaled pile-ups (the random control shifts move a window, they do not resize it)."""
+        if self.paired:
+            s1 = (self.sel["endBin"].values - self.sel["stBin"].values).astype(np.int64)
+            s2 = (self.sel2["endBin"].values - self.sel2["stBin"].values).astype(np.int64)
+            return s1[self.idx1], s2[self.idx2]
+        s1 = (self.sel["endBin1"].values - self.sel["stBin1"].values).astype(np.int64)
+        s2 = (self.sel["endBin2"].values - self.sel["stBin2"].values).astype(np.int64)
+        return s1[self.idx1], s2[self.idx1]
+
     def column(self, name, swap=None):
         """Values of 2-D interval column ``name`` for every window.
 

@@ -15,6 +15,7 @@ PUP_F_EXPCTRL = 2
 PUP_F_COVERAGE = 4
 PUP_F_NODIAG = 8
 PUP_F_ASYNC = 16
+PUP_F_LOCAL = 32
 
 _LIB = None
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200.so")
@@ -24,7 +25,7 @@ SYMBOLS = [
     "pup_region_destroy", "pup_upload", "pup_expected_cis", "pup_pair_windows_count", "pup_pair_windows_fill",
     "pup_region_device_bytes", "pup_acc_stride", "pup_accumulate", "pup_accumulate_region", "pup_acc_export",
     "pup_last_launches", "pup_algorithmic_bytes", "pup_timing_enable", "pup_timing_read", "pup_stripes",
-    "pup_pair_windows_count_range", "pup_rng_create", "pup_rng_read", "pup_rng_destroy", "pup_control_shifts", "pup_pair_windows_device",
+    "pup_pair_windows_count_range", "pup_accumulate_rescaled", "pup_rng_create", "pup_rng_read", "pup_rng_destroy", "pup_control_shifts", "pup_pair_windows_device",
 ]
 
 
@@ -62,6 +63,7 @@ def lib():
     L.pup_acc_stride.argtypes = [C.c_int]
     L.pup_acc_stride.restype = i64
     L.pup_accumulate.argtypes = [vp, i64, vp, vp, vp, C.c_int, C.c_int, u32, vp, vp, C.POINTER(i64)]
+    L.pup_accumulate_rescaled.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_accumulate_region.argtypes = [C.c_int, i32, i64, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, C.c_int, C.c_int,
                                         C.c_int, u32, vp, vp, C.POINTER(i64)]
     L.pup_acc_export.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -189,6 +191,17 @@ class Region:
         check(lib().pup_accumulate(self._h, n, ptr(r0), ptr(c0), ptr(slot), int(W), int(n_slots),
                                    int(flags) & (PUP_F_EXPCTRL | PUP_F_COVERAGE | PUP_F_ASYNC), ptr(acc), stream,
                                    C.byref(nv) if want_n_valid else None))
+        return nv.value if want_n_valid else None
+
+    def accumulate_rescaled(self, r0, c0, h, w, slot, mode, rescale_size, n_slots, flags, acc, stream=0,
+                            want_n_valid=False):
+        """``pup_accumulate_rescaled``: windows ``[r0, r0 + h) x [c0, c0 + w)`` zoomed to ``rescale_size`` squared."""
+        n = int(r0.shape[0])
+        nv = C.c_int64(0)
+        check(lib().pup_accumulate_rescaled(self._h, n, ptr(r0), ptr(c0), ptr(h), ptr(w), ptr(slot), ptr(mode),
+                                            int(rescale_size), int(n_slots),
+                                            int(flags) & (PUP_F_COVERAGE | PUP_F_LOCAL | PUP_F_ASYNC), ptr(acc), stream,
+                                            C.byref(nv) if want_n_valid else None))
         return nv.value if want_n_valid else None
 
     def stripes(self, r0, c0, W, stream=0):

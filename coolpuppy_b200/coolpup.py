@@ -86,25 +86,39 @@ def assign_groups(intervals, groupby=[]):
     return intervals
 
 
+def _expand_scale(start, end, scale):
+    """``bioframe.expand(df, scale=scale)`` (third-party; restated from its source): grow every interval about its
+    midpoint to ``scale`` times its length, round half to even, keep the integer dtype."""
+    start = np.asarray(start)
+    end = np.asarray(end)
+    pads = 0.5 * (scale - 1) * (end - start)
+    return np.round(start - pads).astype(start.dtype), np.round(end + pads).astype(end.dtype)
+
+
 def expand(intervals, flank, resolution, rescale_flank=None):
-    """Window [exp_start, exp_end) around each feature centre (coolpup.py:78-91)."""
-    if rescale_flank is not None:
-        raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
+    """Window [exp_start, exp_end) around each feature centre, or the feature itself grown by ``rescale_flank`` of its
+    size on either side for rescaled pile-ups (coolpup.py:78-91)."""
     intervals = intervals.copy()
-    c = np.floor(intervals["center"] / resolution)
-    intervals["exp_start"] = c * resolution - flank
-    intervals["exp_end"] = (c + 1) * resolution + flank
+    if rescale_flank is None:
+        c = np.floor(intervals["center"] / resolution)
+        intervals["exp_start"] = c * resolution - flank
+        intervals["exp_end"] = (c + 1) * resolution + flank
+    else:
+        intervals["exp_start"], intervals["exp_end"] = _expand_scale(intervals["start"].values, intervals["end"].values,
+                                                                     2 * rescale_flank + 1)
     return intervals
 
 
 def expand2D(intervals, flank, resolution, rescale_flank=None):
     """Two-sided version of :func:`expand` (coolpup.py:94-115)."""
-    if rescale_flank is not None:
-        raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
     for side in ("1", "2"):
-        c = np.floor(intervals["center" + side] / resolution)
-        intervals["exp_start" + side] = c * resolution - flank
-        intervals["exp_end" + side] = (c + 1) * resolution + flank
+        if rescale_flank is None:
+            c = np.floor(intervals["center" + side] / resolution)
+            intervals["exp_start" + side] = c * resolution - flank
+            intervals["exp_end" + side] = (c + 1) * resolution + flank
+        else:
+            a, b = _expand_scale(intervals["start" + side].values, intervals["end" + side].values, 2 * rescale_flank + 1)
+            intervals["exp_start" + side], intervals["exp_end" + side] = a, b
     return intervals
 
 
@@ -146,8 +160,6 @@ class CoordCreator:
         self.maxshift = maxshift
         self.nshifts = nshifts
         self.trans = trans
-        if rescale_flank is not None:
-            raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
         if isinstance(mindist, str) and mindist == "auto":
             self.mindist = 2 * self.flank + 2 * self.resolution
         else:
@@ -190,7 +202,7 @@ class CoordCreator:
             assert all(c in df.columns for c in ["chrom", "start", "end"]), "Column names must include chrom, start, and end"
             df["chrom"] = df["chrom"].astype(str)
             df["center"] = (df["start"] + df["end"]) / 2
-            df = expand(df, flank, res)
+            df = expand(df, flank, res, self.rescale_flank)
         elif self.kind == "bedpe":
             assert all(
                 c in df.columns for c in ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]
@@ -201,7 +213,7 @@ class CoordCreator:
             df["distance"] = df["center2"] - df["center1"]
             ad = df["distance"].abs()
             df = df[(self.mindist <= ad) & (ad <= self.maxdist)].reset_index(drop=True)
-            df = expand2D(df, flank, res)
+            df = expand2D(df, flank, res, self.rescale_flank)
         else:
             raise ValueError('kind can only be "bed" or "bedpe"')
         self.intervals = df
@@ -455,10 +467,17 @@ class PileUpper:
         self.nproc = nproc
         self.ignore_group_order = False
         self._device = int(os.environ.get("LOCAL_RANK", "0")) if device is None else int(device)
-        if rescale:
-            raise NotImplementedError("rescaled pile-ups are not supported by the B200 path")
-        if self.CC.flank % self.resolution != 0:
+        if rescale:  # coolpup.py:970-975
+            if getattr(self, "rescale_flank", None) is None:
+                raise ValueError("Cannot use rescale without setting rescale_flank")
+            if rescale_size % 2 == 0:
+                raise ValueError("Please provide an odd rescale_size")
+            if store_stripes or self.trans:
+                raise NotImplementedError("rescaled pile-ups with store_stripes or trans are not supported by the B200 path")
+        elif self.CC.flank % self.resolution != 0:
             raise ValueError("flank must be a multiple of the cooler's bin size")  # reference fails on shape mismatch
+        elif getattr(self, "rescale_flank", None) is not None:
+            raise ValueError("rescale_flank without rescale=True gives windows of different sizes")
 
         if view_df is None:
             self.view_df = make_cooler_view(clr)
@@ -546,8 +565,12 @@ class PileUpper:
         self._cost_cache = {}
 
     # -- small reference-compatible helpers -------------------------------------------------------
+    def _out_size(self):
+        """Side of the output pile-up: rescale_size, or 2 * pad + 1 bins (make_outmap, coolpup.py:1007-1022)."""
+        return int(self.rescale_size) if self.rescale else 2 * self.pad_bins + 1
+
     def make_outmap(self):
-        return np.zeros((2 * self.pad_bins + 1, 2 * self.pad_bins + 1))
+        return np.zeros((self._out_size(), self._out_size()))
 
     def get_data(self, region1, region2=None):
         """Region matrix as scipy CSR (coolpup.py:1024-1057); the GPU path uses :meth:`_region_arrays` instead."""
@@ -684,7 +707,7 @@ class PileUpper:
             return self._cost_cache[name]
         r = self.view_df.loc[name]
         df = self.CC.intervals
-        W = 2 * self.pad_bins + 1
+        W = self._out_size()
         lo, hi = self.view_df_extents[name]
         nb = max(2, hi - lo)
         nnz = self._region_nnz(name)
@@ -794,7 +817,7 @@ class PileUpper:
     def _prepare(self, plan, regions=None, dist=None):
         """Host phase: window arrays, dense group keys and accumulator slots of my sharding units (no GPU needed)."""
         modify_2Dintervals_func = plan["modify"]
-        W = 2 * self.pad_bins + 1
+        W = self._out_size()
         table = _GroupTable(self.CC)
         region_names = self._unit_keys() if regions is None else list(regions)
         do_control = bool(self.control)
@@ -844,8 +867,14 @@ class PileUpper:
                 nb = hi_rel - lo_rel
                 r0 = rw.st1 - lo_rel
                 c0 = rw.st2 - lo_rel
-                valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
+                if self.rescale:  # windows of their features' own sizes (zoomed to rescale_size on the device)
+                    hh, ww = rw.sizes()
+                    valid = (r0 >= 0) & (r0 + hh <= nb) & (c0 >= 0) & (c0 + ww <= nb)
+                else:
+                    valid = (r0 >= 0) & (r0 + W <= nb) & (c0 >= 0) & (c0 + W <= nb)
             built.append(dict(index=ri, name=name, rw=rw, r0=r0, c0=c0, valid=valid, flip=flipf, cols=cols, pos0=pos0))
+            if self.rescale:
+                built[-1].update(h=hh, w=ww)
         # dense group keys: mixed radix over the group columns (identical on every rank), or the feature id (by-window)
         table.finalize(dist)
         if plan["by_window"]:
@@ -864,7 +893,9 @@ class PileUpper:
             n_keys *= int(radix)
         if n_keys >= 2**31:
             raise ValueError("too many possible groups for dense accumulator slots")
-        nk = 2 if do_control else 1
+        # kinds: ROI, and "control" when there are shifted controls -- or, for rescaled pile-ups with expected and
+        # ooe=False, the bare expected blocks, which are zoomed like snippets and therefore need slots of their own
+        nk = 2 if (do_control or (self.rescale and expctrl)) else 1
         nf = 2 if plan["flip"] else 1
         first = {}  # key -> (is_control_only, region index, position of the first valid emission)
         for b in built:
@@ -887,6 +918,17 @@ class PileUpper:
             b["w_c0"] = np.repeat(b["c0"], ntarget)
             b["key"] = key
             b["slot"] = (key * nk + kind) * nf + flip
+            if self.rescale:
+                b["w_h"], b["w_w"] = np.repeat(b["h"], ntarget), np.repeat(b["w"], ntarget)
+                b["mode"] = np.zeros(len(key), dtype=np.int64)
+                if expctrl:  # every snippet is followed by its expected block as a control snippet (coolpup.py:1135-1139)
+                    for f in ("w_r0", "w_c0", "w_h", "w_w"):
+                        b[f] = np.concatenate([b[f], b[f]])
+                    b["slot"] = np.concatenate([b["slot"], (key * nk + 1) * nf + flip])
+                    b["mode"] = np.concatenate([b["mode"], np.ones(len(key), dtype=np.int64)])
+                order = np.argsort(b["slot"], kind="stable")  # the rescale kernel flushes its tile when the slot changes
+                for f in ("w_r0", "w_c0", "w_h", "w_w", "slot", "mode"):
+                    b[f] = b[f][order]
             pos = np.repeat(b["pos0"], ntarget) * ntarget + np.tile(np.arange(ntarget), n)
             valid = np.repeat(b["valid"], ntarget)
             for ctrl_only, ok in ((0, valid & (kind == 0)), (1, valid & (kind != 0))):
@@ -905,6 +947,8 @@ class PileUpper:
             flags |= _native.PUP_F_COVERAGE
         if self.trans:
             flags |= _native.PUP_F_NODIAG  # no diagonal mask between chromosomes (coolpup.py:1141)
+        if self.rescale and self.local:
+            flags |= _native.PUP_F_LOCAL
         return dict(plan=plan, W=W, built=built, colspec=colspec, table=table, first=first, nk=nk, nf=nf, n_keys=n_keys,
                     n_slots=n_keys * nk * nf, flags=flags, do_control=do_control, expctrl=expctrl,
                     region_names=region_names, imbalance=imbalance)
@@ -983,7 +1027,7 @@ class PileUpper:
         user callbacks and per-ROI stripes keep the host window builder."""
         if os.environ.get("PUP_DEVICE_WINDOWS", "1") == "0" or not _native.device_windows_supported():
             return False
-        if self.CC.kind != "bed" or self.local or self.store_stripes or self.trans:
+        if self.CC.kind != "bed" or self.local or self.store_stripes or self.trans or self.rescale:
             return False
         if plan["modify"] is not None and plan["band_edges"] is None:
             return False
@@ -1007,7 +1051,7 @@ class PileUpper:
         """Host phase of the device-window path: per view region only the feature table is touched (window bins,
         centres, per-feature group-key parts, kept pairs per offset); windows, control shifts, slots and the
         first-appearance order of the groups are produced on the GPU."""
-        W = 2 * self.pad_bins + 1
+        W = self._out_size()
         table = _GroupTable(self.CC)
         df = self.CC.intervals
         region_names = list(self.view_df.index) if regions is None else list(regions)
@@ -1197,7 +1241,10 @@ class PileUpper:
                     hor, ver = region.stripes(np.ascontiguousarray(b["r0"][sel], dtype=np.int32),
                                               np.ascontiguousarray(b["c0"][sel], dtype=np.int32), W, stream=stream)
                     b["stripes"] = (sel, hor, ver)
-            pipe.submit(self._region_kwargs(b["name"], flags), (b["w_r0"], b["w_c0"], b["slot"]), target, after=after)
+            wins = (b["w_r0"], b["w_c0"], b["slot"])
+            if self.rescale:
+                wins += (b["w_h"], b["w_w"]) + ((b["mode"],) if job["expctrl"] else ())
+            pipe.submit(self._region_kwargs(b["name"], flags), wins, target, after=after)
             n_roi = int(np.count_nonzero(b["valid"] & (b["rw"].kind == 0))) * b["targets"]
             if n_roi > 0:
                 logger.info(f"{b['name'] if self.trans else (b['name'], b['name'])}: {n_roi}")
@@ -1311,7 +1358,7 @@ class PileUpper:
                     p["cov_start"] = np.zeros(W)
                     p["cov_end"] = np.zeros(W)
                 per_kind[kind] = p
-            if job["expctrl"] and 0 in per_kind:
+            if job["expctrl"] and not self.rescale and 0 in per_kind:
                 # bare expected blocks are Toeplitz, hence invariant under the anti-transpose flip
                 p = per_kind[0]
                 per_kind[1] = {"data": gather("exp_sum", key, 0), "num": gather("exp_num", key, 0), "n": p["n"],
@@ -1533,7 +1580,7 @@ class PileUpper:
         if not has_ctrl:
             del rows["control_n"], rows["control_num"]
         if self.store_stripes:  # coolpup.py:1556-1600
-            W = 2 * self.pad_bins + 1
+            W = self._out_size()
             cntr = W // 2
             rows["coordinates"], rows["horizontal_stripe"], rows["vertical_stripe"] = [], [], []
             with np.errstate(divide="ignore", invalid="ignore"):

@@ -1156,6 +1156,229 @@ __global__ void k_stripes(const StripeParams p, const int32_t* __restrict__ r0, 
   }
 }
 
+// ------------------------------------------------------------------------------------------ rescaled pile-ups
+// PileUpper._rescale_snip (coolpup.py:1193-1234): a window of its feature's own size h x w is zoomed to rs x rs with
+// cooltools' zoom_array -- scipy.ndimage.zoom(order=1) to the next multiple of rs, then block means -- once for the
+// snippet with NaN -> 0 and once for its NaN mask; output cells that any NaN touches become NaN.  The arithmetic of
+// scipy's NI_ZoomShift is mirrored exactly (validated bit for bit against scipy on the CPU, oracle/zoom_ref.py):
+//   out size n_tmp = rs * mult, mult = ceil(n / rs) when n > rs else 1;  coordinate cc = k * ((n - 1) / (n_tmp - 1));
+//   cc > n - 1 (rounding) -> the sample is the constant 0;  i0 = floor(cc), i1 = i0 + 1 mirrored at the edge
+//   (2n - 2 - i1), weights w0 = 1 - (cc - i0), w1 = 1 - w0;  sample = ((D[i0,j0]*wr0)*wc0 + (D[i0,j1]*wr0)*wc1) + ...
+struct ZoomPlan {
+  int i0, i1;
+  double w0, w1;  // both 0: the sample is the constant 0
+};
+
+__device__ __forceinline__ ZoomPlan zoom_plan_entry(int k, int n, int n_tmp) {
+  ZoomPlan z;
+  z.i0 = z.i1 = 0;
+  z.w0 = z.w1 = 0.0;
+  const double zf = n_tmp > 1 ? __ddiv_rn((double)(n - 1), (double)(n_tmp - 1)) : 1.0;
+  const double cc = __dmul_rn((double)k, zf);
+  if (cc < 0.0 || cc > (double)(n - 1)) return z;
+  const double fl = floor(cc);
+  const double x = __dsub_rn(cc, fl);
+  z.w0 = __dsub_rn(1.0, x);
+  z.w1 = __dsub_rn(1.0, z.w0);
+  if (n > 1) {
+    z.i0 = (int)fl;
+    z.i1 = z.i0 + 1;
+    if (z.i1 >= n) z.i1 = 2 * n - 2 - z.i1;
+  }
+  return z;
+}
+
+struct RescaleParams {
+  StripeParams sp;         // snippet semantics of the region (same as pup_stripes)
+  const double* expected;  // raw expected vector (mode-1 windows: the bare expected block as a snippet)
+  const double* coverage;  // or null
+  const int32_t *r0, *c0, *h, *w, *slot, *mode;
+  int64_t n_win;
+  int rs, n_slots, max_tmp;
+  unsigned flags;          // PUP_F_LOCAL, PUP_F_COVERAGE
+  double* scratch_d;       // [grid][max_cells]
+  uint8_t* scratch_m;      // [grid][max_cells]
+  int64_t max_cells;
+  double* acc;
+  int* work;               // [0] next window, [1] in-bounds windows
+};
+
+__global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int rs = p.rs, rs2 = rs * rs;
+  double* tsum = reinterpret_cast<double*>(smem_raw);
+  int* tnum = reinterpret_cast<int*>(tsum + rs2);
+  ZoomPlan* prow = reinterpret_cast<ZoomPlan*>(smem_raw + (((size_t)rs2 * 12 + 15) / 16) * 16);
+  ZoomPlan* pcol = prow + p.max_tmp;
+  __shared__ int s_win;
+  __shared__ int s_n;
+  const AccLayout L(rs);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double* D = p.scratch_d + (size_t)blockIdx.x * p.max_cells;
+  uint8_t* M = p.scratch_m + (size_t)blockIdx.x * p.max_cells;
+  for (int i = tid; i < rs2; i += nt) {
+    tsum[i] = 0.0;
+    tnum[i] = 0;
+  }
+  if (tid == 0) s_n = 0;
+  int cur_slot = -1;
+  auto flush = [&]() {
+    __syncthreads();
+    if (cur_slot >= 0) {
+      double* a = p.acc + (int64_t)cur_slot * L.stride;
+      for (int i = tid; i < rs2; i += nt) {
+        if (tsum[i] != 0.0) atomicAdd(a + i, tsum[i]);
+        if (tnum[i] != 0) atomicAdd(a + L.off_num + i, (double)tnum[i]);
+        tsum[i] = 0.0;
+        tnum[i] = 0;
+      }
+      if (tid == 0 && s_n) {
+        atomicAdd(a + L.off_n, (double)s_n);
+        s_n = 0;
+      }
+    }
+    __syncthreads();
+  };
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_win = atomicAdd(p.work, 1);
+    __syncthreads();
+    const int wi = s_win;
+    if (wi >= p.n_win) break;
+    const int r = p.r0[wi], c = p.c0[wi], hh = p.h[wi], ww = p.w[wi], sl = p.slot[wi];
+    const int md = p.mode ? p.mode[wi] : 0;
+    if (r < 0 || c < 0 || hh < 0 || ww < 0 || r + hh > p.sp.nb || c + ww > p.sp.nb || sl < 0 || sl >= p.n_slots) continue;
+    if (sl != cur_slot) {
+      flush();
+      cur_slot = sl;
+    }
+    if (tid == 0) {
+      s_n += 1;
+      atomicAdd(p.work + 1, 1);
+    }
+    const int cells = hh * ww;
+    // 1. the dense snippet exactly as _stream_snips builds it (NaN for masked bins / diagonals / expected)
+    bool some = false;
+    for (int idx = tid; idx < cells; idx += nt) {
+      const int di = idx / ww, dj = idx - di * ww;
+      double v;
+      if (md == 1) {
+        const int d = (c + dj) - (r + di);
+        v = p.expected[d < 0 ? -d : d];
+      } else {
+        v = snippet_pixel(p.sp, r + di, c + dj);
+      }
+      D[idx] = v;
+      some |= !isnan(v);
+    }
+    const int any = __syncthreads_or(some ? 1 : 0);
+    if (cells == 0 || !any) {  // size 0 or all NaN: the snippet is a block of zeros (coolpup.py:1212-1213)
+      for (int i = tid; i < rs2; i += nt) tnum[i] += 1;
+      continue;
+    }
+    // 2. local pile-ups are symmetrised before the zoom (1215-1220): nanmean of the snippet and its transpose
+    if ((p.flags & PUP_F_LOCAL) && hh == ww) {
+      for (int idx = tid; idx < cells; idx += nt) {
+        const int di = idx / ww, dj = idx - di * ww;
+        if (di < dj) {
+          const double a = D[idx], b = D[dj * ww + di];
+          double m;
+          if (isnan(a))
+            m = b;
+          else if (isnan(b))
+            m = a;
+          else
+            m = __ddiv_rn(__dadd_rn(a, b), 2.0);
+          D[idx] = m;
+          D[dj * ww + di] = m;
+        }
+      }
+      __syncthreads();
+    }
+    // 3. NaN mask, nan_to_num (NaN -> 0, +-inf -> +-DBL_MAX), zoom plans of both axes
+    for (int idx = tid; idx < cells; idx += nt) {
+      const double v = D[idx];
+      const bool isn = isnan(v);
+      M[idx] = isn ? 1 : 0;
+      if (isn)
+        D[idx] = 0.0;
+      else if (isinf(v))
+        D[idx] = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    }
+    const int mr = hh > rs ? (hh + rs - 1) / rs : 1, mc = ww > rs ? (ww + rs - 1) / rs : 1;
+    for (int k = tid; k < rs * mr; k += nt) prow[k] = zoom_plan_entry(k, hh, rs * mr);
+    for (int k = tid; k < rs * mc; k += nt) pcol[k] = zoom_plan_entry(k, ww, rs * mc);
+    __syncthreads();
+    // 4. every output cell: block mean (rows first, then columns, like np.mean over the split axes) of the
+    //    interpolated samples, for the data and for the mask
+    for (int cell = tid; cell < rs2; cell += nt) {
+      const int i = cell / rs, j = cell - i * rs;
+      double acc_d = 0.0, acc_m = 0.0;
+      for (int bj = 0; bj < mc; ++bj) {
+        const ZoomPlan zc = pcol[j * mc + bj];
+        double col_d = 0.0, col_m = 0.0;
+        for (int bi = 0; bi < mr; ++bi) {
+          const ZoomPlan zr = prow[i * mr + bi];
+          double t = 0.0, tm = 0.0;
+          if ((zr.w0 != 0.0 || zr.w1 != 0.0) && (zc.w0 != 0.0 || zc.w1 != 0.0)) {
+            const int a0 = zr.i0 * ww, a1 = zr.i1 * ww;
+            t = __dmul_rn(__dmul_rn(D[a0 + zc.i0], zr.w0), zc.w0);
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(D[a0 + zc.i1], zr.w0), zc.w1));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(D[a1 + zc.i0], zr.w1), zc.w0));
+            t = __dadd_rn(t, __dmul_rn(__dmul_rn(D[a1 + zc.i1], zr.w1), zc.w1));
+            tm = __dmul_rn(__dmul_rn((double)M[a0 + zc.i0], zr.w0), zc.w0);
+            tm = __dadd_rn(tm, __dmul_rn(__dmul_rn((double)M[a0 + zc.i1], zr.w0), zc.w1));
+            tm = __dadd_rn(tm, __dmul_rn(__dmul_rn((double)M[a1 + zc.i0], zr.w1), zc.w0));
+            tm = __dadd_rn(tm, __dmul_rn(__dmul_rn((double)M[a1 + zc.i1], zr.w1), zc.w1));
+          }
+          col_d = __dadd_rn(col_d, t);
+          col_m = __dadd_rn(col_m, tm);
+        }
+        if (mr > 1) {
+          col_d = __ddiv_rn(col_d, (double)mr);
+          col_m = __ddiv_rn(col_m, (double)mr);
+        }
+        acc_d = __dadd_rn(acc_d, col_d);
+        acc_m = __dadd_rn(acc_m, col_m);
+      }
+      if (mc > 1) {
+        acc_d = __ddiv_rn(acc_d, (double)mc);
+        acc_m = __ddiv_rn(acc_m, (double)mc);
+      }
+      if (!(acc_m > 0.0)) {  // np.ceil(nanzoom).astype(bool): any NaN weight makes the cell NaN
+        if (isfinite(acc_d)) {
+          tsum[cell] += acc_d;
+          tnum[cell] += 1;
+        } else if (!isnan(acc_d)) {
+          tsum[cell] += acc_d;  // an infinite cell poisons the sum like in the reference (not counted in num)
+        }
+      }
+    }
+    // 5. coverage vectors are zoomed the same way in one dimension (1229-1233)
+    if ((p.flags & PUP_F_COVERAGE) && p.coverage != nullptr) {
+      double* a = p.acc + (int64_t)sl * L.stride;
+      for (int o = tid; o < 2 * rs; o += nt) {
+        const bool row = o < rs;
+        const int i = row ? o : o - rs;
+        const int n = row ? hh : ww, m = row ? mr : mc, base = row ? r : c;
+        const ZoomPlan* pl = row ? prow : pcol;
+        double v = 0.0;
+        for (int b = 0; b < m; ++b) {
+          const ZoomPlan z = pl[i * m + b];
+          double t = 0.0;
+          if (z.w0 != 0.0 || z.w1 != 0.0)
+            t = __dadd_rn(__dmul_rn(p.coverage[base + z.i0], z.w0), __dmul_rn(p.coverage[base + z.i1], z.w1));
+          v = __dadd_rn(v, t);
+        }
+        if (m > 1) v = __ddiv_rn(v, (double)m);
+        (void)n;
+        if (!isnan(v) && v != 0.0) atomicAdd(a + (row ? L.off_covs : L.off_cove) + i, v);
+      }
+    }
+  }
+  flush();
+}
+
 // ------------------------------------------------------------------------------------------ byte counter
 // Exact algorithmic pixel count of a window list (measurement helper, not on the timed path).
 __global__ void k_count_nnz(const Pix* __restrict__ pix, const int32_t* __restrict__ prow,
@@ -2472,6 +2695,109 @@ int pup_pair_windows_fill(int32_t m, const int64_t* stbin, const double* center,
       }
     }
     drawn += n * nctrl;
+  }
+  return PUP_OK;
+}
+
+int pup_accumulate_rescaled(const pup_region_t* m, int64_t n_win, const int32_t* r0, const int32_t* c0,
+                            const int32_t* h, const int32_t* w, const int32_t* slot, const int32_t* mode, int rescale_size,
+                            int n_slots, unsigned flags, double* acc, void* stream, int64_t* n_valid_out) {
+  if (!m) return fail(PUP_E_ARG, "pup_accumulate_rescaled: null region");
+  if (n_win < 0 || n_win >= (1ll << 31) || rescale_size <= 0 || rescale_size > 255 || n_slots <= 0 || !acc)
+    return fail(PUP_E_ARG, "pup_accumulate_rescaled: bad sizes or null accumulator");
+  if (n_win > 0 && (!r0 || !c0 || !h || !w || !slot)) return fail(PUP_E_ARG, "pup_accumulate_rescaled: null window arrays");
+  if (flags & ~(PUP_F_COVERAGE | PUP_F_LOCAL | PUP_F_ASYNC))
+    return fail(PUP_E_ARG, "pup_accumulate_rescaled: only PUP_F_COVERAGE / PUP_F_LOCAL / PUP_F_ASYNC apply");
+  const bool async = flags & PUP_F_ASYNC;
+  flags &= ~PUP_F_ASYNC;
+  if (async && n_valid_out) return fail(PUP_E_ARG, "pup_accumulate_rescaled: PUP_F_ASYNC cannot return n_valid");
+  if ((flags & PUP_F_COVERAGE) && !m->coverage) return fail(PUP_E_ARG, "pup_accumulate_rescaled: the region has no coverage");
+  if (mode && !m->expected) return fail(PUP_E_ARG, "pup_accumulate_rescaled: expected-block windows need a region with expected");
+  if (!is_device_ptr(acc)) return fail(PUP_E_ARG, "pup_accumulate_rescaled: the accumulator must be device memory");
+  DeviceGuard guard(m->device);
+  if (!guard.ok) return fail(PUP_E_NODEV, "pup_accumulate_rescaled: cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launches = 0;
+  if (n_valid_out) *n_valid_out = 0;
+  if (n_win == 0) return PUP_OK;
+  Scratch tmp(st);
+  // the window arrays are small next to the snippets: staged from host memory when needed; their maxima size the
+  // per-CTA scratch, so host copies are required (device arrays are read back)
+  std::vector<int32_t> hh((size_t)n_win), hw((size_t)n_win);
+  auto to_host = [&](const int32_t* src, int32_t* dst) -> cudaError_t {
+    if (!is_device_ptr(src)) {
+      memcpy(dst, src, (size_t)n_win * 4);
+      return cudaSuccess;
+    }
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)n_win * 4, cudaMemcpyDeviceToHost, st);
+    return e == cudaSuccess ? cudaStreamSynchronize(st) : e;
+  };
+  CK(to_host(h, hh.data()));
+  CK(to_host(w, hw.data()));
+  int64_t max_cells = 1;
+  int max_side = 1;
+  for (int64_t i = 0; i < n_win; ++i) {
+    if (hh[(size_t)i] < 0 || hw[(size_t)i] < 0) continue;
+    max_cells = std::max<int64_t>(max_cells, (int64_t)hh[(size_t)i] * hw[(size_t)i]);
+    max_side = std::max(max_side, std::max(hh[(size_t)i], hw[(size_t)i]));
+  }
+  const int rs = rescale_size;
+  const int max_tmp = rs * std::max(1, (max_side + rs - 1) / rs);
+  const size_t smem = (((size_t)rs * rs * 12 + 15) / 16) * 16 + 2 * (size_t)max_tmp * sizeof(ZoomPlan);
+  if (smem > 220 * 1024) return fail(PUP_E_ARG, "pup_accumulate_rescaled: windows too large for the zoom plans in shared memory");
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
+  const int grid = (int)std::min<int64_t>(n_win, n_sm);
+  if ((int64_t)grid * max_cells * 9 > (48ll << 30)) return fail(PUP_E_OOM, "pup_accumulate_rescaled: snippet scratch too large");
+  const int32_t *d_r0 = r0, *d_c0 = c0, *d_h = h, *d_w = w, *d_slot = slot, *d_mode = mode;
+  bool host_inputs = false;
+  auto stage = [&](const int32_t*& d, const int32_t* src) -> cudaError_t {
+    if (!src || is_device_ptr(src)) return cudaSuccess;
+    host_inputs = true;
+    int32_t* t;
+    cudaError_t e = tmp.alloc((void**)&t, (size_t)n_win * 4);
+    if (e != cudaSuccess) return e;
+    d = t;
+    return cudaMemcpyAsync(t, src, (size_t)n_win * 4, cudaMemcpyHostToDevice, st);
+  };
+  CK(stage(d_r0, r0));
+  CK(stage(d_c0, c0));
+  CK(stage(d_h, h));
+  CK(stage(d_w, w));
+  CK(stage(d_slot, slot));
+  CK(stage(d_mode, mode));
+  RescaleParams rp;
+  rp.sp = StripeParams{m->pix, m->prow, m->bad, (m->flags & PUP_F_OOE) ? m->expected : nullptr, m->nb, rs,
+                       m->ignore_diags, m->lr, m->flags};
+  rp.expected = m->expected;
+  rp.coverage = m->coverage;
+  rp.r0 = d_r0;
+  rp.c0 = d_c0;
+  rp.h = d_h;
+  rp.w = d_w;
+  rp.slot = d_slot;
+  rp.mode = d_mode;
+  rp.n_win = n_win;
+  rp.rs = rs;
+  rp.n_slots = n_slots;
+  rp.max_tmp = max_tmp;
+  rp.flags = flags;
+  rp.max_cells = max_cells;
+  rp.acc = acc;
+  CK(tmp.alloc((void**)&rp.scratch_d, (size_t)grid * max_cells * 8));
+  CK(tmp.alloc((void**)&rp.scratch_m, (size_t)grid * max_cells));
+  CK(tmp.alloc((void**)&rp.work, 16));
+  CK(zero_async(rp.work, 16, st));
+  CK(cudaFuncSetAttribute(k_rescale, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_rescale<<<grid, 256, smem, st>>>(rp);
+  LAUNCH_CHECK("k_rescale");
+  if (n_valid_out) {
+    int32_t nv = 0;
+    CK(cudaMemcpyAsync(&nv, rp.work + 1, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_valid_out = nv;
+  } else if (host_inputs && !async) {
+    CK(cudaStreamSynchronize(st));
   }
   return PUP_OK;
 }

@@ -129,8 +129,13 @@ class RegionPipeline:
         region, wins, ready, acc, after = item
         torch = self.torch
         self.s_comp.wait_event(ready)
-        r0, c0, slot = wins
-        if r0.shape[0]:
+        r0, c0, slot = wins[:3]
+        if r0.shape[0] and len(wins) >= 5:  # rescaled pile-up: windows of their own sizes, zoomed to W x W
+            mode = wins[5] if len(wins) == 6 else None  # only with bare expected blocks as control snippets
+            region.accumulate_rescaled(r0, c0, wins[3], wins[4], slot, mode, self.W, self.n_slots,
+                                       self.flags | _native.PUP_F_ASYNC, acc, stream=self.s_comp.cuda_stream)
+            self.launches += int(_native.lib().pup_last_launches())
+        elif r0.shape[0]:
             region.accumulate(r0, c0, slot, self.W, self.n_slots, self.flags | _native.PUP_F_ASYNC, acc,
                               stream=self.s_comp.cuda_stream)
             self.launches += int(_native.lib().pup_last_launches())

@@ -54,6 +54,7 @@ extern "C" {
 #define PUP_F_EXPCTRL 2u  /* also accumulate the bare expected block per window (coolpup.py:1135-1139, 1190-1191) */
 #define PUP_F_COVERAGE 4u /* accumulate cov_start / cov_end                      (coolpup.py:1151-1153) */
 #define PUP_F_NODIAG 8u   /* do NOT apply the signed diagonal mask (trans; unused by the cis path) */
+#define PUP_F_LOCAL 32u   /* pup_accumulate_rescaled: symmetrise every snippet before the zoom (local pile-ups, coolpup.py:1215-1220) */
 #define PUP_F_ASYNC 16u   /* pup_region_create / pup_accumulate with HOST input buffers: do not synchronise the
                              stream before returning; the caller keeps the (pinned) buffers alive and unchanged until
                              the stream has passed this call.  Lets uploads of region k+1 overlap the pile-up of k. */
@@ -151,6 +152,24 @@ int pup_accumulate_region(int device, int32_t nb, int64_t nnz, const int32_t* in
  */
 int pup_acc_export(const double* acc, int W, int n_slots, int device, void* stream, double* sum, int64_t* num,
                    int64_t* n, double* cov_start, double* cov_end, double* exp_sum, int64_t* exp_num);
+
+/*
+ * Rescaled pile-ups (PileUpper._rescale_snip, coolpup.py:1193-1234, for the windows of expand(.., rescale_flank),
+ * 87-90, 108-114): window i is the h[i] x w[i] block at (r0[i], c0[i]) -- sizes differ per window -- built exactly as
+ * _stream_snips builds a snippet (NaN for masked bins, masked diagonals, NaN expected; x / 0 = inf), optionally
+ * symmetrised (PUP_F_LOCAL), then zoomed to rescale_size x rescale_size like cooltools.numutils.zoom_array
+ * (scipy.ndimage.zoom(order=1) to the next multiple of rescale_size, block means; scipy's coordinate / weight
+ * arithmetic is mirrored exactly), once for the snippet with NaN -> 0 and once for its NaN mask; output cells any NaN
+ * touches are NaN (not summed, not counted), a snippet that is empty or all NaN counts as a block of zeros.
+ * mode[i] = 1 (mode may be NULL): the snippet is the bare expected block E[|col - row|] instead of the matrix (the
+ * "control" snippets of expected with ooe = False); needs a region created with an expected vector.
+ * Accumulators: the layout of pup_acc_stride(rescale_size); sum and num (whole counts) per slot, n, and with
+ * PUP_F_COVERAGE the zoomed coverage vectors.  Windows must be grouped by slot for speed (not for correctness).
+ * r0 .. mode: host or device int32 arrays; acc: device memory.  Windows outside the region are dropped.
+ */
+int pup_accumulate_rescaled(const pup_region_t* region, int64_t n_win, const int32_t* r0, const int32_t* c0,
+                            const int32_t* h, const int32_t* w, const int32_t* slot, const int32_t* mode, int rescale_size,
+                            int n_slots, unsigned flags, double* acc, void* stream, int64_t* n_valid_out);
 
 /*
  * store_stripes (coolpup.py:1164-1169): for every window the centre row `data[W/2, :]` ("horizontal") and the

@@ -72,6 +72,57 @@ def expand_windows(center, flank, resolution):
     return exp_start, exp_end
 
 
+def expand_scale(start, end, scale):
+    """``bioframe.expand(df, scale=scale)`` as called by coolpup.py:87-90, 108-114 (third-party, restated from its source
+    as remembered: grow about the midpoint to ``scale`` times the length, ``DataFrame.round`` = half to even, cast back to
+    the integer dtype).  No artefact in the reference tree pins it."""
+    start, end = np.asarray(start), np.asarray(end)
+    pads = 0.5 * (scale - 1) * (end - start)
+    return np.round(start - pads).astype(start.dtype), np.round(end + pads).astype(end.dtype)
+
+
+def zoom_array(in_array, final_shape):
+    """``cooltools.lib.numutils.zoom_array`` (third-party; called by coolpup.py:1223-1233), restated from its source as
+    remembered; ``scipy.ndimage.zoom`` is the installed scipy."""
+    from scipy.ndimage import zoom
+
+    in_array = np.asarray(in_array, dtype=np.double)
+    mults = [int(np.ceil(i / f)) if f < i else 1 for i, f in zip(in_array.shape, final_shape)]
+    temp_shape = tuple(f * m for f, m in zip(final_shape, mults))
+    rescaled = zoom(in_array, np.array(temp_shape) / np.array(in_array.shape) + 0.0000001, order=1)
+    for ind, mult in enumerate(mults):
+        if mult != 1:
+            sh = list(rescaled.shape)
+            rescaled.shape = sh[:ind] + [sh[ind] // mult, mult] + sh[ind + 1 :]
+            rescaled = np.mean(rescaled, axis=ind + 1)
+    return rescaled
+
+
+def rescale_snip(snip, rescale_size, local, coverage_norm):
+    """``PileUpper._rescale_snip`` (coolpup.py:1193-1234)."""
+    import warnings
+
+    data = snip["data"]
+    if data.size == 0 or np.all(np.isnan(data)):
+        snip["data"] = np.zeros((rescale_size, rescale_size))
+    else:
+        if local:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", category=RuntimeWarning)
+                data = np.nanmean(np.dstack((data, data.T)), 2)
+        nans = np.isnan(data) * 1
+        data = zoom_array(np.nan_to_num(data), (rescale_size, rescale_size))
+        nanzoom = zoom_array(nans, (rescale_size, rescale_size))
+        data[np.ceil(nanzoom).astype(bool)] = np.nan
+        with np.errstate(divide="ignore", invalid="ignore"):
+            data = data * (1 / np.isfinite(nanzoom))
+        snip["data"] = data
+    if coverage_norm:
+        snip["cov_start"] = zoom_array(snip["cov_start"], (rescale_size,))
+        snip["cov_end"] = zoom_array(snip["cov_end"], (rescale_size,))
+    return snip
+
+
 def to_bins(exp_start, exp_end, resolution):
     """stBin = floor(exp_start/res), endBin = ceil(exp_end/res) (coolpup.py:492-497, 503-514)."""
     return (
@@ -85,7 +136,7 @@ class Coords:
 
     def __init__(self, features, resolution, *, features_format="auto", flank=100000, chroms="all",
                  minshift=10**5, maxshift=10**6, nshifts=10, mindist="auto", maxdist=None, local=False,
-                 subset=0, seed=None, trans=False):
+                 subset=0, seed=None, trans=False, rescale_flank=None):
         df = features.copy()
         self.resolution = resolution
         self.flank = flank
@@ -114,7 +165,10 @@ class Coords:
         if self.kind == "bed":  # 284-294
             df["chrom"] = df["chrom"].astype(str)
             df["center"] = (df["start"] + df["end"]) / 2
-            df["exp_start"], df["exp_end"] = expand_windows(df["center"], flank, resolution)
+            if rescale_flank is None:
+                df["exp_start"], df["exp_end"] = expand_windows(df["center"], flank, resolution)
+            else:
+                df["exp_start"], df["exp_end"] = expand_scale(df["start"].values, df["end"].values, 2 * rescale_flank + 1)
         else:  # 295-321
             df[["chrom1", "chrom2"]] = df[["chrom1", "chrom2"]].astype(str)
             df["center1"] = (df["start1"] + df["end1"]) / 2
@@ -122,8 +176,12 @@ class Coords:
             df["distance"] = df["center2"] - df["center1"]
             df = df[(self.mindist <= df["distance"].abs()) & (df["distance"].abs() <= self.maxdist)]
             df = df.reset_index(drop=True)
-            df["exp_start1"], df["exp_end1"] = expand_windows(df["center1"], flank, resolution)
-            df["exp_start2"], df["exp_end2"] = expand_windows(df["center2"], flank, resolution)
+            for sd in ("1", "2"):
+                if rescale_flank is None:
+                    df["exp_start" + sd], df["exp_end" + sd] = expand_windows(df["center" + sd], flank, resolution)
+                else:
+                    df["exp_start" + sd], df["exp_end" + sd] = expand_scale(df["start" + sd].values, df["end" + sd].values,
+                                                                            2 * rescale_flank + 1)
         self.empty = df.shape[0] == 0  # 323-331
         if self.empty:
             self.final_chroms = []
@@ -334,7 +392,7 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
                   maxshift=10**6, nshifts=0, ooe=True, mindist="auto", maxdist=None, min_diag=2, subset=0,
                   by_window=False, by_strand=False, by_distance=False, groupby=[], ignore_group_order=False,
                   flip_negative_strand=False, local=False, coverage_norm=False, store_stripes=False, seed=None,
-                  max_windows_per_region=None, trans=False):
+                  max_windows_per_region=None, trans=False, rescale=False, rescale_flank=1, rescale_size=99):
     """Restatement of ``pileup()`` -> ``PileUpper.pileupsWith*Control`` (coolpup.py:1922-2279, 1360-1919).
 
     ``max_windows_per_region`` is NOT a reference feature: it truncates every
@@ -370,7 +428,9 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
 
     cc = Coords(features, resolution, features_format=features_format, flank=flank, chroms=chroms, minshift=minshift,
                 maxshift=maxshift, nshifts=nshifts, mindist=mindist, maxdist=maxdist, local=local, subset=subset,
-                seed=seed, trans=trans)
+                seed=seed, trans=trans, rescale_flank=rescale_flank if rescale else None)
+    if rescale and rescale_size % 2 == 0:
+        raise ValueError("Please provide an odd rescale_size")
     if trans and by_distance:
         raise ValueError("Cannot do by-distance pileups for trans")
     if trans and local:
@@ -378,7 +438,8 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
 
     # ---- PileUpper.__init__ (837-997)
     pad = flank // resolution
-    W = 2 * pad + 1
+    W = rescale_size if rescale else 2 * pad + 1
+    rescale_to = rescale_size if rescale else None
     expected = expected_df is not None and expected_df is not False
     E = {}
     if expected:
@@ -483,12 +544,12 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
                 clr, cc, (n1, n2), ((ra["chrom"], ra["start"], ra["end"]), (rb["chrom"], rb["start"], rb["end"])),
                 (extents[n1], extents[n2]), control, modify_final, groupby, do_flip, ignore_group_order, dup_by_region,
                 E.get((n1, n2)) if expected else None, ooe, clr_weight_name, coverage_norm, min_diag, W, store_stripes,
-                max_windows_per_region, trans=True)
+                max_windows_per_region, trans=True, rescale_to=rescale_to, local=local)
     for rname, r in ([] if trans else view.iterrows()):
         region_out[rname], window_log[rname] = _pileup_region(
             clr, cc, rname, (r["chrom"], r["start"], r["end"]), extents[rname], control, modify_final, groupby,
             do_flip, ignore_group_order, dup_by_region, E.get(rname) if expected else None, ooe, clr_weight_name,
-            coverage_norm, min_diag, W, store_stripes, max_windows_per_region)
+            coverage_norm, min_diag, W, store_stripes, max_windows_per_region, rescale_to=rescale_to, local=local)
 
     # ---- reduce over regions, keys in order of first appearance (1511-1531)
     def reduce_kind(kind):
@@ -554,7 +615,7 @@ def oracle_pileup(clr, features, features_format="bed", view_df=None, expected_d
 
 def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_flip, ignore_group_order,
                    dup_by_region, E, ooe, weight_name, coverage_norm, ignore_diags, W, store_stripes, max_windows,
-                   trans=False):
+                   trans=False, rescale_to=None, local=False):
     """``pileup_region`` = ``pos_stream`` -> ``_stream_snips`` -> ``accumulate_stream`` (coolpup.py:1285-1358).
 
     ``trans``: ``region`` / ``extent`` are pairs (region1, region2); the matrix is the rectangular region1 x region2
@@ -627,18 +688,27 @@ def _pileup_region(clr, cc, rname, region, extent, control, modify, groupby, do_
                 with np.errstate(divide="ignore", invalid="ignore"):
                     data = data / exp_data
             snip["data"] = data
+            exp_snip = None
+            if E is not None and not ooe:  # bare expected block as a control snippet (1135-1139)
+                exp_snip = dict(snip)
+                exp_snip["kind"] = "control"
+                exp_snip["data"] = exp_data
+                exp_snip["coordinates"] = []
+            if rescale_to is not None:  # 1159-1162
+                snip = rescale_snip(snip, rescale_to, local, coverage_norm)
+                if exp_snip is not None:
+                    exp_snip = rescale_snip(exp_snip, rescale_to, local, coverage_norm)
+                data = snip["data"]
             if store_stripes:  # 1164-1182
                 cntr = int(np.floor(data.shape[0] / 2))
                 snip["horizontal_stripe"] = np.array(data[cntr, :], dtype=float)
                 snip["vertical_stripe"] = np.array(data[:, cntr][::-1], dtype=float)
                 snip["coordinates"] = ".".join(str(rec[c]) for c in ("chrom1", "start1", "end1", "chrom2", "start2", "end2"))
             emitted = [snip]
-            if E is not None and not ooe:  # bare expected block as a control snippet (1135-1139, 1190-1191)
-                es = dict(snip)
-                es["kind"] = "control"
-                es["data"] = exp_data
-                es["coordinates"] = []
-                emitted.append(es)
+            if exp_snip is not None:  # yielded right after its snippet (1190-1191)
+                if not store_stripes:
+                    exp_snip["horizontal_stripe"], exp_snip["vertical_stripe"] = [], []
+                emitted.append(exp_snip)
             for s in emitted:
                 if do_flip and flip:  # flip_snip_func (128-147): anti-transpose, optional group swap
                     s["data"] = np.rot90(np.flipud(s["data"]))

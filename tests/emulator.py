@@ -10,7 +10,23 @@ import numpy as np
 
 from coolpuppy_b200 import _native
 
-F_OOE, F_EXPCTRL, F_COVERAGE, F_NODIAG = 1, 2, 4, 8
+F_OOE, F_EXPCTRL, F_COVERAGE, F_NODIAG, F_LOCAL = 1, 2, 4, 8, 32
+
+
+def zoom_array(in_array, final_shape):
+    """cooltools.lib.numutils.zoom_array with the real scipy.ndimage.zoom(order=1) (see oracle/refshim)."""
+    from scipy.ndimage import zoom
+
+    in_array = np.asarray(in_array, dtype=np.double)
+    mults = [int(np.ceil(i / f)) if f < i else 1 for i, f in zip(in_array.shape, final_shape)]
+    temp_shape = tuple(f * m for f, m in zip(final_shape, mults))
+    rescaled = zoom(in_array, np.array(temp_shape) / np.array(in_array.shape) + 0.0000001, order=1)
+    for ind, mult in enumerate(mults):
+        if mult != 1:
+            sh = list(rescaled.shape)
+            rescaled.shape = sh[:ind] + [sh[ind] // mult, mult] + sh[ind + 1 :]
+            rescaled = np.mean(rescaled, axis=ind + 1)
+    return rescaled
 
 
 def layout(W):
@@ -143,6 +159,65 @@ class EmuRegion:
                     N[di] += self.bad[c : c + W]
         return nv if want_n_valid else None
 
+    def _snippet(self, r, c, h, w):
+        """Dense snippet with the reference's NaN semantics (coolpup.py:1115-1156)."""
+        from scipy import sparse
+
+        if not hasattr(self, "_mat"):
+            self._mat = sparse.csr_matrix((self.count.astype(np.float64), self.col, self.indptr), shape=(self.nb, self.nb))
+        data = self._mat[r : r + h, c : c + w].toarray().astype(float)
+        if self.balanced:
+            data = (self.weight[r : r + h, None] * self.weight[None, c : c + w]) * data
+        data[self.bad[r : r + h], :] = np.nan
+        data[:, self.bad[c : c + w]] = np.nan
+        ii, jj = np.arange(r, r + h)[:, None], np.arange(c, c + w)[None, :]
+        if not (self.region_flags & F_NODIAG):
+            data[(jj - ii) < self.ignore_diags] = np.nan
+        if self.region_flags & F_OOE:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                data = data / self.expected[np.abs(jj - ii)]
+        return data
+
+    def accumulate_rescaled(self, r0, c0, h, w, slot, mode, rs, n_slots, flags, acc, stream=0, want_n_valid=False):
+        """_rescale_snip (coolpup.py:1193-1234) per window + accumulate, with scipy's zoom."""
+        import warnings
+
+        L = layout(rs)
+        a = (acc.numpy() if hasattr(acc, "numpy") else acc).reshape(n_slots, L["stride"])
+        nv = 0
+        for i in range(len(r0)):
+            r, c, hh, ww, s = int(r0[i]), int(c0[i]), int(h[i]), int(w[i]), int(slot[i])
+            if r < 0 or c < 0 or r + hh > self.nb or c + ww > self.nb or s < 0 or s >= n_slots:
+                continue
+            nv += 1
+            if mode is not None and int(mode[i]) == 1:
+                ii, jj = np.arange(r, r + hh)[:, None], np.arange(c, c + ww)[None, :]
+                data = self.expected[np.abs(jj - ii)].astype(float)
+            else:
+                data = self._snippet(r, c, hh, ww)
+            if data.size == 0 or np.all(np.isnan(data)):
+                data = np.zeros((rs, rs))
+            else:
+                if int(flags) & F_LOCAL:
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore", category=RuntimeWarning)
+                        data = np.nanmean(np.dstack((data, data.T)), 2)
+                nans = np.isnan(data) * 1
+                data = zoom_array(np.nan_to_num(data), (rs, rs))
+                nanzoom = zoom_array(nans, (rs, rs))
+                data[np.ceil(nanzoom).astype(bool)] = np.nan
+            A = a[s]
+            A[L["n"]] += 1
+            S = A[: L["w2"]].reshape(rs, rs)
+            N = A[L["num"] : L["num"] + L["w2"]].reshape(rs, rs)
+            fin = np.isfinite(data)
+            S += np.where(np.isnan(data), 0.0, data)
+            N += fin
+            if int(flags) & F_COVERAGE and hh > 0 and ww > 0:
+                A[L["covs"] : L["covs"] + rs] += np.nan_to_num(zoom_array(self.coverage[r : r + hh], (rs,)), nan=0.0)
+                A[L["cove"] : L["cove"] + rs] += np.nan_to_num(zoom_array(self.coverage[c : c + ww], (rs,)), nan=0.0)
+        return nv if want_n_valid else None
+
     def stripes(self, r0, c0, W, stream=0):
         n = len(r0)
         hor = np.full((n, W), np.nan)
@@ -214,8 +289,13 @@ class SerialPipeline:
 
     def submit(self, region_kwargs, windows, acc, after=None, windows_on_device=None):
         region = EmuRegion(0, **region_kwargs)
-        r0, c0, slot = windows
-        region.accumulate(np.asarray(r0), np.asarray(c0), np.asarray(slot), self.W, self.n_slots, self.flags, acc)
+        r0, c0, slot = windows[:3]
+        if len(windows) >= 5:
+            mode = np.asarray(windows[5]) if len(windows) == 6 else None
+            region.accumulate_rescaled(np.asarray(r0), np.asarray(c0), np.asarray(windows[3]), np.asarray(windows[4]),
+                                       np.asarray(slot), mode, self.W, self.n_slots, self.flags, acc)
+        else:
+            region.accumulate(np.asarray(r0), np.asarray(c0), np.asarray(slot), self.W, self.n_slots, self.flags, acc)
         if after is not None:
             after(region, 0)
         self.regions += 1

@@ -105,6 +105,26 @@ CASES = {
                                              "clr_weight_name": None, "coverage_norm": True}},
     "toy_trans_bedpe_ctrl": {**TOY, "features": "toy_trans.bedpe", "features_schema": "bedpe6",
                              "kwargs": {"features_format": "bedpe", "flank": 1_000_000, "trans": True, "nshifts": 2, "seed": 12}},
+    # ---- rescaled pile-ups: windows of the features' own sizes (+ rescale_flank of it on either side) zoomed to
+    # rescale_size x rescale_size (coolpup.py:1193-1234, 87-90, 108-114); "toy_sized_features.bed" = toy features 2-5 Mb long
+    "toy_rescale_local": {**TOY, "features": "toy_sized_features.bed",
+                          "kwargs": {"features_format": "bed", "local": True, "rescale": True, "rescale_flank": 1, "rescale_size": 9}},
+    "toy_rescale_pairs_strand": {**TOY, "features": "toy_sized_features.bed",
+                                 "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 0.5,
+                                            "rescale_size": 9, "by_strand": True}},
+    "toy_rescale_ooe": {**TOY, "features": "toy_sized_features.bed", "expected": "CN.mm9.toy_expected.tsv",
+                        "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 1, "rescale_size": 11,
+                                   "ooe": True}},
+    "toy_rescale_notooe_local": {**TOY, "features": "toy_sized_features.bed", "expected": "CN.mm9.toy_expected.tsv",
+                                 "kwargs": {"features_format": "bed", "local": True, "rescale": True, "rescale_flank": 1,
+                                            "rescale_size": 9, "ooe": False}},
+    "toy_rescale_cov_ctrl": {**TOY, "features": "toy_sized_features.bed",
+                             "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 0.3,
+                                        "rescale_size": 7, "clr_weight_name": None, "coverage_norm": True, "nshifts": 2, "seed": 3}},
+    "toy_rescale_up": {**TOY, "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 1, "rescale_size": 15}},
+    "scc1_tads_rescale_local": {**SCC1, "features": "CH12_TADs_Rao.bed", "features_schema": "bed3",
+                                "kwargs": dict(features_format="bed", clr_weight_name=None, local=True, rescale=True, rescale_flank=1,
+                                               rescale_size=99, subset=400, seed=1)},
     "scc1_ctcf_pairs_arms": {**SCC1, "features": "ctcf_stranded_chr18_19.bed", "features_schema": "bed6", "view": "scc1_arms_view.bed",
                              "kwargs": dict(features_format="bed", clr_weight_name=None, flank=50_000, mindist=0, maxdist=2_000_000,
                                             nshifts=1, seed=4)},

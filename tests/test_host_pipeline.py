@@ -84,7 +84,9 @@ def test_unsupported_features_raise():
     with pytest.raises(ValueError):
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, trans=True, local=True, view_df=kw["view_df"])
     with pytest.raises(NotImplementedError):
-        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1)
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1, store_stripes=True)
+    with pytest.raises(ValueError):
+        cp.pileup(clr, feats, features_format="bed", flank=2_000_000, rescale=True, rescale_flank=1, rescale_size=10)
     with pytest.raises(ValueError):
         cp.pileup(clr, feats, features_format="bed", flank=2_000_000, local=True, by_distance=True)
     with pytest.raises(ValueError):
