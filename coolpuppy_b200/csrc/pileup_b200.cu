@@ -1160,7 +1160,7 @@ __global__ void k_stripes(const StripeParams p, const int32_t* __restrict__ r0, 
 // PileUpper._rescale_snip (coolpup.py:1193-1234): a window of its feature's own size h x w is zoomed to rs x rs with
 // cooltools' zoom_array -- scipy.ndimage.zoom(order=1) to the next multiple of rs, then block means -- once for the
 // snippet with NaN -> 0 and once for its NaN mask; output cells that any NaN touches become NaN.  The arithmetic of
-// scipy's NI_ZoomShift is mirrored exactly (validated bit for bit against scipy on the CPU, oracle/zoom_ref.py):
+// scipy's NI_ZoomShift is mirrored exactly (validated bit for bit against scipy on the CPU, oracle/zoom_ref.py, tests/test_zoom_ref.py):
 //   out size n_tmp = rs * mult, mult = ceil(n / rs) when n > rs else 1;  coordinate cc = k * ((n - 1) / (n_tmp - 1));
 //   cc > n - 1 (rounding) -> the sample is the constant 0;  i0 = floor(cc), i1 = i0 + 1 mirrored at the edge
 //   (2n - 2 - i1), weights w0 = 1 - (cc - i0), w1 = 1 - w0;  sample = ((D[i0,j0]*wr0)*wc0 + (D[i0,j1]*wr0)*wc1) + ...
@@ -1272,10 +1272,15 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
       some |= !isnan(v);
     }
     const int any = __syncthreads_or(some ? 1 : 0);
+    const int mr = hh > rs ? (hh + rs - 1) / rs : 1, mc = ww > rs ? (ww + rs - 1) / rs : 1;
     if (cells == 0 || !any) {  // size 0 or all NaN: the snippet is a block of zeros (coolpup.py:1212-1213)
       for (int i = tid; i < rs2; i += nt) tnum[i] += 1;
-      continue;
-    }
+      if (!(p.flags & PUP_F_COVERAGE) || cells == 0) continue;
+      // the coverage vectors are zoomed all the same (1229-1233)
+      for (int k = tid; k < rs * mr; k += nt) prow[k] = zoom_plan_entry(k, hh, rs * mr);
+      for (int k = tid; k < rs * mc; k += nt) pcol[k] = zoom_plan_entry(k, ww, rs * mc);
+      __syncthreads();
+    } else {
     // 2. local pile-ups are symmetrised before the zoom (1215-1220): nanmean of the snippet and its transpose
     if ((p.flags & PUP_F_LOCAL) && hh == ww) {
       for (int idx = tid; idx < cells; idx += nt) {
@@ -1305,7 +1310,6 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
       else if (isinf(v))
         D[idx] = v > 0 ? 1.7976931348623157e308 : -1.7976931348623157e308;
     }
-    const int mr = hh > rs ? (hh + rs - 1) / rs : 1, mc = ww > rs ? (ww + rs - 1) / rs : 1;
     for (int k = tid; k < rs * mr; k += nt) prow[k] = zoom_plan_entry(k, hh, rs * mr);
     for (int k = tid; k < rs * mc; k += nt) pcol[k] = zoom_plan_entry(k, ww, rs * mc);
     __syncthreads();
@@ -1353,6 +1357,7 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
           tsum[cell] += acc_d;  // an infinite cell poisons the sum like in the reference (not counted in num)
         }
       }
+    }
     }
     // 5. coverage vectors are zoomed the same way in one dimension (1229-1233)
     if ((p.flags & PUP_F_COVERAGE) && p.coverage != nullptr) {

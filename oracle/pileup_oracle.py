@@ -802,3 +802,51 @@ def oracle_accumulate(nb, indptr, col, count, weight, expected, coverage, r0, c0
             out["cov_start"][s] = np.nansum([out["cov_start"][s], cv[s1 : s1 + W]], axis=0)
             out["cov_end"][s] = np.nansum([out["cov_end"][s], cv[s2 : s2 + W]], axis=0)
     return out
+
+
+def oracle_accumulate_rescaled(nb, indptr, col, count, weight, expected, coverage, r0, c0, h, w, slot, mode, rescale_size,
+                               ignore_diags, n_slots, ooe=False, local=False):
+    """What ``pup_accumulate_rescaled`` + ``pup_acc_export`` must return: ``_stream_snips`` (coolpup.py:1104-1157) over
+    windows of their own sizes ``h[i] x w[i]``, every snippet through ``_rescale_snip`` (1193-1234), then ``_add_snip``.
+    ``mode[i] == 1``: the snippet is the bare expected block (the control snippets of expected with ooe=False)."""
+    indptr = np.asarray(indptr)
+    mat = sparse.csr_matrix((np.asarray(count, dtype=np.float64), np.asarray(col), indptr), shape=(nb, nb))
+    if weight is not None:
+        wt = np.asarray(weight, dtype=np.float64)
+        coo = mat.tocoo()
+        coo.data = wt[coo.row] * wt[coo.col] * coo.data
+        mat = coo.tocsr()
+        isnan = np.isnan(wt)
+    else:
+        isnan = np.zeros(nb, dtype=bool)
+    rs = int(rescale_size)
+    out = {"sum": np.zeros((n_slots, rs, rs)), "num": np.zeros((n_slots, rs, rs), dtype=np.int64),
+           "n": np.zeros(n_slots, dtype=np.int64), "cov_start": np.zeros((n_slots, rs)), "cov_end": np.zeros((n_slots, rs))}
+    for i in range(len(r0)):
+        s1, s2, hh, ww, s = int(r0[i]), int(c0[i]), int(h[i]), int(w[i]), int(slot[i])
+        if s1 < 0 or s1 + hh > nb or s2 < 0 or s2 + ww > nb:
+            continue
+        ii = np.arange(s1, s1 + hh)[:, None]
+        jj = np.arange(s2, s2 + ww)[None, :]
+        if mode is not None and int(mode[i]) == 1:
+            data = np.asarray(expected, dtype=float)[np.abs(jj - ii)]
+        else:
+            data = mat[s1 : s1 + hh, s2 : s2 + ww].toarray().astype(float)
+            data[isnan[s1 : s1 + hh], :] = np.nan
+            data[:, isnan[s2 : s2 + ww]] = np.nan
+            data[(jj - ii) < ignore_diags] = np.nan
+            if ooe:
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    data = data / np.asarray(expected)[np.abs(jj - ii)]
+        snip = {"data": data}
+        if coverage is not None:
+            cv = np.asarray(coverage, dtype=float)
+            snip["cov_start"], snip["cov_end"] = cv[s1 : s1 + hh], cv[s2 : s2 + ww]
+        snip = rescale_snip(snip, rs, local, coverage is not None and hh > 0 and ww > 0)
+        out["sum"][s] = np.nansum([out["sum"][s], snip["data"]], axis=0)
+        out["num"][s] += np.isfinite(snip["data"])
+        out["n"][s] += 1
+        if coverage is not None and hh > 0 and ww > 0:
+            out["cov_start"][s] = np.nansum([out["cov_start"][s], snip["cov_start"]], axis=0)
+            out["cov_end"][s] = np.nansum([out["cov_end"][s], snip["cov_end"]], axis=0)
+    return out

@@ -456,3 +456,48 @@ def test_legacy_loop_ref_statistically(fixtures_dir):
     assert np.corrcoef(mine.ravel(), ref.ravel())[0, 1] > 0.9
     assert abs(mine[10, 10] / ref[10, 10] - 1) < 0.15
     assert np.median(np.abs(mine - ref) / ref) < 0.06
+
+
+@pytest.mark.parametrize("mode", ["raw", "balanced", "balanced_ooe", "balanced_expblocks", "raw_coverage", "raw_local"])
+@pytest.mark.parametrize("nb,rs,hmax,nwin,n_slots", [(300, 9, 40, 300, 3), (500, 11, 8, 400, 2), (900, 99, 260, 60, 2),
+                                                      (400, 7, 90, 200, 4)])
+def test_rescale_kernel_vs_oracle_random(mode, nb, rs, hmax, nwin, n_slots):
+    """pup_accumulate_rescaled on seeded random CSR + windows of random sizes (smaller and larger than rescale_size,
+    empty, outside the region, on the diagonal) == the per-window restatement with the real scipy zoom."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate_rescaled
+
+    ip, col, cnt, w, e, cov = random_region(nb, 60, seed=nb + rs, nan_frac=0.05, with_expected=True, with_cov=True)
+    e = np.where(np.isnan(e) | (e == 0), 1.0, e) if mode == "balanced_ooe" else e  # x / 0 = inf: the zoom would spread it
+    rng = np.random.default_rng(5 * nb + rs)
+    local = mode == "raw_local"
+    h = rng.integers(0 if hmax > 20 else 1, hmax, nwin).astype(np.int32)
+    wd = h.copy() if local else rng.integers(1, hmax, nwin).astype(np.int32)
+    r0 = rng.integers(-3, nb - 2, nwin).astype(np.int32)
+    c0 = r0.copy() if local else np.clip(r0 + rng.integers(-hmax, 3 * hmax, nwin), -2, nb).astype(np.int32)
+    sl = np.sort(rng.integers(0, n_slots, nwin)).astype(np.int32)
+    md = (rng.random(nwin) < 0.4).astype(np.int32) if mode == "balanced_expblocks" else None
+    weight = None if mode.startswith("raw") else w
+    expected = e if mode in ("balanced_ooe", "balanced_expblocks") else None
+    if md is not None:
+        expected = np.where(np.isnan(e), 0.5, e)
+    coverage = cov if mode == "raw_coverage" else None
+    ref = oracle_accumulate_rescaled(nb, ip, col, cnt, weight, expected, coverage, r0, c0, h, wd, sl, md, rs, 2, n_slots,
+                                     ooe=mode == "balanced_ooe", local=local)
+    import torch
+
+    dev = torch.device("cuda", 0)
+    flags = (nat.PUP_F_OOE if mode == "balanced_ooe" else 0)
+    reg = nat.Region(0, nb, ip, col, cnt, weight, expected, coverage, ignore_diags=2, flags=flags)
+    acc = torch.zeros(n_slots * nat.acc_stride(rs), dtype=torch.float64, device=dev)
+    aflags = (nat.PUP_F_COVERAGE if coverage is not None else 0) | (nat.PUP_F_LOCAL if local else 0)
+    nv = reg.accumulate_rescaled(r0, c0, h, wd, sl, md, rs, n_slots, aflags, acc, want_n_valid=True)
+    out = nat.acc_export(acc, rs, n_slots, device=0, want_cov=coverage is not None)
+    reg.close()
+    assert nv == int(ref["n"].sum())
+    assert np.array_equal(out["n"], ref["n"])
+    assert np.array_equal(out["num"], ref["num"])
+    np.testing.assert_allclose(out["sum"], ref["sum"], rtol=RTOL, atol=1e-300)
+    if coverage is not None:
+        np.testing.assert_allclose(out["cov_start"], ref["cov_start"], rtol=RTOL)
+        np.testing.assert_allclose(out["cov_end"], ref["cov_end"], rtol=RTOL)
