@@ -1203,7 +1203,7 @@ struct RescaleParams {
   int* work;               // [0] next window, [1] in-bounds windows
 };
 
-__global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
+__global__ void __launch_bounds__(1024) k_rescale(const RescaleParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rs = p.rs, rs2 = rs * rs;
   double* tsum = reinterpret_cast<double*>(smem_raw);
@@ -1257,19 +1257,71 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleParams p) {
       atomicAdd(p.work + 1, 1);
     }
     const int cells = hh * ww;
-    // 1. the dense snippet exactly as _stream_snips builds it (NaN for masked bins / diagonals / expected)
+    // 1. the dense snippet exactly as _stream_snips builds it: first what an UNSTORED pixel is -- 0, or NaN under a
+    //    masked bin, a masked diagonal, a NaN expected or 0 / 0 -- then the stored pixels of the window's strips,
+    //    streamed once (a per-cell lookup would binary-search the strip h * w times)
     bool some = false;
-    for (int idx = tid; idx < cells; idx += nt) {
-      const int di = idx / ww, dj = idx - di * ww;
-      double v;
-      if (md == 1) {
+    if (md == 1) {
+      for (int idx = tid; idx < cells; idx += nt) {
+        const int di = idx / ww, dj = idx - di * ww;
         const int d = (c + dj) - (r + di);
-        v = p.expected[d < 0 ? -d : d];
-      } else {
-        v = snippet_pixel(p.sp, r + di, c + dj);
+        const double v = p.expected[d < 0 ? -d : d];
+        D[idx] = v;
+        some |= !isnan(v);
       }
-      D[idx] = v;
-      some |= !isnan(v);
+    } else {
+      const double nan = __longlong_as_double(0x7ff8000000000000ll);
+      const bool ooe = (p.sp.flags & PUP_F_OOE) && p.sp.expected != nullptr;
+      const bool nodiag = p.sp.flags & PUP_F_NODIAG;
+      for (int idx = tid; idx < cells; idx += nt) {
+        const int di = idx / ww, dj = idx - di * ww;
+        const int row = r + di, col = c + dj, d = col - row;
+        double v = 0.0;
+        if (p.sp.bad != nullptr && (p.sp.bad[row] || p.sp.bad[col])) {
+          v = nan;
+        } else if (!nodiag && d < p.sp.ignore_diags) {
+          v = nan;
+        } else if (ooe) {
+          const double e = p.sp.expected[d < 0 ? -d : d];
+          if (isnan(e) || e == 0.0) v = nan;
+        }
+        D[idx] = v;
+        some |= !isnan(v);
+      }
+      __syncthreads();
+      if (cells > 0) {
+        const int lane = tid & 31, nwarps = nt >> 5;
+        const int s_hi = (r + hh - 1) >> p.sp.lr;
+        for (int s = (r >> p.sp.lr) + (tid >> 5); s <= s_hi; s += nwarps) {
+          int a = p.sp.prow[s], b = p.sp.prow[s + 1];
+          const int end = b;
+          while (a < b) {  // first record of the strip with col >= c (the same search in every lane)
+            const int mid = (a + b) >> 1;
+            if (__ldg(&p.sp.pix[mid].col) < c)
+              a = mid + 1;
+            else
+              b = mid;
+          }
+          for (int k = a + lane; k < end; k += 32) {
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(p.sp.pix + k));
+            const int col = raw.x;
+            if (col >= c + ww) break;  // the sentinels that close a strip end the run too
+            const int row = (s << p.sp.lr) + raw.y, di = row - r;
+            if (di < 0 || di >= hh) continue;
+            if (p.sp.bad != nullptr && (p.sp.bad[row] || p.sp.bad[col])) continue;
+            const int d = col - row;
+            if (!nodiag && d < p.sp.ignore_diags) continue;
+            const double v = __hiloint2double(raw.w, raw.z);
+            if (ooe) {
+              const double e = p.sp.expected[d < 0 ? -d : d];
+              if (isnan(e)) continue;
+              if (e == 0.0 && !isinf(v)) continue;  // x / 0 = inf, 0 / 0 = NaN
+            }
+            D[di * ww + (col - c)] = v;
+            some = true;
+          }
+        }
+      }
     }
     const int any = __syncthreads_or(some ? 1 : 0);
     const int mr = hh > rs ? (hh + rs - 1) / rs : 1, mc = ww > rs ? (ww + rs - 1) / rs : 1;
@@ -2794,8 +2846,11 @@ int pup_accumulate_rescaled(const pup_region_t* m, int64_t n_win, const int32_t*
   CK(tmp.alloc((void**)&rp.work, 16));
   CK(zero_async(rp.work, 16, st));
   CK(cudaFuncSetAttribute(k_rescale, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_rescale<<<grid, 256, smem, st>>>(rp);
-  LAUNCH_CHECK("k_rescale");
+  {
+    SpanGuard span(2, st);  // timing tag of the main kernel
+      k_rescale<<<grid, 1024, smem, st>>>(rp);
+    LAUNCH_CHECK("k_rescale");
+  }
   if (n_valid_out) {
     int32_t nv = 0;
     CK(cudaMemcpyAsync(&nv, rp.work + 1, 4, cudaMemcpyDeviceToHost, st));
