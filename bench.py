@@ -660,7 +660,7 @@ def main():
     except Exception:
         pass
     roofline = {
-        "kernel": "k_pileup_main", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "kernel": "k_pileup_main + k_pileup_dense (the pile-up phase: sparse strips + dense diagonal band)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "traffic_source": traffic_src,
         "algorithmic_bytes_per_step": int(tot_bytes), "algorithmic_bytes_per_launch": int(slow_b / max(1.0, slow_launches)),
         "kernel_ms_per_step": slow_ms, "launches_per_step": int(slow_launches),

@@ -16,6 +16,8 @@
 //       stream the strip's (col, q, val) records from `start` while col < c0 + W   # 16-byte loads, 4 windows in flight
 //       tile[G * R + q][col - c0] += val                   # fp64 shared-memory tile, race-free by row ownership
 //   flush tile rows (tile row t = window row di + r0 mod R) with red.global.add.f64 when the slot changes
+//   dense windows (k_pileup_dense): a window that lies inside the region's dense diagonal band is read cell by cell
+//       from the band and added to per-thread REGISTER tiles -- no scatter at all (break-even ~18 % occupancy)
 //
 // `num` (count of finite contributions) is dense in the reference (W*W work per window).  Here it is
 //   num = n_fast - rowbad[di] - colbad[dj] + xtile[di][dj]
@@ -246,6 +248,10 @@ struct pup_region {
   int32_t* badlist;   // sorted masked bins
   uint8_t* ebad;      // [nb] expected is NaN or 0
   int32_t* ebadpre;   // [nb+1] exclusive prefix of ebad
+  double* band;       // dense diagonal band: band[row * band_stride + (col - row)] = normalised value (0 when
+                      // unstored), for col - row in [0, *band_bw); null when the region has none
+  int32_t* band_bw;   // device scalar: number of diagonals the band holds (chosen on the device from the density)
+  int band_stride;    // row stride of band[] in doubles (the allocated width, >= *band_bw)
   cudaStream_t stream;
   int64_t bytes;
 };
@@ -537,13 +543,19 @@ __global__ void k_masks(const double* __restrict__ weight, const double* __restr
 // key = [invalid:1][slot][r0 mod R : lr][r0:pb][c0:pb]; out-of-region windows get all ones and sort last.
 // (slot, r0 mod R) is the "extended slot": all windows of one extended slot map matrix rows to tile rows the same
 // way (tile row = window row + r0 mod R), so the main kernel treats a change of either like a change of slot.
+// With a dense diagonal band (band_bw != null) the windows that lie entirely inside it form a second class, keyed as
+// slots [n_slots, 2 n_slots): they sort behind all other windows and are piled up by k_pileup_dense.
 __global__ void k_window_keys(const int32_t* __restrict__ r0, const int32_t* __restrict__ c0,
                               const int32_t* __restrict__ slot, uint64_t* __restrict__ keys, int64_t n, int nb, int W,
-                              int n_slots, int pb, int lr) {
+                              int n_slots, int pb, int lr, const int32_t* __restrict__ band_bw) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int r = r0[i], c = c0[i], s = slot[i];
   bool ok = r >= 0 && c >= 0 && r + W <= nb && c + W <= nb && s >= 0 && s < n_slots;
+  if (band_bw != nullptr) {
+    const int bw = __ldg(band_bw), D0 = c - r;
+    if (D0 - (W - 1) >= 0 && D0 + (W - 1) < bw) s += n_slots;
+  }
   const uint64_t es = ((uint64_t)s << lr) | (uint64_t)(r & ((1 << lr) - 1));
   keys[i] = ok ? ((es << (2 * pb)) | ((uint64_t)r << pb) | (uint64_t)c) : ~0ull;
 }
@@ -590,6 +602,7 @@ struct WinCtx {
   int nb, W, pb, lr, ignore_diags;
   unsigned flags;
   const int32_t* ebadpre;
+  int n_slots;  // accumulator slots; keyed slots [n_slots, 2 n_slots) are the dense-band class of the same slots
 };
 
 // sorted key -> accumulator slot (the r0 mod R bits of the extended slot are dropped), r0, c0
@@ -598,6 +611,7 @@ __device__ __forceinline__ void decode_key(uint64_t k, const WinCtx& c, int& slo
   c0 = (int)(k & m);
   r0 = (int)((k >> c.pb) & m);
   slot = (int)(k >> (2 * c.pb + c.lr));
+  if (slot >= c.n_slots) slot -= c.n_slots;
 }
 
 // A window is "slow" when some pixel is masked by the signed diagonal rule or by a NaN/zero expected value:
@@ -698,7 +712,7 @@ __global__ void __launch_bounds__(256) k_window_counts(const CountParams p) {
 }
 
 // acc += private copies; n comes from the slot boundaries, n_fast = n - n_slow
-__global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int n_slots, int W, int lr,
+__global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int n_slots, int W, int lr, int n_cls,
                                 const int32_t* __restrict__ slot_start, double* __restrict__ acc) {
   const AccLayout L(W);
   const int64_t cs = count_stride(W);
@@ -715,7 +729,9 @@ __global__ void k_counts_reduce(const int* __restrict__ counts, int copies, int 
     } else if (j < L.w2 + 2 * W) {
       if (sum) atomicAdd(a + L.off_cb + (j - L.w2 - W), (double)sum);
     } else if (j == L.w2 + 2 * W) {
-      const int nwin = slot_start[(s + 1) << lr] - slot_start[s << lr];  // over the slot's extended slots
+      int nwin = 0;  // over the slot's extended slots, in both window classes
+      for (int c = 0; c < n_cls; ++c)
+        nwin += slot_start[(c * n_slots + s + 1) << lr] - slot_start[(c * n_slots + s) << lr];
       if (nwin) {
         atomicAdd(a + L.off_n, (double)nwin);
         atomicAdd(a + L.off_nfast, (double)(nwin - sum));
@@ -1018,6 +1034,159 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, MINB) k_pileup
   if (cur_slot >= 0) flush_rows();
 }
 
+
+// ------------------------------------------------------------------------------------------ dense-band pile-up
+// Windows close to the diagonal are dense (in the synthetic 3 Gbp genome a window 10 Mb off the diagonal still holds
+// a pixel in 40 % of its cells): for them a sparse scatter -- one 16-byte record load plus one fp64 shared-memory
+// read-modify-write per stored pixel, ~0.55 L1 wavefronts per pixel -- costs more than reading every cell of the
+// window from a dense copy of the matrix and adding it to a REGISTER: thread t owns the same cells (t, t + T, ...) of
+// the W x W tile for every window, so there is no scatter, no shared memory and no atomics until the slot changes.
+// The dense copy is a diagonal band, band[row][col - row] for col - row < bw (built by k_band_* at region creation,
+// bw chosen on the device where the pixel density falls below PUP_BAND_DENSITY_PCT); a window row is W consecutive
+// doubles of one band row, so a warp's load is one contiguous 256-byte run (~3 L1 wavefronts per 32 cells).
+// Break-even against the sparse path: ~18 % occupancy in L1 wavefronts.  Windows of the class (k_window_keys) come
+// sorted by (slot, r0): the CTAs of the grid walk neighbouring band rows, which stay in L2.
+constexpr int DENSE_MAX_CELLS = 1024 * 8;  // largest tile: 1024 threads x 8 cells (W <= 90)
+
+struct DenseParams {
+  int W, stride, lr, n_slots;
+  const double* band;
+  const int2* win;    // sorted (r0, c0)
+  ChunkTable chunks;  // over all extended slots of both classes
+  int first_eslot;    // first extended slot of the dense class
+  int* work;
+  double* acc;
+};
+
+template <int DENSE_T, int DENSE_CPT>
+__global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const DenseParams p) {
+  __shared__ int s_item;
+  const int W = p.W, w2 = W * W;
+  const AccLayout L(W);
+  const int t = threadIdx.x;
+  int off[DENSE_CPT];
+  double a[DENSE_CPT];
+#pragma unroll
+  for (int k = 0; k < DENSE_CPT; ++k) {
+    const int idx = t + k * DENSE_T;
+    const int i = idx / W, j = idx - i * W;
+    off[k] = idx < w2 ? i * (p.stride - 1) + j : -1;  // (r0 + i) * stride + (c0 + j) - (r0 + i), relative to the window
+    a[k] = 0.0;
+  }
+  const int c_first = __ldg(&p.chunks.chunk_start[p.first_eslot]);
+  const int c_end = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
+  int cur = -1;
+  auto flush = [&]() {
+    if (cur < 0) return;
+    double* dst = p.acc + (int64_t)cur * L.stride;
+#pragma unroll
+    for (int k = 0; k < DENSE_CPT; ++k) {
+      if (off[k] >= 0 && a[k] != 0.0) atomicAdd(dst + t + k * DENSE_T, a[k]);
+      a[k] = 0.0;
+    }
+  };
+  for (;;) {
+    __syncthreads();
+    if (t == 0) s_item = c_first + atomicAdd(p.work, 1);
+    __syncthreads();
+    const int item = s_item;
+    if (item >= c_end) break;
+    int es, lo, hi;
+    locate_chunk(p.chunks, item, es, lo, hi);
+    const int slot = (es >> p.lr) - p.n_slots;
+    if (slot != cur) {
+      flush();
+      cur = slot;
+    }
+    for (int w = lo; w < hi; w += 2) {
+      const int2 rc0 = __ldg(&p.win[w]);
+      const bool two = w + 1 < hi;
+      const int2 rc1 = __ldg(&p.win[two ? w + 1 : w]);
+      const double* b0 = p.band + (int64_t)rc0.x * p.stride + (rc0.y - rc0.x);
+      const double* b1 = p.band + (int64_t)rc1.x * p.stride + (rc1.y - rc1.x);
+      double v0[DENSE_CPT], v1[DENSE_CPT];
+#pragma unroll
+      for (int k = 0; k < DENSE_CPT; ++k) v0[k] = off[k] >= 0 ? __ldg(b0 + off[k]) : 0.0;
+#pragma unroll
+      for (int k = 0; k < DENSE_CPT; ++k) v1[k] = (two && off[k] >= 0) ? __ldg(b1 + off[k]) : 0.0;
+#pragma unroll
+      for (int k = 0; k < DENSE_CPT; ++k) {
+        a[k] += v0[k];
+        a[k] += v1[k];
+      }
+    }
+  }
+  flush();
+}
+
+// ---- building the band (region creation)
+constexpr int BAND_HB = 4096;  // histogram blocks of 2^hs diagonals each
+
+// pixels per block of diagonals (one warp per strip; sentinels have col = INT_MAX)
+__global__ void __launch_bounds__(256) k_band_hist(const Pix* __restrict__ pix, const int32_t* __restrict__ prow, int ns,
+                                                    int lr, int hs, int* __restrict__ hist) {
+  __shared__ int sh[BAND_HB];
+  for (int i = threadIdx.x; i < BAND_HB; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp; s < ns; s += nwarps) {
+    const int lo = prow[s], hi = prow[s + 1];
+    for (int k = lo + lane; k < hi; k += 32) {
+      const int2 cq = __ldg(reinterpret_cast<const int2*>(pix + k));
+      if (cq.x == 0x7fffffff) continue;
+      const int d = cq.x - ((s << lr) + cq.y);
+      if (d >= 0 && (d >> hs) < BAND_HB) atomicAdd(&sh[d >> hs], 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BAND_HB; i += blockDim.x)
+    if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// bw = end of the last block of diagonals (from the diagonal outwards) whose occupancy is still >= pct percent
+__global__ void k_band_choose(const int* __restrict__ hist, int nb, int hs, int bw_max, int pct, int32_t* __restrict__ bw_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int bw = 0;
+  for (int b = 0; (b << hs) < nb && b < BAND_HB; ++b) {
+    const long long d0 = (long long)b << hs, d1 = min((long long)nb, d0 + (1ll << hs));
+    const long long cells = (d1 - d0) * nb - (d0 + d1 - 1) * (d1 - d0) / 2;  // positions (row, row + d), d in [d0, d1)
+    if ((long long)hist[b] * 100 < cells * pct) break;
+    bw = (int)d1;
+  }
+  bw = min(bw, bw_max);
+  *bw_out = bw >= 32 ? bw : 0;
+}
+
+__global__ void k_band_zero(double2* __restrict__ band, int nb, int stride, const int32_t* __restrict__ bw_ptr) {
+  const int half = stride >> 1;  // stride is a multiple of 16
+  const int hw = (__ldg(bw_ptr) + 1) >> 1;
+  const int64_t total = (int64_t)nb * hw;
+  if (hw == 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / hw;
+    band[row * half + (i - row * hw)] = make_double2(0.0, 0.0);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_band_fill(const Pix* __restrict__ pix, const int32_t* __restrict__ prow, int ns,
+                                                    int lr, double* __restrict__ band, int stride,
+                                                    const int32_t* __restrict__ bw_ptr) {
+  const int bw = __ldg(bw_ptr);
+  if (bw == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int s = warp; s < ns; s += nwarps) {
+    const int lo = prow[s], hi = prow[s + 1];
+    for (int k = lo + lane; k < hi; k += 32) {
+      const int4 raw = __ldg(reinterpret_cast<const int4*>(pix + k));
+      if (raw.x == 0x7fffffff) continue;
+      const int row = (s << lr) + raw.y, d = raw.x - row;
+      if (d >= 0 && d < bw) band[(int64_t)row * stride + d] = __hiloint2double(raw.w, raw.z);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ dense-num kernel
 // `num` of slow windows: every pixel of the window is tested (row / column weight, signed diagonal, expected).
 // One CTA per chunk; thread t owns tile cells t, t + blockDim, ... so the int32 tile needs no atomics.
@@ -1066,6 +1235,7 @@ __global__ void __launch_bounds__(512) k_num_slow(const SlowParams p) {
         int slot, lo, hi;
         locate_chunk(p.chunks, item, slot, lo, hi);
         s_slot = slot >> p.ctx.lr;  // extended slot -> accumulator slot
+        if (s_slot >= p.ctx.n_slots) s_slot -= p.ctx.n_slots;
         s_lo = lo;
         s_hi = hi;
       }
@@ -1917,6 +2087,10 @@ int64_t pup_region_device_bytes(const pup_region_t* r) { return r ? r->bytes : 0
 
 namespace {
 
+// With the signed diagonal mask every pixel with col - row < ignore_diags is NaN in the reference's snippets: for
+// ignore_diags >= 0 that is the whole lower triangle, which is then neither mirrored nor stored.
+bool lower_triangle_masked(unsigned flags, int ignore_diags) { return !(flags & PUP_F_NODIAG) && ignore_diags >= 0; }
+
 int choose_bucket_bits(int32_t nb, int32_t ns, int R, int64_t nnz, int* nbk_out) {
   // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (strip, bucket); no table for very sparse rows
   double avg = (double)nnz / nb;  // pixels per row; a strip holds R times as many per column
@@ -2009,6 +2183,34 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
       LAUNCH_CHECK("k_badlist");
     }
   }
+  // dense diagonal band for k_pileup_dense: only when the lower triangle is masked (every cis pile-up), within a
+  // memory budget of PUP_BAND_PCT percent of the pixel table (default 100: the region at most doubles in size);
+  // the number of diagonals actually filled is decided on the device from the pixel density (no host round trip)
+  if (env_int("PUP_BAND", 1) != 0 && lower_triangle_masked(r->flags, r->ignore_diags) && nnz > 0) {
+    const int64_t budget = (int64_t)((double)(n_ent * sizeof(Pix)) * std::max(0, env_int("PUP_BAND_PCT", 100)) / 100.0);
+    int64_t bw_max = std::min<int64_t>(budget / ((int64_t)nb * 8), nb);
+    bw_max &= ~15ll;
+    if (bw_max >= 64) {
+      int hs = 5;
+      while ((nb >> hs) >= BAND_HB) ++hs;
+      int* hist;
+      CK(tmp.alloc((void**)&hist, (size_t)BAND_HB * 4));
+      CK(zero_async(hist, (size_t)BAND_HB * 4, st));
+      CK(cudaMallocAsync((void**)&r->band_bw, 4, st));
+      CK(cudaMallocAsync((void**)&r->band, (size_t)nb * bw_max * 8, st));
+      r->band_stride = (int)bw_max;
+      r->bytes += (int64_t)nb * bw_max * 8 + 4;
+      const int grid = std::min((ns + 7) / 8, 148 * 8);
+      k_band_hist<<<grid, 256, 0, st>>>(r->pix, r->prow, ns, r->lr, hs, hist);
+      LAUNCH_CHECK("k_band_hist");
+      k_band_choose<<<1, 32, 0, st>>>(hist, nb, hs, (int)bw_max, std::max(1, env_int("PUP_BAND_DENSITY_PCT", 20)), r->band_bw);
+      LAUNCH_CHECK("k_band_choose");
+      k_band_zero<<<148 * 8, 256, 0, st>>>(reinterpret_cast<double2*>(r->band), nb, r->band_stride, r->band_bw);
+      LAUNCH_CHECK("k_band_zero");
+      k_band_fill<<<grid, 256, 0, st>>>(r->pix, r->prow, ns, r->lr, r->band, r->band_stride, r->band_bw);
+      LAUNCH_CHECK("k_band_fill");
+    }
+  }
   return PUP_OK;
 }
 
@@ -2053,10 +2255,6 @@ int new_region(int device, int32_t nb, const double* expected, const double* cov
   }
   return PUP_OK;
 }
-
-// With the signed diagonal mask every pixel with col - row < ignore_diags is NaN in the reference's snippets: for
-// ignore_diags >= 0 that is the whole lower triangle, which is then neither mirrored nor stored.
-bool lower_triangle_masked(unsigned flags, int ignore_diags) { return !(flags & PUP_F_NODIAG) && ignore_diags >= 0; }
 
 int check_region_args(const char* who, int device, int32_t nb, int64_t nnz, const void* indptr, const void* col,
                       const void* count, const double* expected, unsigned flags) {
@@ -2306,7 +2504,7 @@ int pup_region_destroy(pup_region_t* r) {
   DeviceGuard guard(r->device);
   cudaStream_t st = r->stream;
   void* ptrs[] = {r->pix, r->prow, r->bucket,  r->expected, r->coverage, r->bad,
-                  r->ebad, r->ebadpre, r->badpre, r->badlist};
+                  r->ebad, r->ebadpre, r->badpre, r->badlist, r->band, r->band_bw};
   for (void* p : ptrs)
     if (p) cudaFreeAsync(p, st);
   delete r;
@@ -2333,9 +2531,14 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     return fail(PUP_E_ARG, "pup_accumulate: coverage requested but the region has none");
   const int pb = ilog2_ceil((int64_t)m->nb + 1);
   const int lr = m->lr;
-  const int n_eslots = n_slots << lr;  // extended slots: (slot, r0 mod R)
+  // windows inside the region's dense band form a second class of every slot (k_window_keys), piled up by
+  // k_pileup_dense; the tile must fit the kernel's register budget (W <= 90)
+  const bool dense_ok = m->band != nullptr && (int64_t)W * W <= DENSE_MAX_CELLS && env_int("PUP_DENSE", 1) != 0;
+  const int n_cls = dense_ok ? 2 : 1;
+  const int n_eslots0 = n_slots << lr;      // extended slots: (slot, r0 mod R)
+  const int n_eslots = n_eslots0 * n_cls;  // ... of both classes
   const int sb = ilog2_ceil((int64_t)n_eslots + 1);
-  if (2 * pb + sb > 62 || (int64_t)n_slots << lr >= (1ll << 30))
+  if (2 * pb + sb > 62 || (int64_t)n_slots * n_cls << lr >= (1ll << 30))
     return fail(PUP_E_ARG, "pup_accumulate: too many slots for this region size");
   DeviceGuard guard(m->device);
   if (!guard.ok) return fail(PUP_E_NODEV, "pup_accumulate: cudaSetDevice failed");
@@ -2392,7 +2595,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(tmp.alloc((void**)&keys_a, (size_t)n_win * 8));
     CK(tmp.alloc((void**)&keys_b, (size_t)n_win * 8));
     k_window_keys<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(d_r0, d_c0, d_slot, keys_a, n_win, m->nb, W,
-                                                                    n_slots, pb, lr);
+                                                                    n_slots, pb, lr, dense_ok ? m->band_bw : nullptr);
     LAUNCH_CHECK("k_window_keys");
     cub::DoubleBuffer<uint64_t> dbuf(keys_a, keys_b);
     size_t tb = 0;
@@ -2433,8 +2636,9 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     CK(cub::DeviceScan::ExclusiveSum(t2, tb2, nchunks, chunk_start, n_eslots + 1, st));
     ++g_launches;
   }
-  WinCtx ctx{m->nb, W, pb, lr, m->ignore_diags, all_flags, m->ebadpre};
-  ChunkTable chunks{slot_start, chunk_start, n_eslots, ch};
+  WinCtx ctx{m->nb, W, pb, lr, m->ignore_diags, all_flags, m->ebadpre, n_slots};
+  ChunkTable chunks{slot_start, chunk_start, n_eslots, ch};          // every window (count / vector / dense-num kernels)
+  ChunkTable chunks_sparse{slot_start, chunk_start, n_eslots0, ch};  // the class k_pileup_main piles up
 
   // 2. per-window counts (n, n_fast, masked rows / columns) and, on request, the O(W) fp64 vectors
   {
@@ -2449,7 +2653,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     k_window_counts<<<(unsigned)((n_win + 255) / 256), 256, 0, st>>>(cp);
     LAUNCH_CHECK("k_window_counts");
     int rgrid = (int)std::min<int64_t>((one + 255) / 256, (int64_t)n_sm * 8);
-    k_counts_reduce<<<rgrid, 256, 0, st>>>(counts, copies, n_slots, W, lr, slot_start, d_acc);
+    k_counts_reduce<<<rgrid, 256, 0, st>>>(counts, copies, n_slots, W, lr, n_cls, slot_start, d_acc);
     LAUNCH_CHECK("k_counts_reduce");
     if (flags & (PUP_F_EXPCTRL | PUP_F_COVERAGE)) {
       VecParams vp{ctx, keys, slot_start, n_eslots, m->expected, m->coverage, d_acc};
@@ -2481,7 +2685,7 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     const int threads = std::min(nt_max, ((Gb * S + 31) / 32) * 32);
     const bool dynamic = env_int("PUP_SCHED", 1) != 0;
     const size_t smem = (size_t)Gb * R * TW * 8 + sizeof(DynSched);
-    MainParams mp{W, m->ns, m->lb, m->pix, m->bucket, win, chunks, Gb, n_groups, n_bands, TW,
+    MainParams mp{W, m->ns, m->lb, m->pix, m->bucket, win, chunks_sparse, Gb, n_groups, n_bands, TW,
                   dynamic ? counters : nullptr, d_acc};
     int occ = 1;
     cudaError_t e = launch_main(R, S, mp, 0, threads, smem, st, &occ);
@@ -2490,6 +2694,24 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     e = launch_main(R, S, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
+    if (dense_ok) {
+      DenseParams dp{W, m->band_stride, lr, n_slots, m->band, win, chunks, n_eslots0, counters + 3, d_acc};
+      // thread t owns tile cells t, t + T, ...: 256 threads (4 CTAs per SM) up to 2048 cells, else 1024 threads
+      const int w2 = W * W;
+      if (w2 <= 256 * 2)
+        k_pileup_dense<256, 2><<<n_sm * 4, 256, 0, st>>>(dp);
+      else if (w2 <= 256 * 4)
+        k_pileup_dense<256, 4><<<n_sm * 4, 256, 0, st>>>(dp);
+      else if (w2 <= 256 * 8)
+        k_pileup_dense<256, 8><<<n_sm * 4, 256, 0, st>>>(dp);
+      else if (w2 <= 1024 * 4)
+        k_pileup_dense<1024, 4><<<n_sm, 1024, 0, st>>>(dp);
+      else if (w2 <= 1024 * 7)
+        k_pileup_dense<1024, 7><<<n_sm, 1024, 0, st>>>(dp);
+      else
+        k_pileup_dense<1024, 8><<<n_sm, 1024, 0, st>>>(dp);
+      LAUNCH_CHECK("k_pileup_dense");
+    }
   }
 
   // 4. dense pixel counts of the slow windows (returns at once when the call has none)

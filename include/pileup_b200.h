@@ -82,6 +82,12 @@ int pup_device_count(int* n_out);
  *
  * The normalisation (balancing, expected divide, diagonal mask, NaN -> "adds nothing") is applied here, once per
  * stored pixel, by a streaming kernel; the pile-up kernel then only gathers and adds.
+ *
+ * Besides the sparse strip layout a cis region (lower triangle masked) keeps a DENSE copy of the diagonals next to
+ * the main diagonal, as far out as the matrix is dense: windows inside that band are piled up from it with register
+ * tiles instead of the sparse scatter (same results up to fp64 summation order).  Memory budget: PUP_BAND_PCT percent
+ * of the sparse pixel table (environment, default 100); the band ends where fewer than PUP_BAND_DENSITY_PCT percent
+ * (default 20) of the cells are stored; PUP_BAND=0 builds none.
  */
 int pup_region_create(int device, int32_t nb, int64_t nnz, const int32_t* indptr, const int32_t* col,
                       const int32_t* count, const double* weight, const double* expected,

@@ -171,7 +171,9 @@ def test_strip_geometries(monkeypatch, strip, lanes, nb, W, dens, nwin, n_slots)
 
 @pytest.mark.parametrize("env", [{"PUP_SCHED": "0"}, {"PUP_SCHED": "1"}, {"PUP_TILE_PAD": "1"},
                                  {"PUP_TILE_PAD": "5", "PUP_TILE_INTERLEAVE": "0"}, {"PUP_TILE_INTERLEAVE": "1"},
-                                 {"PUP_TILE_INTERLEAVE": "0", "PUP_CHUNK": "16"}, {"PUP_SORT_C0_BITS": "0"}, {"PUP_SORT_C0_BITS": "3"}, {"PUP_CHUNK": "7"}])
+                                 {"PUP_TILE_INTERLEAVE": "0", "PUP_CHUNK": "16"}, {"PUP_SORT_C0_BITS": "0"}, {"PUP_SORT_C0_BITS": "3"}, {"PUP_CHUNK": "7"},
+                                 {"PUP_DENSE": "0"}, {"PUP_BAND": "0"}, {"PUP_BAND_PCT": "3000", "PUP_BAND_DENSITY_PCT": "1"},
+                                 {"PUP_BAND_PCT": "50", "PUP_BAND_DENSITY_PCT": "60"}])
 @pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(700, 83, 200, 2500, 3), (900, 203, 400, 90, 2), (300, 21, 30, 4000, 5)])
 def test_main_kernel_variants(monkeypatch, env, nb, W, dens, nwin, n_slots):
     """Scheduling (static round-robin / barrier-free dynamic ring), occupancy and tile-layout variants of the main
@@ -501,3 +503,37 @@ def test_rescale_kernel_vs_oracle_random(mode, nb, rs, hmax, nwin, n_slots):
     if coverage is not None:
         np.testing.assert_allclose(out["cov_start"], ref["cov_start"], rtol=RTOL)
         np.testing.assert_allclose(out["cov_end"], ref["cov_end"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("mode", ["raw", "balanced", "balanced_ooe", "balanced_expctrl"])
+@pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(1500, 83, 800, 3000, 3), (600, 21, 300, 5000, 4), (1200, 45, 500, 2000, 2),
+                                                      (1400, 89, 900, 600, 2), (900, 64, 10, 1500, 2)])
+def test_dense_band_path_vs_oracle(monkeypatch, mode, nb, W, dens, nwin, n_slots):
+    """Windows inside the dense diagonal band go through k_pileup_dense (register tiles over a dense copy of the
+    matrix), the others through the sparse kernel; a budget / density setting that puts most windows into the band, and
+    the default one, both give the oracle's accumulators -- and the same as with the band switched off."""
+    nat = _cuda()
+    from oracle.pileup_oracle import oracle_accumulate
+
+    cfg = MODES[mode]
+    ip, col, cnt, w, e, cov = random_region(nb, dens, seed=nb + W, nan_frac=0.04, with_expected=True)
+    weight = w if cfg["bal"] else None
+    expected = e if cfg.get("exp") else None
+    rng = np.random.default_rng(nb * 7 + W)
+    r0 = rng.integers(0, nb - W, nwin).astype(np.int32)
+    c0 = np.clip(r0 + rng.integers(-W, nb // 2, nwin), 0, nb - W).astype(np.int32)  # most windows near the diagonal
+    sl = rng.integers(0, n_slots, nwin).astype(np.int32)
+    ref = oracle_accumulate(nb, ip, col, cnt, weight, expected, None, r0, c0, sl, W, 2, n_slots,
+                            ooe=cfg["flags"] == 1, expctrl=cfg["flags"] == 2)
+    outs = []
+    for env in ({"PUP_BAND_PCT": "3000", "PUP_BAND_DENSITY_PCT": "1"}, {}, {"PUP_BAND": "0"}):
+        with monkeypatch.context() as mp:
+            for k, v in env.items():
+                mp.setenv(k, v)
+            acc = np.zeros(n_slots * nat.acc_stride(W))
+            nv = nat.accumulate_region(0, nb, ip, col, cnt, weight, expected, None, r0, c0, sl, W, 2, n_slots, cfg["flags"], acc)
+            out = nat.acc_export(acc, W, n_slots, want_expected=True)
+        _check_against_oracle(nv, out, ref)
+        outs.append(out)
+    for o in outs[:2]:
+        assert np.array_equal(o["num"], outs[2]["num"]) and np.array_equal(o["n"], outs[2]["n"])
