@@ -516,7 +516,8 @@ def main():
                 "slots_used": int((n_all > 0).sum())}
 
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    stats = torch.tensor([alg_bytes, phases["main"][0], launches, phases["main"][1]], dtype=torch.float64, device=dev)
+    stats = torch.tensor([alg_bytes, phases["main"][0] + phases["dense_band"][0], launches, phases["main"][1]], dtype=torch.float64,
+                         device=dev)  # the pile-up phase = sparse kernel + dense-band kernel of every call
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         allstats = [torch.zeros_like(stats) for _ in range(world)]

@@ -353,11 +353,12 @@ def timing_enable(on=True):
 
 
 def timing_read(reset=True):
-    """{phase: (milliseconds, spans)} for phases 'plan', 'vector', 'main', 'dense_num' since the last reset."""
-    ms = (C.c_double * 4)()
-    cnt = (C.c_int * 4)()
+    """{phase: (milliseconds, spans)} for phases 'plan', 'vector', 'main' (sparse pile-up kernel), 'dense_num',
+    'dense_band' (dense pile-up kernel) since the last reset."""
+    ms = (C.c_double * 5)()
+    cnt = (C.c_int * 5)()
     check(lib().pup_timing_read(ms, cnt, 1 if reset else 0))
-    return {k: (ms[i], cnt[i]) for i, k in enumerate(("plan", "vector", "main", "dense_num"))}
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(("plan", "vector", "main", "dense_num", "dense_band"))}
 
 
 def acc_export(acc, W, n_slots, device=0, stream=0, want_expected=False, want_cov=False):

@@ -42,10 +42,10 @@ thread_local int g_launches = 0;
 
 // optional per-phase device timing (bench.py): CUDA events recorded on the caller's stream
 struct TimedSpan {
-  int tag;  // 0 sort/plan, 1 vector kernel, 2 main kernel, 3 dense-num kernel
+  int tag;  // 0 sort/plan, 1 vector kernel, 2 main (sparse) kernel, 3 dense-num kernel, 4 dense-band kernel
   cudaEvent_t a, b;
 };
-constexpr int N_TAGS = 4;
+constexpr int N_TAGS = 5;
 thread_local bool g_timing = false;
 thread_local std::vector<TimedSpan> g_spans;
 
@@ -1046,10 +1046,11 @@ __global__ void __launch_bounds__(S == 32 ? NT_MAX : NT_MAX - 32, MINB) k_pileup
 // doubles of one band row, so a warp's load is one contiguous 256-byte run (~3 L1 wavefronts per 32 cells).
 // Break-even against the sparse path: ~18 % occupancy in L1 wavefronts.  Windows of the class (k_window_keys) come
 // sorted by (slot, r0): the CTAs of the grid walk neighbouring band rows, which stay in L2.
-constexpr int DENSE_MAX_CELLS = 1024 * 8;  // largest tile: 1024 threads x 8 cells (W <= 90)
+constexpr int DENSE_BAND_CELLS = 1024 * 7;  // tiles with more cells are cut into row bands of at most this many
 
 struct DenseParams {
   int W, stride, lr, n_slots;
+  int rows_per_band, n_bands;  // the tile's rows are piled up in n_bands passes over the window list (W = 203: 6)
   const double* band;
   const int2* win;    // sorted (r0, c0)
   ChunkTable chunks;  // over all extended slots of both classes
@@ -1061,42 +1062,54 @@ struct DenseParams {
 template <int DENSE_T, int DENSE_CPT>
 __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const DenseParams p) {
   __shared__ int s_item;
-  const int W = p.W, w2 = W * W;
+  const int W = p.W;
   const AccLayout L(W);
   const int t = threadIdx.x;
-  int off[DENSE_CPT];
+  int off[DENSE_CPT], cellid[DENSE_CPT];
   double a[DENSE_CPT];
 #pragma unroll
   for (int k = 0; k < DENSE_CPT; ++k) {
-    const int idx = t + k * DENSE_T;
-    const int i = idx / W, j = idx - i * W;
-    off[k] = idx < w2 ? i * (p.stride - 1) + j : -1;  // (r0 + i) * stride + (c0 + j) - (r0 + i), relative to the window
+    off[k] = cellid[k] = -1;
     a[k] = 0.0;
   }
   const int c_first = __ldg(&p.chunks.chunk_start[p.first_eslot]);
-  const int c_end = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]);
-  int cur = -1;
+  const int n_chunks = __ldg(&p.chunks.chunk_start[p.chunks.n_slots]) - c_first;
+  const int n_items = n_chunks * p.n_bands;
+  int cur = -1, cur_band = -1;
   auto flush = [&]() {
     if (cur < 0) return;
     double* dst = p.acc + (int64_t)cur * L.stride;
 #pragma unroll
     for (int k = 0; k < DENSE_CPT; ++k) {
-      if (off[k] >= 0 && a[k] != 0.0) atomicAdd(dst + t + k * DENSE_T, a[k]);
+      if (cellid[k] >= 0 && a[k] != 0.0) atomicAdd(dst + cellid[k], a[k]);
       a[k] = 0.0;
     }
   };
   for (;;) {
     __syncthreads();
-    if (t == 0) s_item = c_first + atomicAdd(p.work, 1);
+    if (t == 0) s_item = atomicAdd(p.work, 1);
     __syncthreads();
     const int item = s_item;
-    if (item >= c_end) break;
+    if (item >= n_items) break;
+    const int band = item / n_chunks;
     int es, lo, hi;
-    locate_chunk(p.chunks, item, es, lo, hi);
+    locate_chunk(p.chunks, c_first + (item - band * n_chunks), es, lo, hi);
     const int slot = (es >> p.lr) - p.n_slots;
-    if (slot != cur) {
+    if (slot != cur || band != cur_band) {
       flush();
       cur = slot;
+      if (band != cur_band) {  // my cells of this band: band-local index t, t + T, ... -> (row, column) of the tile
+        cur_band = band;
+        const int i0 = band * p.rows_per_band, rows = min(p.rows_per_band, W - i0);
+#pragma unroll
+        for (int k = 0; k < DENSE_CPT; ++k) {
+          const int idx = t + k * DENSE_T;
+          const int il = idx / W, j = idx - il * W, i = i0 + il;
+          const bool ok = il < rows;
+          off[k] = ok ? i * (p.stride - 1) + j : -1;  // (r0 + i) * stride + (c0 + j) - (r0 + i), relative to the window
+          cellid[k] = ok ? i * W + j : -1;
+        }
+      }
     }
     for (int w = lo; w < hi; w += 2) {
       const int2 rc0 = __ldg(&p.win[w]);
@@ -2025,7 +2038,7 @@ void choose_strip(int* R_out, int* S_out) {
 // =========================================================================================== C ABI
 extern "C" {
 
-int pup_abi_version(void) { return 3; }
+int pup_abi_version(void) { return 4; }
 
 const char* pup_last_error(void) { return g_err.c_str(); }
 
@@ -2050,8 +2063,8 @@ int pup_timing_enable(int on) {
 }
 
 int pup_timing_read(double* ms_by_tag, int* count_by_tag, int reset) {
-  double ms[N_TAGS] = {0, 0, 0, 0};
-  int cnt[N_TAGS] = {0, 0, 0, 0};
+  double ms[N_TAGS] = {0, 0, 0, 0, 0};
+  int cnt[N_TAGS] = {0, 0, 0, 0, 0};
   for (auto& sp : g_spans) {
     float f = 0;
     cudaError_t e = cudaEventSynchronize(sp.b);
@@ -2532,8 +2545,8 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
   const int pb = ilog2_ceil((int64_t)m->nb + 1);
   const int lr = m->lr;
   // windows inside the region's dense band form a second class of every slot (k_window_keys), piled up by
-  // k_pileup_dense; the tile must fit the kernel's register budget (W <= 90)
-  const bool dense_ok = m->band != nullptr && (int64_t)W * W <= DENSE_MAX_CELLS && env_int("PUP_DENSE", 1) != 0;
+  // k_pileup_dense
+  const bool dense_ok = m->band != nullptr && env_int("PUP_DENSE", 1) != 0;
   const int n_cls = dense_ok ? 2 : 1;
   const int n_eslots0 = n_slots << lr;      // extended slots: (slot, r0 mod R)
   const int n_eslots = n_eslots0 * n_cls;  // ... of both classes
@@ -2694,22 +2707,29 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
     e = launch_main(R, S, mp, n_sm * occ, threads, smem, st, nullptr);
     ++g_launches;
     if (e != cudaSuccess) return fail(PUP_E_CUDA, "launch k_pileup_main", e);
+    span.close();
     if (dense_ok) {
-      DenseParams dp{W, m->band_stride, lr, n_slots, m->band, win, chunks, n_eslots0, counters + 3, d_acc};
-      // thread t owns tile cells t, t + T, ...: 256 threads (4 CTAs per SM) up to 2048 cells, else 1024 threads
+      SpanGuard span_dense(4, st);
+      // thread t owns tile cells t, t + T, ... (of its row band, when the tile is cut): 256 threads (4 CTAs per SM)
+      // up to 1024 cells, else 1024 threads with up to 7 cells each
       const int w2 = W * W;
-      if (w2 <= 256 * 2)
+      const int n_bands_d = (w2 + DENSE_BAND_CELLS - 1) / DENSE_BAND_CELLS;
+      const int rows_pb = (W + n_bands_d - 1) / n_bands_d;
+      const int cells_pb = rows_pb * W;
+      DenseParams dp{W, m->band_stride, lr, n_slots, rows_pb, (W + rows_pb - 1) / rows_pb, m->band, win, chunks, n_eslots0,
+                     counters + 3, d_acc};
+      if (cells_pb <= 256 * 2)
         k_pileup_dense<256, 2><<<n_sm * 4, 256, 0, st>>>(dp);
-      else if (w2 <= 256 * 4)
+      else if (cells_pb <= 256 * 4)
         k_pileup_dense<256, 4><<<n_sm * 4, 256, 0, st>>>(dp);
-      else if (w2 <= 256 * 8)
-        k_pileup_dense<256, 8><<<n_sm * 4, 256, 0, st>>>(dp);
-      else if (w2 <= 1024 * 4)
+      else if (cells_pb <= 1024 * 2)
+        k_pileup_dense<1024, 2><<<n_sm, 1024, 0, st>>>(dp);
+      else if (cells_pb <= 1024 * 4)
         k_pileup_dense<1024, 4><<<n_sm, 1024, 0, st>>>(dp);
-      else if (w2 <= 1024 * 7)
+      else if (cells_pb <= 1024 * 7)
         k_pileup_dense<1024, 7><<<n_sm, 1024, 0, st>>>(dp);
       else
-        k_pileup_dense<1024, 8><<<n_sm, 1024, 0, st>>>(dp);
+        k_pileup_dense<1024, 8><<<n_sm, 1024, 0, st>>>(dp);  // rows_pb * W can exceed the band budget by < W cells
       LAUNCH_CHECK("k_pileup_dense");
     }
   }

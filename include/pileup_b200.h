@@ -280,9 +280,10 @@ int pup_last_launches(void);
 
 /*
  * Optional device-side timing for benchmarks: when enabled (per host thread), every pup_accumulate() records
- * CUDA events on the caller's stream around its four phases: [0] window sort + chunk plan, [1] vector kernel,
- * [2] main pile-up kernel, [3] dense-num kernel.  pup_timing_read() waits for the recorded events and returns the
- * summed milliseconds and the number of spans per phase (arrays of 4); reset != 0 clears the records.
+ * CUDA events on the caller's stream around its five phases: [0] window sort + chunk plan, [1] vector kernel,
+ * [2] main (sparse) pile-up kernel, [3] dense-num kernel, [4] dense-band pile-up kernel.  pup_timing_read() waits for
+ * the recorded events and returns the summed milliseconds and the number of spans per phase (arrays of 5); reset != 0
+ * clears the records.
  */
 int pup_timing_enable(int on);
 int pup_timing_read(double* ms_by_phase, int* count_by_phase, int reset);

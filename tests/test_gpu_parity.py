@@ -507,7 +507,7 @@ def test_rescale_kernel_vs_oracle_random(mode, nb, rs, hmax, nwin, n_slots):
 
 @pytest.mark.parametrize("mode", ["raw", "balanced", "balanced_ooe", "balanced_expctrl"])
 @pytest.mark.parametrize("nb,W,dens,nwin,n_slots", [(1500, 83, 800, 3000, 3), (600, 21, 300, 5000, 4), (1200, 45, 500, 2000, 2),
-                                                      (1400, 89, 900, 600, 2), (900, 64, 10, 1500, 2)])
+                                                      (1400, 89, 900, 600, 2), (900, 64, 10, 1500, 2), (1600, 203, 900, 250, 2), (1300, 121, 700, 300, 3)])
 def test_dense_band_path_vs_oracle(monkeypatch, mode, nb, W, dens, nwin, n_slots):
     """Windows inside the dense diagonal band go through k_pileup_dense (register tiles over a dense copy of the
     matrix), the others through the sparse kernel; a budget / density setting that puts most windows into the band, and
