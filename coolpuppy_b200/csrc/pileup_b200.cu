@@ -1065,11 +1065,16 @@ __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const 
   const int W = p.W;
   const AccLayout L(W);
   const int t = threadIdx.x;
-  int off[DENSE_CPT], cellid[DENSE_CPT];
+  // band element of my cell k relative to the window's first element; cells beyond the tile read element 0 of the
+  // window (a valid address) into an accumulator that is never flushed: the inner loop carries no predicates
+  unsigned off[DENSE_CPT];
+  int cellid[DENSE_CPT];
   double a[DENSE_CPT];
+  const double* __restrict__ bandp = p.band;
 #pragma unroll
   for (int k = 0; k < DENSE_CPT; ++k) {
-    off[k] = cellid[k] = -1;
+    off[k] = 0u;
+    cellid[k] = -1;
     a[k] = 0.0;
   }
   const int c_first = __ldg(&p.chunks.chunk_start[p.first_eslot]);
@@ -1106,27 +1111,34 @@ __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const 
           const int idx = t + k * DENSE_T;
           const int il = idx / W, j = idx - il * W, i = i0 + il;
           const bool ok = il < rows;
-          off[k] = ok ? i * (p.stride - 1) + j : -1;  // (r0 + i) * stride + (c0 + j) - (r0 + i), relative to the window
+          off[k] = ok ? (unsigned)(i * (p.stride - 1) + j) : 0u;  // (r0 + i) * stride + (c0 + j) - (r0 + i) - window base
           cellid[k] = ok ? i * W + j : -1;
         }
       }
     }
-    for (int w = lo; w < hi; w += 2) {
+    // two windows in flight; 32-bit element indices (the band holds < 2^31 doubles): one IMAD.WIDE per address
+    int w = lo;
+    for (; w + 1 < hi; w += 2) {
       const int2 rc0 = __ldg(&p.win[w]);
-      const bool two = w + 1 < hi;
-      const int2 rc1 = __ldg(&p.win[two ? w + 1 : w]);
-      const double* b0 = p.band + (int64_t)rc0.x * p.stride + (rc0.y - rc0.x);
-      const double* b1 = p.band + (int64_t)rc1.x * p.stride + (rc1.y - rc1.x);
+      const int2 rc1 = __ldg(&p.win[w + 1]);
+      const unsigned e0 = (unsigned)(rc0.x * p.stride + (rc0.y - rc0.x));
+      const unsigned e1 = (unsigned)(rc1.x * p.stride + (rc1.y - rc1.x));
       double v0[DENSE_CPT], v1[DENSE_CPT];
 #pragma unroll
-      for (int k = 0; k < DENSE_CPT; ++k) v0[k] = off[k] >= 0 ? __ldg(b0 + off[k]) : 0.0;
+      for (int k = 0; k < DENSE_CPT; ++k) v0[k] = __ldg(bandp + (e0 + off[k]));
 #pragma unroll
-      for (int k = 0; k < DENSE_CPT; ++k) v1[k] = (two && off[k] >= 0) ? __ldg(b1 + off[k]) : 0.0;
+      for (int k = 0; k < DENSE_CPT; ++k) v1[k] = __ldg(bandp + (e1 + off[k]));
 #pragma unroll
       for (int k = 0; k < DENSE_CPT; ++k) {
         a[k] += v0[k];
         a[k] += v1[k];
       }
+    }
+    if (w < hi) {
+      const int2 rc0 = __ldg(&p.win[w]);
+      const unsigned e0 = (unsigned)(rc0.x * p.stride + (rc0.y - rc0.x));
+#pragma unroll
+      for (int k = 0; k < DENSE_CPT; ++k) a[k] += __ldg(bandp + (e0 + off[k]));
     }
   }
   flush();
@@ -2202,6 +2214,7 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
   if (env_int("PUP_BAND", 1) != 0 && lower_triangle_masked(r->flags, r->ignore_diags) && nnz > 0) {
     const int64_t budget = (int64_t)((double)(n_ent * sizeof(Pix)) * std::max(0, env_int("PUP_BAND_PCT", 100)) / 100.0);
     int64_t bw_max = std::min<int64_t>(budget / ((int64_t)nb * 8), nb);
+    bw_max = std::min<int64_t>(bw_max, ((1ll << 31) - 1) / nb);  // k_pileup_dense indexes the band with 32 bits
     bw_max &= ~15ll;
     if (bw_max >= 64) {
       int hs = 5;
