@@ -417,11 +417,10 @@ def main():
         sys.stderr.write(json.dumps({"algorithmic_bytes_by_chromosome": dict(zip(names, [int(c) for c in cost])),
                                      "windows_by_chromosome": {c: len(windows[c]["r0"]) for c in names}}) + "\n")
     # one contiguous, equal-cost piece of the (chromosome, row anchor) sequence per rank (the product's sharding,
-    # multigpu.contiguous_partition); the per-anchor cost model is rescaled to every chromosome's exact bytes
+    # multigpu.contiguous_partition) with the product's predicted pile-up time per row anchor (PileUpper._feature_costs)
     arrs = []
-    for c, b in zip(names, cost):
-        a = np.array(pu_plan._feature_costs(c) if len(windows[c]["r0"]) else np.zeros(0), dtype=np.float64)
-        arrs.append(a * (b / a.sum()) if a.sum() > 0 else a)
+    for c, b in zip(names, cost):  # the product's own time model (sparse / dense-band kernel), not rescaled
+        arrs.append(np.array(pu_plan._feature_costs(c) if len(windows[c]["r0"]) else np.zeros(0), dtype=np.float64))
     pieces, loads = contiguous_partition(arrs, world)
     my_units = [(names[i], lo, hi, lo == 0 and hi == len(arrs[i])) for i, lo, hi in pieces[rank]]
     predicted_imbalance = float(max(loads) / (sum(loads) / len(loads))) if sum(loads) > 0 else 1.0
@@ -451,7 +450,7 @@ def main():
         "depth": args.depth, "roi_windows": int(n_pairs), "windows_per_step": int(n_windows_total),
         "chromosomes": len(names), "binsize": BINSIZE, "flank": wl["flank"], "accumulator_slots": int(n_slots),
         "l2": "inputs (region matrices, GBs) exceed the 126 MB L2; no flush between iterations",
-        "parallelism": (f"the (chromosome, row anchor) sequence is cut into {world} contiguous pieces of equal algorithmic bytes, one "
+        "parallelism": (f"the (chromosome, row anchor) sequence is cut into {world} contiguous pieces of equal predicted pile-up time, one "
                         "per GPU (a chromosome that straddles a cut is piled up as row bands on two GPUs, its matrix "
                         "replicated); one all-reduce of the accumulators; e2e: whole chromosomes per GPU by LPT"),
     }

@@ -697,12 +697,34 @@ class PileUpper:
         lo, hi = self.clr.extent((r["chrom"], r["start"], r["end"]))
         return int(off[hi] - off[lo])
 
+    # pile-up time model of one window (SM cycles on B200, fitted to configs[3]): the sparse kernel
+    # pays per strip run and per stored pixel, the dense-band kernel reads every cell of the window
+    _COST_SPARSE_PER_ROW, _COST_SPARSE_PER_PIXEL, _COST_DENSE_PER_CELL, _DENSE_FILL = 3.8, 0.52, 0.1465, 0.20
+    _COST_PER_WINDOW = 95.0  # sort, chunk plan and count kernels
+    _COST_PER_REGION = 3.5e7  # launch ramps and tails of one region's kernels (~0.12 ms of the whole GPU)
+
+    @staticmethod
+    def _fit_poisson_scale(nb, nnz):
+        """lambda0 with sum_s (nb - s) * (1 - exp(-lambda0 / s)) = nnz: stored pixels of a matrix whose counts are
+        Poisson(lambda0 / separation) -- the occupancy model of the sharding costs (bisection, s sampled)."""
+        s_ = np.unique(np.round(np.geomspace(1, max(2, nb - 1), 400)).astype(np.int64))
+        wgt = np.gradient(s_.astype(float)) * (nb - s_)
+        lo_, hi_ = 1e-6, 1e9
+        for _ in range(60):
+            mid = np.sqrt(lo_ * hi_)
+            if float(np.sum(wgt * -np.expm1(-mid / s_))) < nnz:
+                lo_ = mid
+            else:
+                hi_ = mid
+        return float(np.sqrt(lo_ * hi_))
+
     def _feature_costs(self, name):
-        """Predicted algorithmic bytes (per window 16 + 4(W+1) [+16W balanced] + 8 per stored pixel) of the
-        windows anchored at every feature of a view region, in the order of the region's feature table: for bed pairs
-        the pairs (k, l > k) count for their row anchor k.  Stored pixels per window are modelled as
-        W^2 * min(1, A / separation) with A fitted to the region's pixel count (contact density ~ 1 / separation).
-        The sum is the region's cost for the LPT sharding; its running sum gives the cut points of window parts."""
+        """Predicted pile-up time (relative units) of the windows anchored at every feature of a view region, in the
+        order of the region's feature table: for bed pairs the pairs (k, l > k) count for their row anchor k.  The
+        occupancy of a window at separation s is modelled as 1 - exp(-lambda0 / s) (contact density ~ 1 / separation,
+        lambda0 fitted to the region's stored pixel count); a window costs a term per tile row plus a term per stored
+        pixel in the sparse kernel, or a term per cell when it lies in the dense diagonal band (occupancy >= 20 %).
+        The sum is the region's cost for the sharding; its running sum gives the cut points of window parts."""
         if name in self._cost_cache:
             return self._cost_cache[name]
         r = self.view_df.loc[name]
@@ -711,13 +733,18 @@ class PileUpper:
         lo, hi = self.view_df_extents[name]
         nb = max(2, hi - lo)
         nnz = self._region_nnz(name)
-        A = 1.0 if nnz is None else max(1e-3, nnz / (nb * max(1.0, np.log(nb) - 1.0)))
-        fixed = 16 + 4 * (W + 1) + (16 * W if self.clr_weight_name else 0)
+        lam = 1.0 if nnz is None else self._fit_poisson_scale(nb, max(1.0, float(nnz)))  # upper-triangle pixels
         reps = 1 + (self.CC.nshifts if self.control else 0)
         res = float(self.resolution)
+        band_ok = not self.trans and self.ignore_diags >= 0  # the regions that get a dense band
 
         def cost_of(sep_bins):
-            return (fixed + 8.0 * W * W * np.minimum(1.0, A / np.maximum(np.abs(sep_bins), 1.0))) * reps
+            sep = np.maximum(np.abs(sep_bins), 1.0)
+            fill = -np.expm1(-lam / sep)
+            cost = self._COST_SPARSE_PER_ROW * W + self._COST_SPARSE_PER_PIXEL * W * W * fill
+            if band_ok:
+                cost = np.where((fill >= self._DENSE_FILL) & (sep >= W - 1), self._COST_DENSE_PER_CELL * W * W, cost)
+            return (cost + self._COST_PER_WINDOW) * reps
 
         if self.CC.kind == "bedpe":
             m = ((df["chrom1"].values == r["chrom"]) & (df["chrom2"].values == r["chrom"])
@@ -742,7 +769,10 @@ class PileUpper:
                     out[kk] = np.where(keep, cost_of(d), 0.0).sum(axis=1)
                 if step > 1:
                     out = np.interp(np.arange(n), ks, out[ks])
-        self._cost_cache[name] = np.asarray(out, dtype=np.float64)
+        out = np.asarray(out, dtype=np.float64)
+        if len(out) and out.sum() > 0:
+            out = out + self._COST_PER_REGION / len(out)
+        self._cost_cache[name] = out
         return self._cost_cache[name]
 
     def _region_cost(self, name):
