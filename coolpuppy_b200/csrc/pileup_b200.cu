@@ -2253,18 +2253,19 @@ int new_region(int device, int32_t nb, const double* expected, const double* cov
   // host vectors go through the internal copy stream like the matrix arrays (FIFO with them), not through the
   // caller's stream, where a small copy could wait behind uploads that other calls queued on the copy engine
   auto put = [&](double** dst, const double* src) -> int {
-    CK(cudaMallocAsync((void**)dst, (size_t)nb * 8, st));
     r->bytes += (int64_t)nb * 8;
     cudaStream_t cs = is_device_ptr(src) ? st : copy_stream(device);
     if (!cs || cs == st) {
+      CK(cudaMallocAsync((void**)dst, (size_t)nb * 8, st));
       CK(cudaMemcpyAsync(*dst, src, (size_t)nb * 8, cudaMemcpyDefault, st));
       return PUP_OK;
     }
+    // allocated AND filled on the copy stream, like the matrix arrays (Uploader): an allocation on the caller's stream
+    // would order this copy -- and every upload queued behind it -- after the previous region's preparation kernels
+    CK(cudaMallocAsync((void**)dst, (size_t)nb * 8, cs));
     cudaEvent_t ev;
     CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    cudaError_t e = cudaEventRecord(ev, st);  // the allocation is ordered on st
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ev, 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(*dst, src, (size_t)nb * 8, cudaMemcpyHostToDevice, cs);
+    cudaError_t e = cudaMemcpyAsync(*dst, src, (size_t)nb * 8, cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess) e = cudaEventRecord(ev, cs);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
     cudaEventDestroy(ev);
