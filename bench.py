@@ -567,12 +567,30 @@ def main():
 
         e2e_step()
         barrier()
+        # plain pinned-host -> device copy rate of this process's largest pixel array (the ceiling of the e2e step)
+        probe_src = max((host_data[c]["upper_col"] for c in mine), key=lambda t: t.numel(), default=None)
+        h2d_probe = None
+        if probe_src is not None and probe_src.numel() > 0:
+            probe_dst = torch.empty_like(probe_src, device=dev)
+            probe_dst.copy_(probe_src, non_blocking=True)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            probe_dst.copy_(probe_src, non_blocking=True)
+            p1.record()
+            torch.cuda.synchronize(dev)
+            h2d_probe = probe_src.numel() * probe_src.element_size() / 1e9 / (p0.elapsed_time(p1) / 1e3)
+            del probe_dst
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
+        step_wall = []
         for _ in range(args.e2e_steps):
+            t_w = time.perf_counter()
             e2e_step()
+            step_wall.append((time.perf_counter() - t_w) * 1e3)
         a1.record()
         barrier()
+        if os.environ.get("PUP_BENCH_VERBOSE") and rank == 0:
+            sys.stderr.write(json.dumps({"e2e_step_wall_ms": [round(x, 1) for x in step_wall]}) + "\n")
         ems = torch.tensor([a0.elapsed_time(a1) / args.e2e_steps], dtype=torch.float64, device=dev)
         bts = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
         if dist is not None:
@@ -580,7 +598,8 @@ def main():
             dist.all_reduce(bts)
         e2e = {"value": n_valid_total / (float(ems.item()) / 1e3), "unit": "pile-ups/s", "ms_per_step": float(ems.item()),
                "h2d_bytes_per_step": int(bts[0].item()), "d2h_bytes_per_step": int(bts[1].item()),
-               "steps": args.e2e_steps,
+               "steps": args.e2e_steps, "h2d_probe_gbs": h2d_probe,
+               "step_wall_ms_min_max": [min(step_wall), max(step_wall)],
                "what": "coolpuppy_b200.pipeline.RegionPipeline (the product's own region loop) with pinned HOST buffers: per "
                        "chromosome pup_region_create_upper(cooler-style upper-triangle pixels, weights[, expected]) + pup_upload"
                        "(window arrays) on a prepare stream while the previous chromosome's pup_accumulate runs on a compute "
