@@ -241,3 +241,23 @@ def test_part_ranges_cover_features_once():
         cuts = [pu._part_ranges(name, [p], 4) for p in range(4)]
         loads = [sum(c[lo:hi].sum() for lo, hi in r) for r in cuts]
         assert max(loads) <= 0.5 * c.sum()  # equal-cost cut points, up to one feature's cost
+
+
+def test_sharding_cost_model_follows_the_two_kernels():
+    """PileUpper._feature_costs: the Poisson occupancy fit recovers the scale of a synthetic matrix, and a window costs
+    the dense-band kernel's flat price where the matrix is dense, the sparse kernel's per-pixel price further out."""
+    from coolpuppy_b200.coolpup import PileUpper
+
+    nb = 20000
+    s_ = np.arange(1, nb)
+    nnz = float(np.sum((nb - s_) * -np.expm1(-300.0 / s_))) + nb
+    lam = PileUpper._fit_poisson_scale(nb, nnz)
+    assert abs(lam - 300.0) / 300.0 < 0.02
+    W = 83
+    dense = PileUpper._COST_DENSE_PER_CELL * W * W
+    fill_far = -np.expm1(-lam / 10000.0)
+    sparse_far = PileUpper._COST_SPARSE_PER_ROW * W + PileUpper._COST_SPARSE_PER_PIXEL * W * W * fill_far
+    assert sparse_far < dense  # far windows are cheaper through the sparse kernel ...
+    fill_near = -np.expm1(-lam / 200.0)
+    sparse_near = PileUpper._COST_SPARSE_PER_ROW * W + PileUpper._COST_SPARSE_PER_PIXEL * W * W * fill_near
+    assert fill_near > PileUpper._DENSE_FILL and sparse_near > dense  # ... near ones through the dense band
