@@ -2211,7 +2211,8 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
   // dense diagonal band for k_pileup_dense: only when the lower triangle is masked (every cis pile-up), within a
   // memory budget of PUP_BAND_PCT percent of the pixel table (default 100: the region at most doubles in size);
   // the number of diagonals actually filled is decided on the device from the pixel density (no host round trip)
-  if (env_int("PUP_BAND", 1) != 0 && lower_triangle_masked(r->flags, r->ignore_diags) && nnz > 0) {
+  // (matrices with fewer than 32 stored pixels per row cannot have a dense band worth building)
+  if (env_int("PUP_BAND", 1) != 0 && lower_triangle_masked(r->flags, r->ignore_diags) && nnz >= 32ll * nb) {
     const int64_t budget = (int64_t)((double)(n_ent * sizeof(Pix)) * std::max(0, env_int("PUP_BAND_PCT", 100)) / 100.0);
     int64_t bw_max = std::min<int64_t>(budget / ((int64_t)nb * 8), nb);
     bw_max = std::min<int64_t>(bw_max, ((1ll << 31) - 1) / nb);  // k_pileup_dense indexes the band with 32 bits
@@ -2223,7 +2224,11 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
       CK(tmp.alloc((void**)&hist, (size_t)BAND_HB * 4));
       CK(zero_async(hist, (size_t)BAND_HB * 4, st));
       CK(cudaMallocAsync((void**)&r->band_bw, 4, st));
-      CK(cudaMallocAsync((void**)&r->band, (size_t)nb * bw_max * 8, st));
+      if (cudaMallocAsync((void**)&r->band, (size_t)nb * bw_max * 8, st) != cudaSuccess) {
+        cudaGetLastError();  // no memory for the band: the region works without it (sparse kernel only)
+        r->band = nullptr;
+        return PUP_OK;
+      }
       r->band_stride = (int)bw_max;
       r->bytes += (int64_t)nb * bw_max * 8 + 4;
       const int grid = std::min((ns + 7) / 8, 148 * 8);
