@@ -292,6 +292,42 @@ def generate_genome(args, sizes, dev, keep_device, keep_host, pin):
     return dev_data, host_data
 
 
+def ensure_fast_pinned(host_data, dev, threshold_gbs=45.0, rounds=3):
+    """Pinned host buffers whose plain H2D copy runs well below the link rate (seen intermittently on the VM hosts of
+    this pool: a whole process at ~33 GB/s instead of ~55) are re-allocated: the old block stays allocated until the
+    end so that the allocator hands out different memory.  Returns (arrays re-pinned, arrays still slow, slowest
+    rate).  Input staging only -- nothing here is part of a timed region."""
+    import torch
+
+    def rate(t):
+        d = torch.empty_like(t, device=dev)
+        d.copy_(t, non_blocking=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d.copy_(t, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize(dev)
+        return t.numel() * t.element_size() / 1e9 / (a.elapsed_time(b) / 1e3)
+
+    keep, repinned, slow, worst = [], 0, 0, float("inf")
+    for c, h in host_data.items():
+        for k, t in list(h.items()):
+            if not hasattr(t, "is_pinned") or not t.is_pinned() or t.numel() * t.element_size() < (32 << 20):
+                continue
+            r = rate(t)
+            for _ in range(rounds):
+                if r >= threshold_gbs:
+                    break
+                keep.append(t)
+                t = torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
+                h[k] = t
+                repinned += 1
+                r = rate(t)
+            slow += int(r < threshold_gbs)
+            worst = min(worst, r)
+    return repinned, slow, (None if worst == float("inf") else worst), keep
+
+
 def expected_table(host_or_dev):
     import pandas as pd
 
@@ -388,6 +424,10 @@ def main():
     dev_data, host_data = generate_genome(args, sizes, dev, keep_device=set(names), keep_host=set(names) if want_host else set(),
                                           pin=world == 1)
     expected_df = expected_table(dev_data) if wl["expected"] else None
+    pin_report, _pin_keep = None, None
+    if world == 1 and want_host and os.environ.get("PUP_BENCH_REPIN", "1") != "0":
+        n_re, n_slow, worst, _pin_keep = ensure_fast_pinned(host_data, dev)
+        pin_report = {"arrays_repinned": n_re, "arrays_still_slow": n_slow, "slowest_pinned_h2d_gbs": worst}
     t_host0 = time.perf_counter()
     nnz_by_chrom = {c: int(dev_data[c]["upper_col"].shape[0]) for c in names}
     windows, n_slots, flags, pu_plan = build_windows(args, sizes, features, expected_df, nnz_by_chrom)
@@ -598,7 +638,7 @@ def main():
             dist.all_reduce(bts)
         e2e = {"value": n_valid_total / (float(ems.item()) / 1e3), "unit": "pile-ups/s", "ms_per_step": float(ems.item()),
                "h2d_bytes_per_step": int(bts[0].item()), "d2h_bytes_per_step": int(bts[1].item()),
-               "steps": args.e2e_steps, "h2d_probe_gbs": h2d_probe,
+               "steps": args.e2e_steps, "h2d_probe_gbs": h2d_probe, "pinned_input_check": pin_report,
                "step_wall_ms_min_max": [min(step_wall), max(step_wall)],
                "what": "coolpuppy_b200.pipeline.RegionPipeline (the product's own region loop) with pinned HOST buffers: per "
                        "chromosome pup_region_create_upper(cooler-style upper-triangle pixels, weights[, expected]) + pup_upload"
