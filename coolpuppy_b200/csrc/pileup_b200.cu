@@ -1170,11 +1170,18 @@ __global__ void __launch_bounds__(256) k_band_hist(const Pix* __restrict__ pix, 
 }
 
 // bw = end of the last block of diagonals (from the diagonal outwards) whose occupancy is still >= pct percent
-__global__ void k_band_choose(const int* __restrict__ hist, int nb, int hs, int bw_max, int pct, int32_t* __restrict__ bw_out) {
+__global__ void k_band_choose(const int* __restrict__ hist, int nb, int hs, int bw_max, int pct, int ignore_diags,
+                              int32_t* __restrict__ bw_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int bw = 0;
   for (int b = 0; (b << hs) < nb && b < BAND_HB; ++b) {
-    const long long d0 = (long long)b << hs, d1 = min((long long)nb, d0 + (1ll << hs));
+    long long d0 = (long long)b << hs;
+    const long long d1 = min((long long)nb, d0 + (1ll << hs));
+    d0 = max(d0, (long long)ignore_diags);  // the masked diagonals hold nothing by construction: not counted
+    if (d0 >= d1) {
+      bw = (int)d1;
+      continue;
+    }
     const long long cells = (d1 - d0) * nb - (d0 + d1 - 1) * (d1 - d0) / 2;  // positions (row, row + d), d in [d0, d1)
     if ((long long)hist[b] * 100 < cells * pct) break;
     bw = (int)d1;
@@ -2234,7 +2241,8 @@ int finish_region(pup_region* r, const int32_t* rs, const int32_t* re, const int
       const int grid = std::min((ns + 7) / 8, 148 * 8);
       k_band_hist<<<grid, 256, 0, st>>>(r->pix, r->prow, ns, r->lr, hs, hist);
       LAUNCH_CHECK("k_band_hist");
-      k_band_choose<<<1, 32, 0, st>>>(hist, nb, hs, (int)bw_max, std::max(1, env_int("PUP_BAND_DENSITY_PCT", 20)), r->band_bw);
+      k_band_choose<<<1, 32, 0, st>>>(hist, nb, hs, (int)bw_max, std::max(1, env_int("PUP_BAND_DENSITY_PCT", 20)),
+                                    std::max(0, r->ignore_diags), r->band_bw);
       LAUNCH_CHECK("k_band_choose");
       k_band_zero<<<148 * 8, 256, 0, st>>>(reinterpret_cast<double2*>(r->band), nb, r->band_stride, r->band_bw);
       LAUNCH_CHECK("k_band_zero");
