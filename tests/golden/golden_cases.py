@@ -122,6 +122,18 @@ CASES = {
                              "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 0.3,
                                         "rescale_size": 7, "clr_weight_name": None, "coverage_norm": True, "nshifts": 2, "seed": 3}},
     "toy_rescale_up": {**TOY, "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 1, "rescale_size": 15}},
+    "toy_rescale_bedpe_ctrl": {**TOY, "features": "toy_sized.bedpe", "features_schema": "bedpe6",
+                               "kwargs": {"features_format": "bedpe", "mindist": 0, "rescale": True, "rescale_flank": 0.5,
+                                          "rescale_size": 9, "nshifts": 2, "seed": 4}},
+    "toy_rescale_bywindow": {**TOY, "features": "toy_sized_features.bed",
+                             "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 1,
+                                        "rescale_size": 9, "by_window": True}},
+    "toy_rescale_flip_dist": {**TOY, "features": "toy_sized_features.bed", "expected": "CN.mm9.toy_expected.tsv",
+                              "kwargs": {"features_format": "bed", "mindist": 0, "rescale": True, "rescale_flank": 0.5,
+                                         "rescale_size": 11, "by_strand": True, "flip_negative_strand": True, "ooe": True}},
+    "scc1_tads_rescale_ctrl": {**SCC1, "features": "CH12_TADs_Rao.bed", "features_schema": "bed3",
+                               "kwargs": dict(features_format="bed", clr_weight_name=None, local=True, rescale=True, rescale_flank=1,
+                                              rescale_size=33, subset=150, seed=2, nshifts=3)},
     "scc1_tads_rescale_local": {**SCC1, "features": "CH12_TADs_Rao.bed", "features_schema": "bed3",
                                 "kwargs": dict(features_format="bed", clr_weight_name=None, local=True, rescale=True, rescale_flank=1,
                                                rescale_size=99, subset=400, seed=1)},

@@ -460,6 +460,36 @@ def test_legacy_loop_ref_statistically(fixtures_dir):
     assert np.median(np.abs(mine - ref) / ref) < 0.06
 
 
+def test_legacy_tad_ref_statistically(fixtures_dir):
+    """tests/tad_ref.np.txt: the legacy (pre-1.0 CLI) golden of a local, rescaled TAD pile-up -- rescale_pad 1, rescale_size
+    99, nshifts 10, seed 0, coverage_norm, unbalanced (header of the file).  Like loop_ref it is a Monte-Carlo output of
+    another random generator, and the legacy code did not mask the first diagonals (it has no NaN cells; the current
+    reference, and this path, leave the cells the masked diagonals touch NaN), so it is compared statistically on the
+    cells both have: a flat matrix around 1 -- median relative difference 4 %, Pearson 0.77."""
+    _cuda()
+    import os
+
+    import pandas as pd
+
+    from coolpuppy_b200 import coolpup as cp
+    from coolpuppy_b200.coolio import Cooler
+
+    clr = Cooler(os.path.join(fixtures_dir, "Scc1-control.10000.cool"))
+    tads = pd.read_csv(os.path.join(fixtures_dir, "CH12_TADs_Rao.bed"), sep="\t", header=None).iloc[:, :3]
+    tads.columns = ["chrom", "start", "end"]
+    ref = np.loadtxt(os.path.join(fixtures_dir, "tad_ref.np.txt"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pups = cp.pileup(clr, tads, features_format="bed", local=True, rescale=True, rescale_flank=1.0, rescale_size=99,
+                         clr_weight_name=None, nshifts=10, seed=0, coverage_norm=True)
+    mine = np.asarray(pups["data"].iloc[0], dtype=float)
+    assert mine.shape == ref.shape == (99, 99)
+    m = np.isfinite(mine) & np.isfinite(ref)
+    assert m.sum() > 0.95 * m.size
+    assert np.corrcoef(mine[m], ref[m])[0, 1] > 0.6
+    assert np.median(np.abs(mine[m] - ref[m]) / np.abs(ref[m])) < 0.08
+
+
 @pytest.mark.parametrize("mode", ["raw", "balanced", "balanced_ooe", "balanced_expblocks", "raw_coverage", "raw_local"])
 @pytest.mark.parametrize("nb,rs,hmax,nwin,n_slots", [(300, 9, 40, 300, 3), (500, 11, 8, 400, 2), (900, 99, 260, 60, 2),
                                                       (400, 7, 90, 200, 4)])
