@@ -18,7 +18,7 @@ PUP_F_ASYNC = 16
 PUP_F_LOCAL = 32
 
 _LIB = None
-_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200.so")
+_PATH = os.environ.get("PUP_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpileup_b200.so")  # PUP_LIB: tuning builds
 
 SYMBOLS = [
     "pup_abi_version", "pup_last_error", "pup_device_count", "pup_region_create", "pup_region_create_upper",

@@ -1059,6 +1059,9 @@ struct DenseParams {
   double* acc;
 };
 
+#ifndef PUP_DENSE_LD
+#define PUP_DENSE_LD __ldg  // tuning: -DPUP_DENSE_LD=__ldcg / __ldcs / __ldlu
+#endif
 template <int DENSE_T, int DENSE_CPT>
 __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const DenseParams p) {
   __shared__ int s_item;
@@ -1125,9 +1128,9 @@ __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const 
       const unsigned e1 = (unsigned)(rc1.x * p.stride + (rc1.y - rc1.x));
       double v0[DENSE_CPT], v1[DENSE_CPT];
 #pragma unroll
-      for (int k = 0; k < DENSE_CPT; ++k) v0[k] = __ldg(bandp + (e0 + off[k]));
+      for (int k = 0; k < DENSE_CPT; ++k) v0[k] = PUP_DENSE_LD(bandp + (e0 + off[k]));
 #pragma unroll
-      for (int k = 0; k < DENSE_CPT; ++k) v1[k] = __ldg(bandp + (e1 + off[k]));
+      for (int k = 0; k < DENSE_CPT; ++k) v1[k] = PUP_DENSE_LD(bandp + (e1 + off[k]));
 #pragma unroll
       for (int k = 0; k < DENSE_CPT; ++k) {
         a[k] += v0[k];
@@ -1138,7 +1141,7 @@ __global__ void __launch_bounds__(DENSE_T, 1024 / DENSE_T) k_pileup_dense(const 
       const int2 rc0 = __ldg(&p.win[w]);
       const unsigned e0 = (unsigned)(rc0.x * p.stride + (rc0.y - rc0.x));
 #pragma unroll
-      for (int k = 0; k < DENSE_CPT; ++k) a[k] += __ldg(bandp + (e0 + off[k]));
+      for (int k = 0; k < DENSE_CPT; ++k) a[k] += PUP_DENSE_LD(bandp + (e0 + off[k]));
     }
   }
   flush();
