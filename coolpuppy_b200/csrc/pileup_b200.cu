@@ -2023,9 +2023,11 @@ cudaError_t launch_main_t(const MainParams& p, int grid, int threads, size_t sme
 template <int R, int S>
 cudaError_t launch_main_rs(const MainParams& p, int grid, int threads, size_t smem, cudaStream_t st, int* occ) {
   // tuning variants: PUP_TILE_INTERLEAVE=0 stores the tile rows of a strip one after the other instead of interleaved
-  // column by column; PUP_PREFETCH=0 (default geometry only) drops the L2 prefetch
+  // column by column; PUP_PREFETCH=2 (default geometry only) adds an L2 prefetch two steps ahead (it paid while the
+  // kernel still saw the dense windows: long runs; the sparse class left to it has short runs, -0.8 ms without;
+  // wide windows, W >= 128, keep it)
   const int qi = env_int("PUP_TILE_INTERLEAVE", 1);
-  if (R == 2 && S == 8 && env_int("PUP_PREFETCH", 2) == 0) return launch_main_t<R, S, 0, 2, true>(p, grid, threads, smem, st, occ);
+  if (R == 2 && S == 8 && env_int("PUP_PREFETCH", p.W >= 128 ? 2 : 0) == 0) return launch_main_t<R, S, 0, 2, true>(p, grid, threads, smem, st, occ);
   if (qi) return launch_main_t<R, S, 2, 2, true>(p, grid, threads, smem, st, occ);
   return launch_main_t<R, S, 2, 2, false>(p, grid, threads, smem, st, occ);
 }
@@ -2129,7 +2131,7 @@ bool lower_triangle_masked(unsigned flags, int ignore_diags) { return !(flags & 
 int choose_bucket_bits(int32_t nb, int32_t ns, int R, int64_t nnz, int* nbk_out) {
   // bucket width: aim at ~PUP_BUCKET_TARGET stored pixels per (strip, bucket); no table for very sparse rows
   double avg = (double)nnz / nb;  // pixels per row; a strip holds R times as many per column
-  int target = env_int("PUP_BUCKET_TARGET", 4);
+  int target = env_int("PUP_BUCKET_TARGET", 8);
   if (avg <= 24.0) {
     *nbk_out = 1;
     return 31;
@@ -2620,12 +2622,12 @@ int pup_accumulate(const pup_region_t* m, int64_t n_win, const int32_t* r0, cons
 
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, m->device);
-  // windows per work item: 32, fewer when the call is small (at least ~4 items per resident CTA, so that a launch of
+  // windows per work item: 64, fewer when the call is small (at least ~4 items per resident CTA, so that a launch of
   // a few thousand dense windows -- BASELINE configs[2] -- still keeps every SM busy)
-  int ch = std::max(1, env_int("PUP_CHUNK", 32));
+  int ch = std::max(1, env_int("PUP_CHUNK", 64));
   if (env_int("PUP_CHUNK", 0) == 0) {
     const int64_t per_item = n_win / (int64_t)(n_sm * 2 * 4);
-    ch = (int)std::max<int64_t>(4, std::min<int64_t>(32, per_item));
+    ch = (int)std::max<int64_t>(4, std::min<int64_t>(64, per_item));
   }
   uint64_t *keys_a, *keys_b;
   int32_t *slot_start, *nchunks, *chunk_start;
