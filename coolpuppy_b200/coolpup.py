@@ -1111,7 +1111,30 @@ class PileUpper:
         nk = 2 if bool(self.control) else 1
         nf = 2 if plan["flip"] else 1
         nctrl = self.CC.nshifts if do_control else 0
-        chrom_v, start_v, end_v = df["chrom"].values, df["start"].values, df["end"].values
+        # per-feature columns as plain numpy arrays, made once: a region's item then costs a few fancy-index takes instead
+        # of a boolean-mask copy of the whole feature frame (the items are made while the GPU works on earlier regions)
+        start_v, end_v = df["start"].values, df["end"].values
+        chrom_codes, chrom_uniques = pd.factorize(df["chrom"])
+        chrom_code = {str(c): i for i, c in enumerate(chrom_uniques)}
+        center_v = np.ascontiguousarray(df["center"].values, dtype=np.float64)
+        stbin_v = np.asarray(df["stBin"].values)
+        region_rows = {name: (str(r["chrom"]), r["start"], r["end"]) for name, r in self.view_df.iterrows()}
+        col_cache = {}
+
+        def column(name):
+            if name not in col_cache:
+                col_cache[name] = df[name].to_numpy()
+            return col_cache[name]
+
+        def group_codes(g, source, idx):
+            """Codes of group column ``g`` (values of feature column ``source``) for the features ``idx``: static
+            dictionaries are applied to the whole column once."""
+            if table.is_dynamic(g):
+                return table.codes(g, column(source)[idx])
+            key = ("codes", g)
+            if key not in col_cache:
+                col_cache[key] = np.asarray(table.codes(g, column(source)), dtype=np.int64)
+            return col_cache[key][idx]
 
         def items():
             """One item per view region, made while the GPU works on the previous ones."""
@@ -1119,29 +1142,28 @@ class PileUpper:
                 yield make_item(ri, name)
 
         def make_item(ri, name):
-            r = self.view_df.loc[name]
-            m_ = (chrom_v == r["chrom"]) & (start_v >= r["start"]) & (end_v < r["end"])
-            sel = df[m_]
-            center = np.ascontiguousarray(sel["center"].values, dtype=np.float64)
+            chrom, r_start, r_end = region_rows[name]
+            idx = np.flatnonzero((chrom_codes == chrom_code.get(chrom, -1)) & (start_v >= r_start) & (end_v < r_end))
+            center = center_v[idx]
             q, total = _native.pair_windows_count(center, self.CC.mindist, self.CC.maxdist)
             it = dict(index=ri, name=name, total=total, nctrl=nctrl, segs=(q[q > 0] * nctrl) if nctrl else np.zeros(0, np.int64),
                       owned=name in my_units and total > 0)
             if it["owned"]:
                 lo_rel, hi_rel = self.view_df_extents[name]
                 it.update(nb=hi_rel - lo_rel, ranges=my_units[name] or [(0, len(center))], center=center, per_offset=q,
-                          stbin=np.ascontiguousarray(sel["stBin"].values - lo_rel, dtype=np.int32),
+                          stbin=np.ascontiguousarray(stbin_v[idx] - lo_rel, dtype=np.int32),
                           key1=None, key2=None, flipval=None, ident=None, band_weight=0)
                 if plan["by_window"]:
-                    mi = pd.MultiIndex.from_arrays([sel["chrom"].values, sel["start"].values, sel["end"].values])
+                    mi = pd.MultiIndex.from_arrays([column("chrom")[idx], start_v[idx], end_v[idx]])
                     it["ident"] = np.ascontiguousarray(self._ident_index.reindex(mi).values, dtype=np.int32)
                 else:
-                    k1 = np.zeros(len(sel), dtype=np.int64)
-                    k2 = np.zeros(len(sel), dtype=np.int64)
+                    k1 = np.zeros(len(idx), dtype=np.int64)
+                    k2 = np.zeros(len(idx), dtype=np.int64)
                     for (g, _), wt in zip(colspec, weights):
                         if g == "distance_band" and plan["band_edges"] is not None:
                             it["band_weight"] = wt
                             continue
-                        codes = table.codes(g, sel[g[:-1]].to_numpy())
+                        codes = group_codes(g, g[:-1], idx)
                         if g[-1] == "1":
                             k1 += codes * wt
                         else:
@@ -1149,11 +1171,10 @@ class PileUpper:
                     it["key1"], it["key2"] = k1, k2
                 if plan["flip"]:
                     if self.flip_negative_strand:
-                        it["flipval"] = np.ascontiguousarray(sel["strand"].values == "-", dtype=np.int32)
+                        it["flipval"] = np.ascontiguousarray(column("strand")[idx] == "-", dtype=np.int32)
                     else:
                         fb = plan["flipby"]
-                        table.is_dynamic(fb + "1")
-                        it["flipval"] = np.ascontiguousarray(table.codes(fb + "1", sel[fb].to_numpy()), dtype=np.int32)
+                        it["flipval"] = np.ascontiguousarray(group_codes(fb + "1", fb, idx), dtype=np.int32)
             return it
         flags = 0
         if self.expected is True and self.ooe:
