@@ -287,8 +287,9 @@ def generate_genome(args, sizes, dev, keep_device, keep_host, pin):
             h["nb"] = nb
             host_data[c] = h
         del t
-    torch.cuda.synchronize(dev)
-    torch.cuda.empty_cache()
+    if torch.device(dev).type == "cuda":
+        torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
     return dev_data, host_data
 
 
@@ -296,7 +297,8 @@ def ensure_fast_pinned(host_data, dev, threshold_gbs=45.0, rounds=3):
     """Pinned host buffers whose plain H2D copy runs well below the link rate (seen intermittently on the VM hosts of
     this pool: a whole process at ~33 GB/s instead of ~55) are re-allocated: the old block stays allocated until the
     end so that the allocator hands out different memory.  Returns (arrays re-pinned, arrays still slow, slowest
-    rate).  Input staging only -- nothing here is part of a timed region."""
+    rate, the replaced blocks -- keep them referenced until the run ends).  Input staging only: nothing here is part of
+    a timed region."""
     import torch
 
     def rate(t):
