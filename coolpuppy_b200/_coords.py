@@ -149,6 +149,19 @@ def _draw_shifts(n, minshift, maxshift, resolution):
     return np.round(shift / resolution).astype(np.int64)
 
 
+def _chrom_is(cc, col, chrom):
+    """``cc.intervals[col] == chrom`` through integer codes made once per feature table (a string comparison of the
+    whole column per view region is the host path's largest cost for 1e5+ features)."""
+    df = cc.intervals
+    cache = cc.__dict__.setdefault("_chrom_code_cache", {})
+    key = (col, id(df), len(df))
+    if key not in cache:
+        codes, uniques = pd.factorize(df[col])
+        cache[key] = (np.asarray(codes), {str(u): i for i, u in enumerate(uniques)})
+    codes, lut = cache[key]
+    return codes == lut.get(str(chrom), -2)
+
+
 def build_region_windows(cc, region, control, draw_only=False):
     """Windows of one view region ``(chrom, start, end)`` (reference: coolpup.py:546-563, 598-746).
 
@@ -161,7 +174,7 @@ def build_region_windows(cc, region, control, draw_only=False):
     res = cc.resolution
     if cc.kind == "bedpe":
         m = (
-            (df["chrom1"].values == chrom) & (df["chrom2"].values == chrom)
+            _chrom_is(cc, "chrom1", chrom) & _chrom_is(cc, "chrom2", chrom)
             & (df["start1"].values >= start) & (df["end1"].values < end)
             & (df["start2"].values >= start) & (df["end2"].values < end)
         )
@@ -184,7 +197,7 @@ def build_region_windows(cc, region, control, draw_only=False):
             idx = np.concatenate([idx, cidx])
         return RegionWindows(region, sel, st1, st2, kind, idx, idx, dist, paired=False)
 
-    m = (df["chrom"].values == chrom) & (df["start"].values >= start) & (df["end"].values < end)
+    m = _chrom_is(cc, "chrom", chrom) & (df["start"].values >= start) & (df["end"].values < end)
     sel = df[m].reset_index(drop=True)
     nfeat = len(sel)
     stbin = sel["stBin"].values.astype(np.int64)
